@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ (and the product's Jb/Jf table file) by RUNNING
+THE REFERENCE ITSELF in the build container.
+
+TEST INFRASTRUCTURE.  Run once, here:   python oracle/gen_golden.py
+The reference (/root/reference, pure Python) is imported from a writable scratch copy because its
+finiteT module writes two cache files next to itself on first import (finiteT.py:153-163,183-193).
+It does not travel to the GPU box, so everything the tests need is frozen into small files:
+
+  cosmotransitions_b200/data/finiteT_tables.npz  the 2x1000 exact-integral samples (xb,yb,xf,yf)
+                                                 and scipy's splrep knots/coefficients (tb,cb,tf,cf)
+  tests/golden/jspline.npz      Jb_spline / Jf_spline (finiteT.py:167-204), deriv 0..3
+  tests/golden/quartic.json     SingleFieldInstanton findProfile/findAction on quartic potentials
+  tests/golden/profiles.npz     full R/Phi/dPhi profiles for three cases
+  tests/golden/units.npz        exactSolution / rkqs unit vectors
+  tests/golden/model1.npz       generic_potential.Vtot for examples/testModel1.py + finite-T bounces
+  tests/golden/model1f.json     one-field thermal model sweep
+  tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
+"""
+import json
+import os
+import shutil
+import sys
+import tempfile
+import types
+import warnings
+
+import numpy as np
+import scipy
+
+warnings.filterwarnings("ignore")
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("CTB_REFERENCE", "/root/reference")
+GOLD = os.path.join(REPO, "tests", "golden")
+DATA = os.path.join(REPO, "cosmotransitions_b200", "data")
+
+
+def import_reference():
+    tmp = tempfile.mkdtemp(prefix="ctref_")
+    shutil.copytree(os.path.join(REF, "cosmoTransitions"), os.path.join(tmp, "cosmoTransitions"))
+    shutil.copytree(os.path.join(REF, "examples"), os.path.join(tmp, "examples"))
+    sys.path.insert(0, tmp)
+    sys.path.insert(0, os.path.join(tmp, "examples"))
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+    import cosmoTransitions.tunneling1D as t1
+    import cosmoTransitions.helper_functions as hf
+    import cosmoTransitions.finiteT as fT
+    import cosmoTransitions.generic_potential as gp
+    return t1, hf, fT, gp
+
+
+t1, hf, fT, gp = import_reference()
+
+# ---- instrumentation -------------------------------------------------------------------------
+_counts = {"rkck": 0, "exact": 0}
+_orig_rkck = hf._rkck
+
+
+def _rkck_counted(*a, **k):
+    _counts["rkck"] += 1
+    return _orig_rkck(*a, **k)
+
+
+hf._rkck = _rkck_counted
+
+
+class SFI(t1.SingleFieldInstanton):
+    def __init__(self, *a, **k):
+        self.shots = []
+        super().__init__(*a, **k)
+
+    def exactSolution(self, *a):
+        _counts["exact"] += 1
+        return super().exactSolution(*a)
+
+    def integrateProfile(self, r0, y0, *a):
+        rv = super().integrateProfile(r0, y0, *a)
+        self.shots.append([float(r0), float(y0[0]), float(y0[1]), float(rv.r), float(rv.y[0]), float(rv.y[1]),
+                           {"converged": 0, "undershoot": 1, "overshoot": 2}[rv.convergence_type]])
+        return rv
+
+
+def run_case(V, dV, d2V, phi_abs, phi_meta, alpha, init_kw=None, prof_kw=None, keep_profile=False):
+    _counts["rkck"] = _counts["exact"] = 0
+    out = {}
+    try:
+        o = SFI(phi_abs, phi_meta, V, dV, d2V, alpha=alpha, **(init_kw or {}))
+        out.update(phi_bar=float(o.phi_bar), rscale=float(o.rscale))
+        p = o.findProfile(**(prof_kw or {}))
+        S = o.findAction(p)
+        last = o.shots[-1]
+        out.update(S=float(S), phi0=float(p.Phi[0]), R0=float(p.R[0]), r0=last[0], rf=float(p.R[-1]),
+                   npts=int(len(p.R)), n_shots=len(o.shots), shot_types=[s[6] for s in o.shots],
+                   shot_rf=[s[3] for s in o.shots], n_rkck=_counts["rkck"], n_exact=_counts["exact"],
+                   error=None)
+        if keep_profile:
+            out["_profile"] = p
+    except t1.PotentialError as e:
+        out["error"] = "PotentialError:" + e.args[1]
+    except hf.IntegrationError as e:
+        out["error"] = "IntegrationError:" + str(e.args[0])
+    except ValueError as e:
+        out["error"] = "ValueError:" + str(e)[:40]
+    except AssertionError as e:
+        out["error"] = "AssertionError"
+    return out
+
+
+def poly_funcs(coef_low_to_high):
+    c = np.asarray(coef_low_to_high, dtype=float)
+    p = c[::-1]
+    dp = np.polyder(p)
+    d2p = np.polyder(dp)
+    return (lambda x: np.polyval(p, x)), (lambda x: np.polyval(dp, x)), (lambda x: np.polyval(d2p, x))
+
+
+# ---- 1. tables ------------------------------------------------------------------------------
+def gen_tables():
+    os.makedirs(DATA, exist_ok=True)
+    tb, cb, kb = fT._tckb
+    tf, cf, kf = fT._tckf
+    assert kb == 3 and kf == 3
+    np.savez(os.path.join(DATA, "finiteT_tables.npz"), xb=fT._xb, yb=fT._yb, xf=fT._xf, yf=fT._yf, tb=tb, cb=cb,
+             tf=tf, cf=cf, xbmin=fT._xbmin, xbmax=fT._xbmax, xfmin=fT._xfmin, xfmax=fT._xfmax)
+
+
+def gen_jspline():
+    rng = np.random.default_rng(7)
+    th = np.concatenate([
+        rng.uniform(-10, 2000, 600), rng.uniform(-7, 7, 500), rng.normal(0, 1e-3, 50), 10 ** rng.uniform(-8, 3, 300),
+        fT._xb[::37], fT._xf[::41], fT._xb[[0, 1, 2, 3, -4, -3, -2, -1]], fT._xf[[0, 1, 2, 3, -4, -3, -2, -1]],
+        np.array([fT._xbmin, fT._xbmax, fT._xfmin, fT._xfmax, 0.0, -0.0, 1410.0, 1350.0, 1409.9999, 1410.0001,
+                  np.nextafter(fT._xbmin, -np.inf), np.nextafter(fT._xbmin, np.inf), -4.84123428, -4.85, -8.868, -9,
+                  1e-300, -1e-300, 5e3, 1e6, -1e6]),
+    ])
+    out = {"theta": th}
+    for n in range(4):
+        out["Jb%d" % n] = fT.Jb_spline(th, n)
+        out["Jf%d" % n] = fT.Jf_spline(th, n)
+    np.savez(os.path.join(GOLD, "jspline.npz"), **out)
+
+
+# ---- 2. quartic bounces --------------------------------------------------------------------
+def quartic_lambdas(c):
+    V = lambda p: 0.25 * p ** 4 - (1 + c) / 3 * p ** 3 + c / 2 * p ** 2
+    dV = lambda p: p * (p - c) * (p - 1)
+    d2V = lambda p: 3 * p * p - 2 * (1 + c) * p + c
+    return V, dV, d2V
+
+
+def gen_quartic():
+    cases = []
+    cs = list(np.round(0.02 + 0.475 * (np.arange(40) + 0.5) / 40, 12)) + [0.01, 0.2, 0.47, 0.4975, 0.498, 0.499]
+    for alpha in (2, 3):
+        for c in cs:
+            V, dV, d2V = quartic_lambdas(c)
+            r = run_case(V, dV, d2V, 1.0, 0.0, alpha)
+            r.update(kind="family", c=float(c), alpha=alpha, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0,
+                     phi_meta=0.0, opts={})
+            cases.append(r)
+    # non-default knobs
+    knob_sets = [
+        dict(phitol=1e-6, xtol=1e-6), dict(npoints=200), dict(npoints=301, thinCutoff=0.05),
+        dict(max_interior_pts=0), dict(max_interior_pts=40), dict(rmin=1e-3), dict(xguess=3.0),
+        dict(phitol=1e-5, xtol=1e-5, npoints=1000),
+    ]
+    for alpha in (2, 3):
+        for c in (0.1, 0.3, 0.45, 0.49):
+            for kw in knob_sets:
+                V, dV, d2V = quartic_lambdas(c)
+                r = run_case(V, dV, d2V, 1.0, 0.0, alpha, prof_kw=kw)
+                r.update(kind="knobs", c=float(c), alpha=alpha, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0,
+                         phi_meta=0.0, opts=kw)
+                cases.append(r)
+    # phi_eps knob (enters dV_from_absMin)
+    for c in (0.2, 0.47):
+        V, dV, d2V = quartic_lambdas(c)
+        r = run_case(V, dV, d2V, 1.0, 0.0, 2, init_kw=dict(phi_eps=1e-2))
+        r.update(kind="knobs", c=float(c), alpha=2, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0, phi_meta=0.0,
+                 opts=dict(phi_eps=1e-2))
+        cases.append(r)
+    # shifted / scaled / mirrored quartics, driven through np.polyval so that V, dV, d2V come from
+    # the same coefficient vector the device functor receives
+    rng = np.random.default_rng(11)
+    for k in range(16):
+        c = float(rng.uniform(0.05, 0.49))
+        pm, pa = float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5))
+        if abs(pm - pa) < 0.3:
+            pa = pm + 1.7
+        lam = float(10 ** rng.uniform(-2, 2))
+        # V(phi) = lam * q(u), u = (phi - pm)/(pa - pm), q(u) = u^4/4 - (1+c)/3 u^3 + c/2 u^2
+        u = np.poly1d([1.0 / (pa - pm), -pm / (pa - pm)])
+        q = 0.25 * u ** 4 - (1 + c) / 3 * u ** 3 + c / 2 * u ** 2
+        coef = (lam * q).coeffs[::-1]
+        coef = np.concatenate([coef, np.zeros(5 - len(coef))])
+        V, dV, d2V = poly_funcs(coef)
+        alpha = 2 + (k % 2)
+        r = run_case(V, dV, d2V, pa, pm, alpha)
+        r.update(kind="affine", c=c, alpha=alpha, coef=[float(x) for x in coef], phi_abs=pa, phi_meta=pm, opts={})
+        cases.append(r)
+    # error kinds
+    for name, coef, pa, pm in [
+        ("stable", [0, 0, 0.1, -0.4, 0.25], 0.0, 1.0),       # minima swapped
+        ("nobarrier", [0, 0, -0.1, -0.8 / 3, 0.25], 1.0, 0.0),  # c = -0.2: phi=0 is a maximum
+        ("nobarrier2", [0, -0.05, 0.1, -0.4, 0.25], 1.0, 0.0),  # tilted
+    ]:
+        V, dV, d2V = poly_funcs(coef)
+        r = run_case(V, dV, d2V, pa, pm, 2)
+        r.update(kind="error", name=name, alpha=2, coef=[float(x) for x in coef], phi_abs=pa, phi_meta=pm, opts={})
+        cases.append(r)
+    with open(os.path.join(GOLD, "quartic.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+    return cases
+
+
+def gen_profiles():
+    out = {}
+    for name, c, alpha in [("thin2", 0.47, 2), ("thick2", 0.2, 2), ("mid3", 0.35, 3)]:
+        V, dV, d2V = quartic_lambdas(c)
+        # the docstring examples pass only V and dV; d2V then falls back to the FD stencil, but it
+        # only enters through phi0-dependent start data, so pass the analytic one like the batch does
+        r = run_case(V, dV, d2V, 1.0, 0.0, alpha, keep_profile=True)
+        p = r["_profile"]
+        out[name + "_R"], out[name + "_Phi"], out[name + "_dPhi"] = p.R, p.Phi, p.dPhi
+        out[name + "_S"] = r["S"]
+        out[name + "_c"] = c
+        out[name + "_alpha"] = alpha
+    # docstring form: V and dV only (d2V by finite differences, tunneling1D.py:112-122)
+    for name, c in [("doc_thin", 0.47), ("doc_thick", 0.2)]:
+        V, dV, _ = quartic_lambdas(c)
+        o = t1.SingleFieldInstanton(1.0, 0.0, V, dV)
+        p = o.findProfile()
+        out[name + "_S"] = o.findAction(p)
+    np.savez(os.path.join(GOLD, "profiles.npz"), **out)
+
+
+# ---- 3. unit vectors ------------------------------------------------------------------------
+def gen_units():
+    rng = np.random.default_rng(3)
+    out = {}
+    rows, vals = [], []
+    for alpha in (2, 3):
+        o = t1.SingleFieldInstanton(1.0, 0.0, *quartic_lambdas(0.3), alpha=alpha)
+        for k in range(400):
+            r = 10 ** rng.uniform(-5, 3)
+            phi0 = rng.uniform(-2, 2)
+            dV = rng.normal() * 10 ** rng.uniform(-20, 1)
+            d2V = rng.normal() * 10 ** rng.uniform(-3, 1)
+            with np.errstate(all="ignore"):
+                ph, dph = o.exactSolution(r, phi0, dV, d2V)
+            rows.append([alpha, r, phi0, dV, d2V])
+            vals.append([ph, dph])
+    out["exact_in"], out["exact_out"] = np.array(rows), np.array(vals)
+    # rkqs on the quartic EOM
+    rows, vals = [], []
+    for alpha in (2, 3):
+        for k in range(200):
+            c = rng.uniform(0.05, 0.49)
+            V, dV, d2V = quartic_lambdas(c)
+            o = t1.SingleFieldInstanton(1.0, 0.0, V, dV, d2V, alpha=alpha)
+            y = np.array([rng.uniform(-0.1, 1.1), rng.normal() * 0.3])
+            t = 10 ** rng.uniform(-3, 2)
+            dt = 10 ** rng.uniform(-4, 1)
+            epsfrac = np.array([1e-4, 1e-4])
+            epsabs = np.array([1e-4, 1e-4 / rng.uniform(0.5, 5)])
+            f = lambda y_, r_: o.equationOfMotion(y_, r_)
+            dy, dtu, dtn = hf.rkqs(y, f(y, t), t, f, dt, epsfrac, epsabs)
+            rows.append([alpha, c, y[0], y[1], t, dt, epsabs[0], epsabs[1]])
+            vals.append([dy[0], dy[1], dtu, dtn])
+    out["rkqs_in"], out["rkqs_out"] = np.array(rows), np.array(vals)
+    np.savez(os.path.join(GOLD, "units.npz"), **out)
+
+
+# ---- 4. model1 (examples/testModel1.py) ----------------------------------------------------
+def gen_model1():
+    from scipy import optimize
+    import testModel1
+    m = testModel1.model1()
+    v2 = testModel1.v2
+    params = dict(l1=m.l1, l2=m.l2, mu2=m.mu2, Y1=m.Y1, Y2=m.Y2, n=float(m.n), renorm=m.renormScaleSq, v2=v2)
+    x_low = np.array([286.39824989, 382.19727238])
+    x_high = np.array([231.10296383, -136.82260069])
+    L = np.linalg.norm(x_high - x_low)
+    nhat = (x_high - x_low) / L
+    s = np.linspace(-0.2 * L, 1.2 * L, 96)
+    T = np.concatenate([np.linspace(1, 250, 40), [0.0, 1e-3, 84.2381996653]])
+    X = x_low[None, :] + s[:, None] * nhat[None, :]
+    # (the reference's in-place `y +=` needs X already broadcast to the full grid shape)
+    Vg = m.Vtot(np.broadcast_to(X[:, None, :], (len(s), len(T), 2)), T[None, :])
+    out = dict(grid_s=s, grid_T=T, grid_V=Vg, grid_x0=x_low, grid_nhat=nhat, **{"p_" + k: v for k, v in params.items()})
+    # scattered 2-D points
+    rng = np.random.default_rng(5)
+    Xs = rng.uniform(-400, 400, (300, 2))
+    Ts = rng.uniform(0, 300, 300)
+    out["pts_X"], out["pts_T"], out["pts_V"] = Xs, Ts, m.Vtot(Xs, Ts)
+    # finite-T bounces along the straight line between the two phases' minima at each T
+    bT, bxl, bxh, res = [], [], [], []
+    xl, xh = x_low.copy(), x_high.copy()
+    for Tb in [84.2381996653, 78.0, 80.0, 90.0, 95.0, 100.0, 105.0]:
+        xl = optimize.fmin(m.Vtot, xl if Tb >= 84 else x_low, args=(Tb,), xtol=1e-8, ftol=1e-12, disp=0)
+        xh = optimize.fmin(m.Vtot, xh if Tb >= 84 else x_high, args=(Tb,), xtol=1e-8, ftol=1e-12, disp=0)
+        Lb = np.linalg.norm(xh - xl)
+        nb = (xh - xl) / Lb
+        Vline = lambda phi, xl=xl, nb=nb, Tb=Tb: m.Vtot(xl + np.asarray(phi)[..., None] * nb, Tb)
+        r = run_case(Vline, None, None, 0.0, Lb, 2)
+        r.update(T=Tb, L=Lb)
+        bT.append(Tb); bxl.append(xl.copy()); bxh.append(xh.copy()); res.append(r)
+        print("model1 bounce T=%g L=%g" % (Tb, Lb), {k: r.get(k) for k in ("S", "npts", "n_shots", "n_rkck", "error")})
+    out["b_T"], out["b_xlow"], out["b_xhigh"] = np.array(bT), np.array(bxl), np.array(bxh)
+    out["b_json"] = json.dumps(res)
+    np.savez(os.path.join(GOLD, "model1.npz"), **out)
+
+
+class Model1F(gp.generic_potential):
+    """One-field model1-style thermal potential, written against the real
+    generic_potential so that Vtot / V1 / V1T / Jb_spline are the reference's own code."""
+
+    def init(self, lam=0.12, Y=0.35, n=30., v2=246. ** 2):
+        self.Ndim = 1
+        self.renormScaleSq = v2
+        self.lam, self.Y, self.n, self.v2 = lam, Y, n, v2
+
+    def V0(self, X):
+        phi = np.asanyarray(X)[..., 0]
+        return .25 * self.lam * (phi * phi - self.v2) ** 2
+
+    def boson_massSq(self, X, T):
+        phi = np.asanyarray(X)[..., 0]
+        T = np.asanyarray(T, dtype=float)
+        M = np.array([self.lam * (3 * phi * phi - self.v2) + 0 * T, self.Y * phi * phi + 0 * T])
+        M = np.rollaxis(M, 0, len(M.shape))
+        return M, np.array([1., self.n]), np.array([1.5, 1.5])
+
+
+def gen_model1f():
+    from scipy import optimize
+    rng = np.random.default_rng(20260101)
+    cases = []
+    for k in range(6):
+        lam, Y, n = (0.12, 0.35, 30.) if k == 0 else (0.12 * rng.uniform(.8, 1.2), 0.35 * rng.uniform(.8, 1.2),
+                                                      30. * rng.uniform(.8, 1.2))
+        m = Model1F(lam=lam, Y=Y, n=n)
+        V = lambda phi, T: m.Vtot(np.asarray(phi, dtype=float)[..., None], T)
+        # T0: phi=0 turns into a local minimum; Tc: degenerate with the broken minimum
+        def curv0(T):
+            h = 0.5
+            return float(V(h, T) - V(0.0, T))
+        T0 = optimize.brentq(curv0, 20, 300)
+        def gap(T):
+            pa = optimize.minimize_scalar(lambda p: float(V(p, T)), bounds=(50, 500), method="bounded",
+                                          options=dict(xatol=1e-10)).x
+            return float(V(pa, T) - V(0.0, T))
+        Tc = optimize.brentq(gap, T0 + 0.5, 300)
+        for frac in (0.15, 0.4, 0.65, 0.85, 0.95):
+            T = T0 + frac * (Tc - T0)
+            pa = float(optimize.minimize_scalar(lambda p: float(V(p, T)), bounds=(50, 500), method="bounded",
+                                                options=dict(xatol=1e-10)).x)
+            Vl = lambda phi, T=T: V(phi, T)
+            r = run_case(Vl, None, None, pa, 0.0, 2)
+            r.update(lam=lam, Y=Y, n=n, v2=246. ** 2, T=float(T), phi_abs=pa, phi_meta=0.0, T0=float(T0), Tc=float(Tc),
+                     Vsamples=[float(V(x, T)) for x in (0.0, 0.3 * pa, 0.7 * pa, pa, 1.1 * pa)])
+            cases.append(r)
+            print("model1f", k, "T=%.3f" % T, {q: r.get(q) for q in ("S", "npts", "n_shots", "n_rkck", "error")})
+    with open(os.path.join(GOLD, "model1f.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["tables", "jspline", "quartic", "profiles", "units", "model1", "model1f"]
+    for w in which:
+        print("generating", w)
+        globals()["gen_" + w]()
+    with open(os.path.join(GOLD, "VERSIONS.json"), "w") as f:
+        json.dump(dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0],
+                       reference="clwainwright/CosmoTransitions setup.py version 2.0.7"), f)

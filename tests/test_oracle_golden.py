@@ -1,0 +1,169 @@
+"""Pins the CPU oracle (oracle/ctb_oracle.c) against outputs of the reference itself, frozen by
+oracle/gen_golden.py (tests/golden/*).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+S_RTOL = 1e-9      # required by BASELINE.json: 1e-6; the restatement is trajectory-faithful
+ERR2STATUS = {"PotentialError:stable, not metastable": 2, "PotentialError:no barrier": 3,
+              "IntegrationError:r > rmax": 4, "IntegrationError:dr < drmin": 5,
+              "IntegrationError:Stepsize rounds down to zero.": 6}
+
+
+def _status_for(err):
+    if err in ERR2STATUS:
+        return ERR2STATUS[err]
+    if err.startswith("ValueError:The function value"):
+        return 7
+    if err.startswith("ValueError"):
+        return 8
+    if err.startswith("AssertionError"):
+        return 9
+    raise KeyError(err)
+
+
+def _cfg(oracle, case, **kw):
+    opts = dict(case.get("opts", {}))
+    return oracle.make_config(alpha=case["alpha"], **opts, **kw)
+
+
+def test_quartic_cases(oracle, gold_dir):
+    cases = json.load(open(os.path.join(gold_dir, "quartic.json")))
+    assert len(cases) > 150
+    worst = 0.0
+    for case in cases:
+        cfg = _cfg(oracle, case)
+        r = oracle.bounce_one(cfg, case["coef"], case["phi_abs"], case["phi_meta"])
+        if case["error"] is not None:
+            assert r["status"] == _status_for(case["error"]), (case, r["status"])
+            continue
+        assert r["status"] in (0, 1), case
+        rel = abs(r["S"] - case["S"]) / abs(case["S"])
+        worst = max(worst, rel)
+        assert rel < S_RTOL, (case["c"], case["alpha"], case["opts"], rel)
+        assert r["n_points"] == case["npts"]
+        assert r["n_shots"] == case["n_shots"]
+        assert list(r["shot_type"]) == case["shot_types"]
+        assert r["n_rkck"] == case["n_rkck"]
+        # brentq inside initialConditions may take one evaluation more/less when sinh/exp differ
+        # from scipy's iv() in the last ulp
+        assert abs(r["n_exact"] - case["n_exact"]) <= 8
+        # golden "phi0" is profile.Phi[0] (= phi(r=0) unless max_interior_pts=0)
+        assert abs(r["Phi"][0] - case["phi0"]) <= 1e-12 * max(1.0, abs(case["phi0"]))
+        assert abs(r["R"][0] - case["R0"]) <= 1e-9 * abs(case["R0"])
+        # rf is where phi' (or phi - phi_meta) crosses zero in the flat tail: ill-conditioned, so
+        # last-ulp differences in the start data are amplified (bar: solver tolerance 1e-4)
+        assert abs(r["rf"] - case["rf"]) <= 1e-7 * abs(case["rf"])
+        assert abs(r["r0"] - case["r0"]) <= 1e-9 * abs(case["r0"])
+        assert abs(r["phi_bar"] - case["phi_bar"]) <= 1e-12 * max(1.0, abs(case["phi_bar"]))
+        assert abs(r["rscale"] - case["rscale"]) <= 1e-9 * case["rscale"]
+    print("worst S rel err", worst)
+
+
+def test_profiles(oracle, gold_dir):
+    g = np.load(os.path.join(gold_dir, "profiles.npz"))
+    for name in ("thin2", "thick2", "mid3"):
+        cfg = oracle.make_config(alpha=int(g[name + "_alpha"]))
+        r = oracle.bounce_one(cfg, oracle.quartic_params(float(g[name + "_c"]))[0], 1.0, 0.0)
+        assert len(r["R"]) == len(g[name + "_R"])
+        np.testing.assert_allclose(r["R"], g[name + "_R"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(r["Phi"], g[name + "_Phi"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(r["dPhi"], g[name + "_dPhi"], rtol=0, atol=1e-10)
+        assert abs(r["S"] - float(g[name + "_S"])) < S_RTOL * abs(float(g[name + "_S"]))
+    # docstring form (d2V by finite differences in the reference): within the 1e-6 bar
+    for name, c in (("doc_thin", 0.47), ("doc_thick", 0.2)):
+        cfg = oracle.make_config(alpha=2)
+        r = oracle.bounce_one(cfg, oracle.quartic_params(c)[0], 1.0, 0.0)
+        assert abs(r["S"] - float(g[name + "_S"])) < 1e-8 * abs(float(g[name + "_S"]))
+
+
+def test_exact_solution_units(oracle, gold_dir):
+    g = np.load(os.path.join(gold_dir, "units.npz"))
+    bad = 0
+    for row, ref in zip(g["exact_in"], g["exact_out"]):
+        alpha, r, phi0, dV, d2V = row
+        ph, dph = oracle.exact_solution(int(alpha), r, phi0, dV, d2V)
+        for a, b in ((ph, ref[0]), (dph, ref[1])):
+            if np.isnan(b):
+                assert np.isnan(a)
+            elif np.isinf(b):
+                assert a == b
+            else:
+                # the reference's own formula cancels (I_{nu-1} - 2nu/z I_nu - I_{nu+1} ...): compare
+                # against the magnitude of the uncancelled terms
+                scale = max(abs(b), abs(dV / d2V) if d2V != 0 else 0.0, 1e-300)
+                if not abs(a - b) <= 5e-10 * scale + 1e-13 * abs(phi0):
+                    bad += 1
+    assert bad == 0
+
+
+def test_rkqs_units(oracle, gold_dir):
+    g = np.load(os.path.join(gold_dir, "units.npz"))
+    for row, ref in zip(g["rkqs_in"], g["rkqs_out"]):
+        alpha, c, y0, y1, t, dt, ea0, ea1 = row
+        st, out = oracle.rkqs_poly4(oracle.quartic_params(c)[0], int(alpha), [y0, y1], t, dt, [1e-4, 1e-4], [ea0, ea1])
+        assert st == 0
+        np.testing.assert_allclose(out[2:], ref[2:], rtol=1e-9)
+        np.testing.assert_allclose(out[:2], ref[:2], rtol=1e-9, atol=1e-14)
+
+
+def test_jspline(oracle, tables, gold_dir):
+    g = np.load(os.path.join(gold_dir, "jspline.npz"))
+    th = g["theta"]
+    for der in range(4):
+        jb = oracle.jspline(tables.tb, tables.cb, tables.xbmin, tables.xbmax, th, der)
+        jf = oracle.jspline(tables.tf, tables.cf, tables.xfmin, tables.xfmax, th, der)
+        tol = 1e-10 if der < 2 else 1e-9 * max(1.0, np.max(np.abs(g["Jb%d" % der])))
+        np.testing.assert_allclose(jb, g["Jb%d" % der], rtol=0, atol=tol)
+        np.testing.assert_allclose(jf, g["Jf%d" % der], rtol=0, atol=tol)
+
+
+def _model1_params(g, T, x0, nhat):
+    return np.array([g["p_l1"], g["p_l2"], g["p_mu2"], g["p_Y1"], g["p_Y2"], g["p_n"], g["p_renorm"], g["p_v2"], T,
+                     x0[0], x0[1], nhat[0], nhat[1]], dtype=float)
+
+
+def test_model1_vtot(oracle, tables, gold_dir):
+    g = np.load(os.path.join(gold_dir, "model1.npz"))
+    cfg = oracle.make_config(kind=oracle.POT_MODEL1_LINE, tables=tables)
+    p = _model1_params(g, 0.0, g["grid_x0"], g["grid_nhat"])
+    V = oracle.vtot_model1_grid(cfg, p, g["grid_s"], g["grid_T"])
+    ref = g["grid_V"]
+    np.testing.assert_allclose(V, ref, rtol=1e-12, atol=1e-9 * np.max(np.abs(ref)) * 1e-3)
+    # scattered points: a "line" through each point with phi = 0
+    for X, T, v in zip(g["pts_X"][:100], g["pts_T"][:100], g["pts_V"][:100]):
+        p = _model1_params(g, T, X, [1.0, 0.0])
+        out = oracle.potential(cfg, p, np.array([0.0]))[0]
+        assert abs(out - v) <= 1e-12 * abs(v) + 1e-6
+
+
+def test_model1_line_bounces(oracle, tables, gold_dir):
+    g = np.load(os.path.join(gold_dir, "model1.npz"))
+    res = json.loads(str(g["b_json"]))
+    cfg = oracle.make_config(kind=oracle.POT_MODEL1_LINE, tables=tables, alpha=2)
+    for T, xl, xh, ref in zip(g["b_T"], g["b_xlow"], g["b_xhigh"], res):
+        L = np.linalg.norm(xh - xl)
+        nhat = (xh - xl) / L
+        assert abs(L - ref["L"]) < 1e-12 * L
+        r = oracle.bounce_one(cfg, _model1_params(g, T, xl, nhat), 0.0, L)
+        assert ref["error"] is None and r["status"] in (0, 1)
+        assert abs(r["S"] - ref["S"]) < 1e-6 * abs(ref["S"]), (T, r["S"], ref["S"])
+        assert r["n_points"] == ref["npts"]
+        assert r["n_shots"] == ref["n_shots"]
+
+
+def test_model1f_bounces(oracle, tables, gold_dir):
+    cases = json.load(open(os.path.join(gold_dir, "model1f.json")))
+    cfg = oracle.make_config(kind=oracle.POT_MODEL1F, tables=tables, alpha=2)
+    for c in cases:
+        p = np.array([c["lam"], c["v2"], c["Y"], c["n"], c["v2"], c["T"]])
+        pa = c["phi_abs"]
+        V = oracle.potential(cfg, p, np.array([0.0, 0.3 * pa, 0.7 * pa, pa, 1.1 * pa]))
+        np.testing.assert_allclose(V, c["Vsamples"], rtol=1e-12)
+        r = oracle.bounce_one(cfg, p, pa, 0.0)
+        assert c["error"] is None and r["status"] in (0, 1)
+        assert abs(r["S"] - c["S"]) < 1e-6 * abs(c["S"]), (c["T"], r["S"], c["S"])
+        assert r["n_points"] == c["npts"]
+        assert r["n_shots"] == c["n_shots"]
