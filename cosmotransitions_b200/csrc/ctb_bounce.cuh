@@ -1,0 +1,73 @@
+// ctb_bounce.cuh -- the batched bounce kernel (one thread = one instance) and its launchers.
+// Each potential functor is instantiated in its own translation unit (ctb_bounce_<pot>.cu) so that
+// the build can compile them in parallel.
+#pragma once
+#include "ctb_device.cuh"
+
+#ifndef CTB_MAX_BLOCK
+#define CTB_MAX_BLOCK 128
+#endif
+#ifndef CTB_MIN_BLOCKS
+#define CTB_MIN_BLOCKS 1
+#endif
+
+namespace ctb {
+
+struct BounceArgs {
+    const double *params, *phi_abs, *phi_meta;
+    int64_t n;
+    Knobs knobs;
+    JTab jb, jf;
+    ctb_bounce_out out;
+};
+
+// One thread = one instance.  Adjacent instances (adjacent model parameters) share a warp, so that
+// lanes follow similar trajectories; blocks are small so that the hardware block scheduler balances
+// the 4x spread in work per instance across the 148 SMs.
+template <class Pot, int ALPHA>
+__global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(const BounceArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Sfi<Pot, ALPHA> s;
+    s.pot.load(a.params + i * Pot::nparam, &a.jb, &a.jf);
+    s.phi_abs = a.phi_abs[i];
+    s.phi_meta = a.phi_meta[i];
+    InstanceResult r;
+    ProfileSink sink{nullptr, nullptr, nullptr};
+    if (a.out.d_prof_R) {
+        sink.R = a.out.d_prof_R + i * a.out.prof_stride;
+        sink.Phi = a.out.d_prof_Phi + i * a.out.prof_stride;
+        sink.dPhi = a.out.d_prof_dPhi + i * a.out.prof_stride;
+    }
+    solve_instance<Pot, ALPHA>(s, a.knobs, r, sink);
+    if (a.out.d_S) a.out.d_S[i] = r.S;
+    if (a.out.d_phi0) a.out.d_phi0[i] = r.phi0;
+    if (a.out.d_r0) a.out.d_r0[i] = r.r0;
+    if (a.out.d_rf) a.out.d_rf[i] = r.rf;
+    if (a.out.d_x) a.out.d_x[i] = r.x;
+    if (a.out.d_phi_bar) a.out.d_phi_bar[i] = r.phi_bar;
+    if (a.out.d_rscale) a.out.d_rscale[i] = r.rscale;
+    if (a.out.d_status) a.out.d_status[i] = r.status;
+    if (a.out.d_n_shots) a.out.d_n_shots[i] = r.n_shots;
+    if (a.out.d_n_rkck) a.out.d_n_rkck[i] = r.n_rkck;
+    if (a.out.d_n_points) a.out.d_n_points[i] = r.n_points;
+}
+
+
+template <class Pot>
+int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st)
+{
+    if (block < 32 || block > CTB_MAX_BLOCK || (block & 31)) return CTB_ERR_UNSUPPORTED;
+    unsigned grid = (unsigned)((a.n + block - 1) / block);
+    if (alpha == 2) bounce_kernel<Pot, 2><<<grid, block, 0, st>>>(a);
+    else if (alpha == 3) bounce_kernel<Pot, 3><<<grid, block, 0, st>>>(a);
+    else return CTB_ERR_UNSUPPORTED;
+    return (int)cudaGetLastError();
+}
+
+int launch_bounce_poly4(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+int launch_bounce_model1_line(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+int launch_bounce_model1f(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+
+} // namespace ctb

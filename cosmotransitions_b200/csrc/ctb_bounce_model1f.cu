@@ -1,0 +1,9 @@
+// bounce kernel instantiation for the PotModel1F potential functor (see ctb_bounce.cuh)
+#include "ctb_bounce.cuh"
+
+namespace ctb {
+int launch_bounce_model1f(const BounceArgs &a, int alpha, int block, cudaStream_t st)
+{
+    return launch_bounce_any<PotModel1F>(a, alpha, block, st);
+}
+} // namespace ctb

@@ -1,0 +1,9 @@
+// bounce kernel instantiation for the PotPoly4 potential functor (see ctb_bounce.cuh)
+#include "ctb_bounce.cuh"
+
+namespace ctb {
+int launch_bounce_poly4(const BounceArgs &a, int alpha, int block, cudaStream_t st)
+{
+    return launch_bounce_any<PotPoly4>(a, alpha, block, st);
+}
+} // namespace ctb

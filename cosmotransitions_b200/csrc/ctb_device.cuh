@@ -1,0 +1,804 @@
+// ctb_device.cuh -- device-side building blocks of the batched bounce solver (sm_100a, FP64).
+//
+// Behavioural spec: SURVEY.md Appendix A.  Reference locations are cited per function
+// (cosmoTransitions/tunneling1D.py = T1D, helper_functions.py = HF, finiteT.py = FT,
+// generic_potential.py = GP).  One THREAD owns one instance; all state lives in registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/ctbounce.h"
+
+namespace ctb {
+
+#define CTB_DEV __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------
+// Jb / Jf spline tables (piecewise cubic, see ctbounce.h)                      FT:167-174,197-204
+struct JTab {
+    const double *__restrict__ brk;
+    const double *__restrict__ coef;
+    int nint;
+    double xmin, xmax;
+};
+
+CTB_DEV int jtab_locate(const JTab &t, double x)
+{
+    // largest j in [0, nint-1] with brk[j] <= x  (j = 0 below the table: first piece extrapolates)
+    int lo = 0, hi = t.nint - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (x >= __ldg(t.brk + mid)) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int DER>
+CTB_DEV double jtab_eval(const JTab &t, double theta)
+{
+    double x = (theta < t.xmin) ? t.xmin : theta;
+    int j = jtab_locate(t, x);
+    double dx = x - __ldg(t.brk + j);
+    const double2 c01 = __ldg(reinterpret_cast<const double2 *>(t.coef) + 2 * j);
+    const double2 c23 = __ldg(reinterpret_cast<const double2 *>(t.coef) + 2 * j + 1);
+    struct { double x, y, z, w; } c = {c01.x, c01.y, c23.x, c23.y};
+    double v;
+    if (DER == 0) v = c.x + dx * (c.y + dx * (c.z + dx * c.w));
+    else if (DER == 1) v = c.y + dx * (2.0 * c.z + dx * (3.0 * c.w));
+    else if (DER == 2) v = 2.0 * c.z + dx * (6.0 * c.w);
+    else v = 6.0 * c.w;
+    return (theta > t.xmax) ? 0.0 : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// potentials
+#define CTB_PI 3.14159265358979323846
+
+struct PotPoly4 {
+    static constexpr bool analytic = true;
+    static constexpr int nparam = CTB_NPARAM_POLY4;
+    double c0, c1, c2, c3, c4;
+    CTB_DEV void load(const double *p, const JTab *, const JTab *)
+    {
+        c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; c4 = p[4];
+    }
+    // V steers the barrier bisection and fminbound (discrete decisions): keep the reference's
+    // rounding (no FMA contraction).  dV / d2V feed the integrator and may contract.
+    CTB_DEV double V(double x) const
+    {
+        double v = __dadd_rn(c3, __dmul_rn(x, c4));
+        v = __dadd_rn(c2, __dmul_rn(x, v));
+        v = __dadd_rn(c1, __dmul_rn(x, v));
+        return __dadd_rn(c0, __dmul_rn(x, v));
+    }
+    CTB_DEV double dV(double x) const { return c1 + x * (2 * c2 + x * (3 * c3 + x * 4 * c4)); }
+    CTB_DEV double d2V(double x) const { return 2 * c2 + x * (6 * c3 + x * 12 * c4); }
+};
+
+// examples/testModel1.py:62-116 through GP:312-337, on the line X = x0 + phi*nhat
+CTB_DEV double vtot_model1(double l1, double l2, double mu2, double Y1, double Y2, double nb, double rs, double v2,
+                           const JTab &jb, double phi1, double phi2, double T)
+{
+    double a = l1 * (3 * phi1 * phi1 - v2);
+    double b = l2 * (3 * phi2 * phi2 - v2);
+    double A = .5 * (a + b);
+    double B = sqrt(.25 * (a - b) * (a - b) + mu2 * mu2);
+    double mb = Y1 * (phi1 * phi1 + phi2 * phi2) + Y2 * phi1 * phi2;
+    double m0 = A + B, m1 = A - B;
+    double r = .25 * l1 * (phi1 * phi1 - v2) * (phi1 * phi1 - v2) + .25 * l2 * (phi2 * phi2 - v2) * (phi2 * phi2 - v2);
+    r -= mu2 * phi1 * phi2;
+    double y1 = 0.0;
+    y1 += 1.0 * m0 * m0 * (log(fabs(m0 / rs) + 1e-100) - 1.5);
+    y1 += 1.0 * m1 * m1 * (log(fabs(m1 / rs) + 1e-100) - 1.5);
+    y1 += nb * mb * mb * (log(fabs(mb / rs) + 1e-100) - 1.5);
+    r += y1 / (64 * CTB_PI * CTB_PI);
+    double T2 = T * T + 1e-100, T4 = T * T * T * T;
+    double yt = 0.0;
+    yt += 1.0 * jtab_eval<0>(jb, m0 / T2);
+    yt += 1.0 * jtab_eval<0>(jb, m1 / T2);
+    yt += nb * jtab_eval<0>(jb, mb / T2);
+    r += yt * T4 / (2 * CTB_PI * CTB_PI);
+    return r;
+}
+
+struct PotModel1Line {
+    static constexpr bool analytic = false;
+    static constexpr int nparam = CTB_NPARAM_MODEL1_LINE;
+    double l1, l2, mu2, Y1, Y2, nb, rs, v2, T, x0, x1, n0, n1;
+    JTab jb;
+    CTB_DEV void load(const double *p, const JTab *jb_, const JTab *)
+    {
+        l1 = p[0]; l2 = p[1]; mu2 = p[2]; Y1 = p[3]; Y2 = p[4]; nb = p[5]; rs = p[6]; v2 = p[7]; T = p[8];
+        x0 = p[9]; x1 = p[10]; n0 = p[11]; n1 = p[12];
+        jb = *jb_;
+    }
+    CTB_DEV double V(double phi) const
+    {
+        return vtot_model1(l1, l2, mu2, Y1, Y2, nb, rs, v2, jb, x0 + phi * n0, x1 + phi * n1, T);
+    }
+};
+
+struct PotModel1F {
+    static constexpr bool analytic = false;
+    static constexpr int nparam = CTB_NPARAM_MODEL1F;
+    double lam, v2, Y, nb, rs, T;
+    JTab jb;
+    CTB_DEV void load(const double *p, const JTab *jb_, const JTab *)
+    {
+        lam = p[0]; v2 = p[1]; Y = p[2]; nb = p[3]; rs = p[4]; T = p[5];
+        jb = *jb_;
+    }
+    CTB_DEV double V(double phi) const
+    {
+        double m0 = lam * (3 * phi * phi - v2), m1 = Y * phi * phi;
+        double r = .25 * lam * (phi * phi - v2) * (phi * phi - v2);
+        double y1 = 0.0;
+        y1 += 1.0 * m0 * m0 * (log(fabs(m0 / rs) + 1e-100) - 1.5);
+        y1 += nb * m1 * m1 * (log(fabs(m1 / rs) + 1e-100) - 1.5);
+        r += y1 / (64 * CTB_PI * CTB_PI);
+        double T2 = T * T + 1e-100, T4 = T * T * T * T;
+        double yt = 0.0;
+        yt += 1.0 * jtab_eval<0>(jb, m0 / T2);
+        yt += nb * jtab_eval<0>(jb, m1 / T2);
+        r += yt * T4 / (2 * CTB_PI * CTB_PI);
+        return r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+CTB_DEV double sgn(double x) { return (double)((x > 0) - (x < 0)); }
+
+// 1/x for normal, finite, non-zero x: MUFU.RCP64H seed + two Newton steps (<= 1 ulp; no special-case
+// slow path, unlike the IEEE division sequence).  Used where the operand is a radius or a tolerance.
+CTB_DEV double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+// scipy.optimize.brentq (Zeros/brentq.c) restated; F: double -> double.
+// err: 0 ok, 1 same sign, 2 NaN function value (scipy raises ValueError), 3 maxiter
+template <class F>
+CTB_DEV double brentq(F f, double xa, double xb, int &err)
+{
+    const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+    double xpre = xa, xcur = xb;
+    double xblk = 0., fpre, fcur, fblk = 0., spre = 0., scur = 0., sbis;
+    double delta, stry, dpre, dblk;
+    err = 0;
+    fpre = f(xpre);
+    fcur = f(xcur);
+    if (isnan(fpre) || isnan(fcur)) { err = 2; return nan(""); }
+    if (fpre == 0) return xpre;
+    if (fcur == 0) return xcur;
+    if (signbit(fpre) == signbit(fcur)) { err = 1; return 0.; }
+    for (int i = 0; i < 100; i++) {
+        if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) {
+            xblk = xpre; fblk = fpre;
+            spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        delta = (xtol + rtol * fabs(xcur)) / 2;
+        sbis = (xblk - xcur) / 2;
+        if (fcur == 0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            } else {
+                dpre = (fpre - fcur) / (xpre - xcur);
+                dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            double m1 = fabs(spre), m2 = 3 * fabs(sbis) - delta;
+            double mn = (m1 < m2) ? m1 : m2;
+            if (2 * fabs(stry) < mn) { spre = scur; scur = stry; }
+            else { spre = sbis; scur = sbis; }
+        } else {
+            spre = sbis; scur = sbis;
+        }
+        xpre = xcur; fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = f(xcur);
+        if (isnan(fcur)) { err = 2; return nan(""); }
+    }
+    err = 3;
+    return xcur;
+}
+
+// scipy.optimize.fminbound (_optimize.py:_minimize_scalar_bounded) restated; returns xf
+template <class F>
+CTB_DEV double fminbound(F func, double x1, double x2, double xatol)
+{
+    const double sqrt_eps = 1.4832396974191326e-08; // sqrt(2.2e-16)
+    const double golden_mean = 0.3819660112501051;  // 0.5*(3-sqrt(5))
+    double a = x1, b = x2;
+    double fulc = a + golden_mean * (b - a);
+    double nfc = fulc, xf = fulc;
+    double rat = 0.0, e = 0.0;
+    double x = xf;
+    double fx = func(x);
+    int num = 1;
+    double fu;
+    double ffulc = fx, fnfc = fx;
+    double xm = 0.5 * (a + b);
+    double tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+    double tol2 = 2.0 * tol1;
+    while (fabs(xf - xm) > (tol2 - 0.5 * (b - a))) {
+        bool golden = true;
+        if (fabs(e) > tol1) {
+            golden = false;
+            double r = (xf - nfc) * (fx - ffulc);
+            double q = (xf - fulc) * (fx - fnfc);
+            double p = (xf - fulc) * q - (xf - nfc) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) p = -p;
+            q = fabs(q);
+            r = e;
+            e = rat;
+            if ((fabs(p) < fabs(0.5 * q * r)) && (p > q * (a - xf)) && (p < q * (b - xf))) {
+                rat = (p + 0.0) / q;
+                x = xf + rat;
+                if (((x - a) < tol2) || ((b - x) < tol2)) {
+                    double si = sgn(xm - xf) + ((xm - xf) == 0);
+                    rat = tol1 * si;
+                }
+            } else {
+                golden = true;
+            }
+        }
+        if (golden) {
+            e = (xf >= xm) ? a - xf : b - xf;
+            rat = golden_mean * e;
+        }
+        double si = sgn(rat) + (rat == 0);
+        double ar = fabs(rat);
+        x = xf + si * (ar > tol1 ? ar : tol1);
+        fu = func(x);
+        num += 1;
+        if (fu <= fx) {
+            if (x >= xf) a = xf; else b = xf;
+            fulc = nfc; ffulc = fnfc;
+            nfc = xf; fnfc = fx;
+            xf = x; fx = fu;
+        } else {
+            if (x < xf) a = x; else b = x;
+            if ((fu <= fnfc) || (nfc == xf)) {
+                fulc = nfc; ffulc = fnfc;
+                nfc = x; fnfc = fu;
+            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+                fulc = x; ffulc = fu;
+            }
+        }
+        xm = 0.5 * (a + b);
+        tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+        tol2 = 2.0 * tol1;
+        if (num >= 500) break;
+    }
+    return xf;
+}
+
+// scipy.integrate.simpson on a non-uniform grid, as a STREAM: points are fed in order and only the
+// last three are kept.  N (total number of points) must be known up front.   T1D:787 + scipy
+struct SimpsonStream {
+    double xa, ya, xb, yb, xc, yc; // oldest .. newest
+    double sum;
+    int idx, nbasic;
+    CTB_DEV void init(int N)
+    {
+        sum = 0.0; idx = 0;
+        nbasic = (N & 1) ? N : N - 1; // even N: composite rule on the first N-1 points
+        xa = ya = xb = yb = xc = yc = 0.0;
+    }
+    static CTB_DEV double pair(double x0, double y0, double x1, double y1, double x2, double y2)
+    {
+        double h0 = x1 - x0, h1 = x2 - x1;
+        double hsum = h0 + h1, hprod = h0 * h1;
+        if (hprod > 0 && hprod < 1e300) { // regular case: h0/h1, h1/h0, hsum/hprod from one reciprocal
+            double rp = rcp_fast(hprod);
+            double h0divh1 = h0 * h0 * rp, inv = h1 * h1 * rp, q = hsum * rp;
+            return hsum * (1.0 / 6.0) * (y0 * (2.0 - inv) + y1 * (hsum * q) + y2 * (2.0 - h0divh1));
+        }
+        double h0divh1 = (h1 != 0) ? h0 / h1 : 0.0; // scipy's guarded divisions (repeated abscissae)
+        double inv = (h0divh1 != 0) ? 1.0 / h0divh1 : 0.0;
+        double q = (hprod != 0) ? hsum / hprod : 0.0;
+        return hsum / 6.0 * (y0 * (2.0 - inv) + y1 * (hsum * q) + y2 * (2.0 - h0divh1));
+    }
+    CTB_DEV void feed(double x, double y)
+    {
+        xa = xb; ya = yb; xb = xc; yb = yc; xc = x; yc = y;
+        if (idx >= 2 && !(idx & 1) && idx < nbasic) sum += pair(xa, ya, xb, yb, xc, yc);
+        idx++;
+    }
+    CTB_DEV double finish(int N) const
+    {
+        if (N & 1) return sum;
+        if (N == 2) return 0.5 * (xc - xb) * (yc + yb);
+        double h0 = xb - xa, h1 = xc - xb;
+        double num, den, al, be, et;
+        num = 2 * h1 * h1 + 3 * h0 * h1; den = 6 * (h1 + h0);
+        al = (den != 0) ? num / den : 0.0;
+        num = h1 * h1 + 3.0 * h0 * h1; den = 6 * h0;
+        be = (den != 0) ? num / den : 0.0;
+        num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1);
+        et = (den != 0) ? num / den : 0.0;
+        return sum + (al * yc + be * yb - et * ya);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the instance solver
+struct Knobs {
+    double xtol, phitol, thinCutoff, rmin, rmax, phi_eps, xguess;
+    int npoints, max_interior_pts;
+};
+
+struct ProfileSink { // optional Profile1D dump
+    double *R, *Phi, *dPhi;
+};
+
+enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
+
+template <class Pot, int ALPHA>
+struct Sfi {
+    Pot pot;
+    double phi_abs, phi_meta, phi_eps;
+    int n_rkck;
+
+    // T1D:151-161, 191-201 (5-point stencils) or the functor's analytic forms
+    CTB_DEV double dV(double phi) const
+    {
+        if constexpr (Pot::analytic) {
+            return pot.dV(phi);
+        } else {
+            double eps = phi_eps;
+            return (pot.V(phi - 2 * eps) - 8 * pot.V(phi - eps) + 8 * pot.V(phi + eps) - pot.V(phi + 2 * eps))
+                   / (12. * eps);
+        }
+    }
+    CTB_DEV double d2V(double phi) const
+    {
+        if constexpr (Pot::analytic) {
+            return pot.d2V(phi);
+        } else {
+            double eps = phi_eps;
+            return (-pot.V(phi - 2 * eps) + 16 * pot.V(phi - eps) - 30 * pot.V(phi) + 16 * pot.V(phi + eps)
+                    - pot.V(phi + 2 * eps)) / (12. * eps * eps);
+        }
+    }
+    // T1D:163-189
+    CTB_DEV double dV_from_absMin(double delta_phi) const
+    {
+        double phi = phi_abs + delta_phi;
+        double dv = dV(phi);
+        if (phi_eps > 0) {
+            double dv_ = d2V(phi) * delta_phi;
+            double q = delta_phi / phi_eps;
+            double blend = exp(-(q * q));
+            dv = dv_ * blend + dv * (1 - blend);
+        }
+        return dv;
+    }
+
+    // T1D:294-373.  nu = (ALPHA-1)/2: closed forms for nu = 1/2, I0/I1/J0/J1 + recurrences for nu = 1.
+    template <bool WANT_DPHI>
+    CTB_DEV void exact_solution(double r, double phi0, double dv, double d2v, double &phi, double &dphi) const
+    {
+        double beta = sqrt(fabs(d2v));
+        double z = beta * r;
+        if (z < 1e-2) {
+            const double s = (d2v > 0) ? 1.0 : -1.0;
+            // Gamma(k+1) Gamma(k+1+nu), k = 1..3 ; Gamma(nu+1)
+            const double G1 = (ALPHA == 2) ? 1.3293403881791370 : 2.0;
+            const double G2 = (ALPHA == 2) ? 2.0 * 3.3233509704478426 : 12.0;
+            const double G3 = (ALPHA == 2) ? 6.0 * 11.631728396567448 : 144.0;
+            const double g = (ALPHA == 2) ? 0.88622692545275801 : 1.0;
+            double h2 = (0.5 * z) * (0.5 * z);
+            double t1 = s / G1, t2 = h2 / G2, t3 = h2 * h2 * s / G3;
+            double p = t1 + t2 + t3;
+            double dp = t1 * 2 + t2 * 4 + t3 * 6;
+            phi = p * (0.25 * g * (r * r) * dv * s) + phi0;
+            dphi = dp * (0.25 * g * r * dv * s);
+            return;
+        }
+        const bool modified = d2v > 0;
+        double ratio = dv / d2v;
+        if (ALPHA == 2) {
+            // Gamma(3/2) (z/2)^(-1/2) I_{1/2}(z) = sinh(z)/z ; J: sin(z)/z
+            double sh, ch;
+            if (modified) {
+                if (z < 1.0) { sh = sinh(z); ch = cosh(z); }
+                else if (z < 700.0) { // one exp for both; no cancellation for z >= 1
+                    double ez = exp(z), emz = rcp_fast(ez);
+                    sh = 0.5 * (ez - emz); ch = 0.5 * (ez + emz);
+                } else { double e2 = exp(0.5 * z); sh = (0.5 * e2) * e2; ch = sh; } // overflows with I_nu
+                phi = (sh / z - 1.0) * ratio + phi0;
+                if (WANT_DPHI) dphi = ((ch - sh / z) / r) * ratio;
+            } else {
+                sincos(z, &sh, &ch);
+                phi = (sh / z - 1.0) * ratio + phi0;
+                if (WANT_DPHI) dphi = ((ch - sh / z) / r) * ratio;
+            }
+        } else {
+            double hp = 2.0 / z; // (z/2)^-1, Gamma(2) = 1
+            double Inu, Im, Ip;
+            if (modified) {
+                double i0 = cyl_bessel_i0(z), i1 = cyl_bessel_i1(z);
+                Inu = i1; Im = i0; Ip = i0 - 2.0 * i1 / z;
+                phi = (hp * Inu - 1) * dv / d2v + phi0;
+                if (WANT_DPHI) {
+                    double d = -1.0 * (hp / r) * Inu;
+                    d += hp * 0.5 * beta * (Im + Ip);
+                    dphi = d * ratio;
+                }
+            } else {
+                double j0_ = j0(z), j1_ = j1(z);
+                Inu = j1_; Im = j0_; Ip = 2.0 * j1_ / z - j0_;
+                phi = (hp * Inu - 1) * dv / d2v + phi0;
+                if (WANT_DPHI) {
+                    double d = -1.0 * (hp / r) * Inu;
+                    d += hp * 0.5 * beta * (Im - Ip);
+                    dphi = d * ratio;
+                }
+            }
+        }
+    }
+
+    // T1D:377-434; returns 0 or a CTB_ST_* error
+    CTB_DEV int initial_conditions(double delta_phi0, double rmin, double cutoff, double &r0, double &phi_r0,
+                                   double &dphi_r0) const
+    {
+        double phi0 = phi_abs + delta_phi0;
+        double dv = dV_from_absMin(delta_phi0);
+        double d2v = d2V(phi0);
+        exact_solution<true>(rmin, phi0, dv, d2v, phi_r0, dphi_r0);
+        r0 = rmin;
+        if (fabs(phi_r0 - phi_abs) > fabs(cutoff)) return 0;
+        if (isnan(dphi_r0) || isnan(delta_phi0) || sgn(dphi_r0) != sgn(delta_phi0)) return 0;
+        double r = rmin, rlast = rmin;
+        while (isfinite(r)) {
+            rlast = r;
+            r *= 10;
+            double p, dp;
+            exact_solution<false>(r, phi0, dv, d2v, p, dp);
+            if (fabs(p - phi_abs) > fabs(cutoff)) break;
+        }
+        int err;
+        const double pa = phi_abs, ac = fabs(cutoff);
+        double rr = brentq(
+            [&](double r_) {
+                double p, dp;
+                exact_solution<false>(r_, phi0, dv, d2v, p, dp);
+                return fabs(p - pa) - ac;
+            },
+            rlast, r, err);
+        if (err == 2) return CTB_ST_NONFINITE;
+        if (err == 1) return CTB_ST_BRENT_SIGN;
+        r0 = rr;
+        exact_solution<true>(r0, phi0, dv, d2v, phi_r0, dphi_r0);
+        return 0;
+    }
+
+    // T1D:436-440
+    CTB_DEV void eom(double y0, double y1, double r, double &f0, double &f1) const
+    {
+        f0 = y1;
+        f1 = dV(y0) - (ALPHA * y1) * rcp_fast(r);
+    }
+
+    // HF:204-236 Cash-Karp step
+    CTB_DEV void rkck(double y0, double y1, double d0, double d1, double t, double dt, double &dy0, double &dy1,
+                      double &e0, double &e1)
+    {
+        const double a2 = 0.2, a3 = 0.3, a4 = 0.6, a5 = 1.0, a6 = 0.875, b21 = 0.2;
+        const double b31 = 3.0 / 40.0, b32 = 9.0 / 40.0, b41 = 0.3, b42 = -0.9, b43 = 1.2;
+        const double b51 = -11.0 / 54.0, b52 = 2.5, b53 = -70.0 / 27.0, b54 = 35.0 / 27.0;
+        const double b61 = 1631.0 / 55296.0, b62 = 175.0 / 512.0, b63 = 575.0 / 13824.0;
+        const double b64 = 44275.0 / 110592.0, b65 = 253.0 / 4096.0, c1 = 37.0 / 378.0;
+        const double c3 = 250.0 / 621.0, c4 = 125.0 / 594.0, c6 = 512.0 / 1771.0;
+        const double dc5 = -277.00 / 14336.0;
+        const double dc1 = c1 - 2825.0 / 27648.0, dc3 = c3 - 18575.0 / 48384.0;
+        const double dc4 = c4 - 13525.0 / 55296.0, dc6 = c6 - 0.25;
+        double k20, k21, k30, k31, k40, k41, k50, k51, k60, k61;
+        n_rkck++;
+        eom(y0 + b21 * dt * d0, y1 + b21 * dt * d1, t + a2 * dt, k20, k21);
+        eom(y0 + dt * (b31 * d0 + b32 * k20), y1 + dt * (b31 * d1 + b32 * k21), t + a3 * dt, k30, k31);
+        eom(y0 + dt * (b41 * d0 + b42 * k20 + b43 * k30), y1 + dt * (b41 * d1 + b42 * k21 + b43 * k31), t + a4 * dt,
+            k40, k41);
+        eom(y0 + dt * (b51 * d0 + b52 * k20 + b53 * k30 + b54 * k40),
+            y1 + dt * (b51 * d1 + b52 * k21 + b53 * k31 + b54 * k41), t + a5 * dt, k50, k51);
+        eom(y0 + dt * (b61 * d0 + b62 * k20 + b63 * k30 + b64 * k40 + b65 * k50),
+            y1 + dt * (b61 * d1 + b62 * k21 + b63 * k31 + b64 * k41 + b65 * k51), t + a6 * dt, k60, k61);
+        dy0 = dt * (c1 * d0 + c3 * k30 + c4 * k40 + c6 * k60);
+        dy1 = dt * (c1 * d1 + c3 * k31 + c4 * k41 + c6 * k61);
+        e0 = dt * (dc1 * d0 + dc3 * k30 + dc4 * k40 + dc5 * k50 + dc6 * k60);
+        e1 = dt * (dc1 * d1 + dc3 * k31 + dc4 * k41 + dc5 * k51 + dc6 * k61);
+    }
+
+    // HF:113-179; returns 0 or CTB_ST_STEP_UNDERFLOW.  dt is in/out (try -> used).
+    CTB_DEV int rkqs(double y0, double y1, double d0, double d1, double t, double &dt, double epsfrac,
+                     double inv_ea0, double inv_ea1, double &dy0, double &dy1, double &dtnext)
+    {
+        double errmax;
+        for (;;) {
+            double e0, e1;
+            rkck(y0, y1, d0, d1, t, dt, dy0, dy1, e0, e1);
+            double a0 = fabs(e0) * inv_ea0, b0 = fabs(e0) * rcp_fast((fabs(y0) + 1e-300) * epsfrac);
+            double a1 = fabs(e1) * inv_ea1, b1 = fabs(e1) * rcp_fast((fabs(y1) + 1e-300) * epsfrac);
+            double m0 = (a0 < b0) ? a0 : b0, m1 = (a1 < b1) ? a1 : b1;
+            errmax = (m0 > m1) ? m0 : m1;
+            // numpy min/max propagate NaN; nan_to_num: NaN -> 0, +inf -> DBL_MAX
+            if (isnan(a0) || isnan(b0) || isnan(a1) || isnan(b1)) errmax = 0.0;
+            else if (isinf(errmax)) errmax = 1.7976931348623157e308;
+            if (errmax < 1.0) break;
+            double dttemp = 0.9 * dt * rsqrt(sqrt(errmax));
+            if (dt > 0) dt = (dt * .1 > dttemp) ? dt * .1 : dttemp;
+            else dt = (dt * .1 < dttemp) ? dt * .1 : dttemp;
+            if (t + dt == t) return CTB_ST_STEP_UNDERFLOW;
+        }
+        if (errmax > 1.89e-4) dtnext = 0.9 * dt * exp2(-.2 * log2(errmax));
+        else dtnext = 5 * dt;
+        return 0;
+    }
+};
+
+// HF:583-599 cubic Bezier through (y0, y0'dr) and (y1, y1'dr), one component
+// (the Bezier form Y0 (1-t)^3 + 3 Y1 (1-t)^2 t + 3 Y2 (1-t) t^2 + Y3 t^3 expanded in powers of t once per
+// step, so that each of the ~500 dense-output points costs three FMAs per component)
+struct Cubic {
+    double A0, A1, A2, A3, Yend;
+    CTB_DEV void init(double y0, double dy0, double y1, double dy1)
+    {
+        const double third = 1.0 / 3.0;
+        double Y1 = y0 + dy0 * third, Y2 = y1 - dy1 * third;
+        A0 = y0;
+        A1 = 3.0 * (Y1 - y0);
+        A2 = 3.0 * ((y0 - Y1) + (Y2 - Y1));
+        A3 = (y1 - y0) + 3.0 * (Y1 - Y2);
+        Yend = y1;
+    }
+    CTB_DEV double operator()(double t) const
+    {
+        double v = fma(t, fma(t, fma(t, A3, A2), A1), A0);
+        return (t == 1.0) ? Yend : v; // exact end point, as in the Bezier form
+    }
+};
+
+struct InstanceResult {
+    double S, phi0, r0, rf, x, phi_bar, rscale;
+    int status, n_shots, n_rkck, n_points;
+};
+
+// __init__ + findProfile + findAction for one instance.                        T1D:128-149, 615-791
+template <class Pot, int ALPHA>
+__device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, InstanceResult &res, const ProfileSink &sink)
+{
+    const double qnan = nan("");
+    res.S = res.phi0 = res.r0 = res.rf = res.x = res.phi_bar = res.rscale = qnan;
+    res.n_shots = res.n_rkck = res.n_points = 0;
+    s.n_rkck = 0;
+    s.phi_eps = 0.0;
+    const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
+    const Pot &pot = s.pot;
+
+    // ---- __init__ : T1D:128-149 ----
+    const double V_meta = pot.V(phi_meta);
+    if (V_meta <= pot.V(phi_abs)) { res.status = CTB_ST_STABLE; return; }
+    double phi_bar;
+    { // findBarrierLocation T1D:203-226
+        double phi_tol = fabs(phi_meta - phi_abs) * 1e-12;
+        double phi1 = phi_meta, phi2 = phi_abs, phi0 = 0.5 * (phi1 + phi2);
+        while (fabs(phi1 - phi2) > phi_tol) {
+            double V0 = pot.V(phi0);
+            if (V0 > V_meta) phi1 = phi0; else phi2 = phi0;
+            phi0 = 0.5 * (phi1 + phi2);
+        }
+        phi_bar = phi0;
+    }
+    res.phi_bar = phi_bar;
+    double rscale;
+    { // findRScale T1D:228-285
+        double phi_tol = fabs(phi_bar - phi_meta) * 1e-6;
+        double x1 = fmin(phi_bar, phi_meta), x2 = fmax(phi_bar, phi_meta);
+        double top = fminbound([&](double x) { return -pot.V(x); }, x1, x2, phi_tol);
+        if (top + phi_tol > x2 || top - phi_tol < x1) { res.status = CTB_ST_NO_BARRIER; return; }
+        double Vtop = pot.V(top) - V_meta;
+        double xtop = top - phi_meta;
+        if (Vtop <= 0) { res.status = CTB_ST_NO_BARRIER; return; }
+        rscale = fabs(xtop) / sqrt(fabs(6 * Vtop));
+    }
+    res.rscale = rscale;
+    s.phi_eps = k.phi_eps * fabs(phi_abs - phi_meta);
+
+    // ---- findProfile : T1D:676-727 ----
+    const double xtol = k.xtol, phitol = k.phitol;
+    double xmin = xtol * 10, xmax = INFINITY, x;
+    if (!isnan(k.xguess)) x = k.xguess;
+    else x = -log(fabs((phi_bar - phi_abs) / (phi_meta - phi_abs)));
+    const double rmin = k.rmin * rscale;
+    const double dr0 = rmin, drmin = 0.01 * rmin, rmax_rel = k.rmax * rscale;
+    const double delta_phi = phi_meta - phi_abs;
+    const double ea0 = fabs(delta_phi * phitol), ea1 = fabs(delta_phi / rscale * phitol);
+    const double epsfrac = phitol;
+    const double inv_ea0 = 1.0 / ea0, inv_ea1 = 1.0 / ea1;
+    const double cutoff = k.thinCutoff * delta_phi;
+    bool have_rf = false;
+    double rf = qnan, r0 = qnan, y00 = qnan, y01 = qnan, delta_phi0 = qnan;
+    int status = CTB_ST_XTOL, nshots = 0;
+
+    for (;;) {
+        delta_phi0 = exp(-x) * delta_phi;
+        double r0_, p0, dp0;
+        int e = s.initial_conditions(delta_phi0, rmin, cutoff, r0_, p0, dp0);
+        if (e) { res.status = e; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
+        if (!isfinite(r0_) || !isfinite(x)) {
+            if (!have_rf) { res.status = CTB_ST_FIRST_SHOT; res.n_rkck = s.n_rkck; return; }
+            status = CTB_ST_XTOL;
+            break;
+        }
+        r0 = r0_; y00 = p0; y01 = dp0;
+        // ---- integrateProfile : T1D:489-536 ----
+        int ctype;
+        {
+            double r_ = r0, ya = y00, yb = y01, dr = dr0, da, db;
+            s.eom(ya, yb, r_, da, db);
+            const double ysign = sgn(ya - phi_meta);
+            const double rmax = rmax_rel + r0;
+            double yf0, yf1;
+            for (;;) {
+                double dy0, dy1, drnext;
+                e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
+                if (e) { res.status = e; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
+                double r1 = r_ + dr, na = ya + dy0, nb = yb + dy1, nda, ndb;
+                s.eom(na, nb, r1, nda, ndb);
+                if (r1 > rmax) { res.status = CTB_ST_RMAX; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
+                else if (dr < drmin) { res.status = CTB_ST_DRMIN; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
+                else if (fabs(na - phi_meta) < 3 * ea0 && fabs(nb) < 3 * ea1) {
+                    rf = r1; yf0 = na; yf1 = nb; ctype = CT_CONVERGED;
+                    break;
+                } else if (nb * ysign > 0 || (na - phi_meta) * ysign < 0) {
+                    Cubic f0, f1;
+                    f0.init(ya, dr * da, na, dr * nda);
+                    f1.init(yb, dr * db, nb, dr * ndb);
+                    double xx;
+                    int berr;
+                    if (nb * ysign > 0) {
+                        xx = brentq([&](double t) { return f1(t); }, 0.0, 1.0, berr);
+                        ctype = CT_UNDERSHOOT;
+                    } else {
+                        const double pm = phi_meta;
+                        xx = brentq([&](double t) { return f0(t) - pm; }, 0.0, 1.0, berr);
+                        ctype = CT_OVERSHOOT;
+                    }
+                    if (berr == 1 || berr == 2) {
+                        res.status = (berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN;
+                        res.n_shots = nshots; res.n_rkck = s.n_rkck;
+                        return;
+                    }
+                    rf = r_ + dr * xx;
+                    yf0 = f0(xx); yf1 = f1(xx);
+                    break;
+                }
+                r_ = r1; ya = na; yb = nb; da = nda; db = ndb;
+                dr = drnext;
+            }
+            if (fabs(yf0 - phi_meta) < 3 * ea0 && fabs(yf1) < 3 * ea1) ctype = CT_CONVERGED;
+        }
+        have_rf = true;
+        nshots++;
+        res.x = x;
+        if (ctype == CT_CONVERGED) { status = CTB_ST_CONVERGED; break; }
+        else if (ctype == CT_UNDERSHOOT) { xmin = x; x = (xmax == INFINITY) ? x * 5.0 : .5 * (xmin + xmax); }
+        else { xmax = x; x = .5 * (xmin + xmax); }
+        if ((xmax - xmin) < xtol) { status = CTB_ST_XTOL; break; }
+    }
+    res.n_shots = nshots;
+    res.r0 = r0; res.rf = rf;
+    res.phi0 = phi_abs + delta_phi0;
+
+    // ---- second pass with dense output, interior points and the action, fused: T1D:729-791 ----
+    const int npoints = k.npoints;
+    const double step = (rf - r0) / (npoints - 1);
+    const double Rl1 = (npoints == 2) ? rf : __dadd_rn(__dmul_rn(1.0, step), r0);
+    int nint = 0;
+    double a_int = 0.0, dx0 = Rl1 - r0, st_int = 0.0;
+    bool lin_int = true;
+    const int max_interior = (k.max_interior_pts < 0) ? npoints / 2 : k.max_interior_pts;
+    if (max_interior > 0) {
+        if (r0 / dx0 <= max_interior) {
+            nint = (int)ceil(r0 / dx0);
+            st_int = r0 / nint;
+        } else {
+            nint = max_interior;
+            lin_int = false;
+            a_int = (r0 / dx0 - nint) * 2 / ((double)nint * (nint + 1));
+        }
+    }
+    const int N = nint + npoints;
+    res.n_points = N;
+    const double afac = (ALPHA == 2) ? 12.566370614359172 : 19.739208802178716;  // 2 pi^(d/2) / Gamma(d/2)
+    const double vfac = (ALPHA == 2) ? 4.1887902047863905 : 4.934802200544679;   // pi^(d/2) / Gamma(d/2+1)
+    SimpsonStream simp;
+    simp.init(N);
+    double R_first = 0.0, Phi_first = 0.0;
+    int pidx = 0;
+    auto emit = [&](double r, double phi, double dphi) {
+        double ra = (ALPHA == 2) ? r * r : r * r * r;
+        double integrand = (0.5 * (dphi * dphi) + pot.V(phi) - V_meta) * (ra * afac);
+        simp.feed(r, integrand);
+        if (pidx == 0) { R_first = r; Phi_first = phi; }
+        if (sink.R) { sink.R[pidx] = r; sink.Phi[pidx] = phi; sink.dPhi[pidx] = dphi; }
+        pidx++;
+    };
+    if (nint > 0) { // T1D:734-760
+        const double phi_c = phi_abs + delta_phi0;
+        const double dv = s.dV_from_absMin(delta_phi0);
+        const double d2v = s.d2V(phi_c);
+        emit(0.0, phi_c, 0.0);
+        for (int i = 1; i < nint; i++) {
+            double ri;
+            if (lin_int) ri = __dadd_rn(__dmul_rn((double)i, st_int), 0.0);
+            else {
+                double Nv = (double)(nint - i);
+                ri = r0 - dx0 * (Nv + 0.5 * a_int * Nv * (Nv + 1));
+            }
+            double p, dp;
+            s.template exact_solution<true>(ri, phi_c, dv, d2v, p, dp);
+            emit(ri, p, dp);
+        }
+    }
+    { // integrateAndSaveProfile T1D:578-613
+        double r_ = r0, ya = y00, yb = y01, dr = dr0, da, db;
+        s.eom(ya, yb, r_, da, db);
+        emit(r0, ya, yb);
+        int i = 1;
+        double Ri = (npoints == 2) ? rf : __dadd_rn(__dmul_rn(1.0, step), r0);
+        while (i < npoints) {
+            double dy0, dy1, drnext;
+            int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
+            if (e) { res.status = e; res.n_rkck = s.n_rkck; return; }
+            double r1, na, nb;
+            if (dr >= drmin) {
+                r1 = r_ + dr; na = ya + dy0; nb = yb + dy1;
+            } else {
+                na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;
+                dr = drnext = drmin;
+                r1 = r_ + dr;
+            }
+            double nda, ndb;
+            s.eom(na, nb, r1, nda, ndb);
+            if (r_ < Ri && Ri <= r1) {
+                Cubic f0, f1;
+                f0.init(ya, dr * da, na, dr * nda);
+                f1.init(yb, dr * db, nb, dr * ndb);
+                const double inv_dr = rcp_fast(dr);
+                while (i < npoints && r_ < Ri && Ri <= r1) {
+                    double t = (Ri - r_) * inv_dr;
+                    emit(Ri, f0(t), f1(t));
+                    i++;
+                    Ri = (i == npoints - 1) ? rf : __dadd_rn(__dmul_rn((double)i, step), r0);
+                }
+            }
+            r_ = r1; ya = na; yb = nb; da = nda; db = ndb;
+            dr = drnext;
+        }
+    }
+    // findAction T1D:780-791
+    double S = simp.finish(N);
+    double Rd = (ALPHA == 2) ? R_first * R_first * R_first : (R_first * R_first) * (R_first * R_first);
+    S += (Rd * vfac) * (pot.V(Phi_first) - V_meta);
+    res.S = S;
+    res.n_rkck = s.n_rkck;
+    res.status = status;
+}
+
+} // namespace ctb

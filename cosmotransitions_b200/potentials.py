@@ -1,0 +1,81 @@
+"""Device-functor potentials: the objects that stand in for the Python callables V, dV, d2V of
+SingleFieldInstanton(phi_absMin, phi_metaMin, V, dV, d2V) (tunneling1D.py:128-130).
+
+A functor names a potential the CUDA kernels know how to evaluate (include/ctbounce.h CTB_POT_*)
+plus one row of parameters.  Calling it evaluates V(phi) ON THE GPU (ctb_potential)."""
+import numpy as np
+
+from . import _lib, _tables
+
+
+class DevicePotential:
+    kind = None
+
+    def __init__(self, params):
+        self.params = np.ascontiguousarray(params, dtype=np.float64).reshape(_lib.NPARAM[self.kind])
+
+    needs_tables = False
+
+    def __call__(self, phi):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x = np.asarray(phi, dtype=np.float64)
+        d_phi = torch.from_numpy(np.ascontiguousarray(x.reshape(-1))).to(dev)
+        d_par = torch.from_numpy(self.params).to(dev)
+        out = torch.empty_like(d_phi)
+        tabs = _tables.device_tables(dev) if self.needs_tables else None
+        jb = tabs.jb if tabs else None
+        jf = tabs.jf if tabs else None
+        _lib.check(lib.ctb_potential(self.kind, d_par.data_ptr(), jb, jf, d_phi.data_ptr(), out.data_ptr(),
+                                     d_phi.numel(), torch.cuda.current_stream().cuda_stream), "ctb_potential")
+        res = out.cpu().numpy().reshape(x.shape)
+        return float(res) if res.ndim == 0 else res
+
+
+class Poly4Potential(DevicePotential):
+    """V = c0 + c1 phi + c2 phi^2 + c3 phi^3 + c4 phi^4 with analytic dV, d2V."""
+    kind = _lib.POT_POLY4
+
+    def __init__(self, c0=0.0, c1=0.0, c2=0.0, c3=0.0, c4=0.0):
+        super().__init__([c0, c1, c2, c3, c4])
+
+
+def quartic_family_params(c):
+    """Rows [c0..c4] of V = phi^4/4 - (1+c)/3 phi^3 + c/2 phi^2, i.e. dV = phi (phi-c) (phi-1)
+    (the family of the reference's docstring examples, tunneling1D.py:112-122; minima at 0 and 1)."""
+    c = np.atleast_1d(np.asarray(c, dtype=np.float64))
+    p = np.zeros((c.size, 5))
+    p[:, 2] = c / 2
+    p[:, 3] = -(1 + c) / 3
+    p[:, 4] = 0.25
+    return p
+
+
+class QuarticPotential(Poly4Potential):
+    def __init__(self, c):
+        DevicePotential.__init__(self, quartic_family_params(c)[0])
+
+
+def model1_model8(m1=120., m2=50., mu=25., Y1=.1, Y2=.15, n=30, v2=246. ** 2):
+    """(l1, l2, mu2, Y1, Y2, n, renormScaleSq, v2) of examples/testModel1.py:19-47."""
+    return np.array([.5 * m1 ** 2 / v2, .5 * m2 ** 2 / v2, mu ** 2, Y1, Y2, float(n), v2, v2])
+
+
+class Model1LinePotential(DevicePotential):
+    """model1.Vtot along X(phi) = x0 + phi * nhat at temperature T; derivatives by finite differences."""
+    kind = _lib.POT_MODEL1_LINE
+    needs_tables = True
+
+    def __init__(self, x0, nhat, T, model8=None):
+        m8 = model1_model8() if model8 is None else np.asarray(model8, dtype=np.float64)
+        super().__init__(np.concatenate([m8, [T], np.asarray(x0, float), np.asarray(nhat, float)]))
+
+
+class Model1FPotential(DevicePotential):
+    """One-field model1-style thermal potential (see include/ctbounce.h CTB_POT_MODEL1F)."""
+    kind = _lib.POT_MODEL1F
+    needs_tables = True
+
+    def __init__(self, lam, Y, n, T, v2=246. ** 2, renormScaleSq=None):
+        super().__init__([lam, v2, Y, n, v2 if renormScaleSq is None else renormScaleSq, T])

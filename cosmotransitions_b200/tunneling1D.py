@@ -1,0 +1,109 @@
+"""Drop-in for cosmoTransitions.tunneling1D.SingleFieldInstanton (tunneling1D.py:49-826) whose
+numerical work -- __init__ (barrier location, rscale), findProfile, findAction -- runs on the GPU as a
+batch of one through the same kernel the batched entry point uses.
+
+Same constructor signature, same findProfile knobs and defaults, same Profile1D namedtuple, same
+exceptions (PotentialError(msg, kind) with kind in {"no barrier", "stable, not metastable"},
+helper_functions.IntegrationError), so it can be handed to pathDeformation.fullTunneling as
+`tunneling_class=` (pathDeformation.py:849,959-968) for potentials the device knows.
+
+The one difference: V must be a device functor (cosmotransitions_b200.potentials.DevicePotential),
+not an arbitrary Python callable -- arbitrary callables cannot run inside a CUDA kernel and there is
+no CPU fallback.  dV / d2V are taken from the functor (analytic where it has them, otherwise the
+reference's own 5-point stencils, tunneling1D.py:151-161,191-201, evaluated on the device).
+"""
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib, batch
+from .helper_functions import IntegrationError
+from .potentials import DevicePotential
+
+
+class PotentialError(Exception):
+    """
+    Used when the potential does not have the expected characteristics.
+
+    The error messages should be tuples, with the second item being one of
+    ``("no barrier", "stable, not metastable")``.
+    """
+    pass
+
+
+_ERRORS = {
+    _lib.ST_STABLE: lambda: PotentialError("V(phi_metaMin) <= V(phi_absMin); tunneling cannot occur.",
+                                           "stable, not metastable"),
+    _lib.ST_NO_BARRIER: lambda: PotentialError("The potential barrier does not exist between phi_bar and "
+                                               "phi_metaMin.", "no barrier"),
+    _lib.ST_RMAX: lambda: IntegrationError("r > rmax"),
+    _lib.ST_DRMIN: lambda: IntegrationError("dr < drmin"),
+    _lib.ST_STEP_UNDERFLOW: lambda: IntegrationError("Stepsize rounds down to zero."),
+    _lib.ST_NONFINITE: lambda: ValueError("The function value in the initialConditions root find is NaN; "
+                                          "solver cannot continue."),
+    _lib.ST_BRENT_SIGN: lambda: ValueError("f(a) and f(b) must have different signs"),
+    _lib.ST_FIRST_SHOT: lambda: AssertionError("Failed to retrieve initial conditions on the first try."),
+}
+
+
+def raise_for_status(status):
+    """Maps a per-instance status code to the exception the reference raises at that point."""
+    status = int(status)
+    if status in _ERRORS:
+        raise _ERRORS[status]()
+    if status not in (_lib.ST_CONVERGED, _lib.ST_XTOL):
+        raise RuntimeError("bounce solver: " + _lib.status_string(status))
+
+
+class SingleFieldInstanton:
+    """GPU-backed counterpart of tunneling1D.SingleFieldInstanton (see module docstring)."""
+
+    profile_rval = namedtuple("Profile1D", "R Phi dPhi Rerr")
+
+    def __init__(self, phi_absMin, phi_metaMin, V, dV=None, d2V=None, phi_eps=1e-3, alpha=2, phi_bar=None,
+                 rscale=None):
+        if not isinstance(V, DevicePotential):
+            raise TypeError("V must be a cosmotransitions_b200.potentials.DevicePotential (device functor); "
+                            "arbitrary Python callables cannot run on the GPU and there is no CPU fallback")
+        if phi_bar is not None or rscale is not None:
+            raise NotImplementedError("phi_bar / rscale overrides are not supported by the device solver")
+        self.phi_absMin, self.phi_metaMin = float(phi_absMin), float(phi_metaMin)
+        self.V = V
+        self.alpha = alpha
+        self._phi_eps_rel = phi_eps
+        self.phi_eps = phi_eps * abs(self.phi_absMin - self.phi_metaMin)
+        self._last = None
+        # the reference validates the potential in __init__ (tunneling1D.py:133-147): do the same
+        r = self._solve(npoints=2)
+        st = int(r["status"][0])
+        if st in (_lib.ST_STABLE, _lib.ST_NO_BARRIER):
+            raise_for_status(st)
+        self.phi_bar = float(r["phi_bar"][0])
+        self.rscale = float(r["rscale"][0])
+
+    def _solve(self, return_profiles=False, **knobs):
+        return batch.find_bounce_batch(self.V.kind, self.V.params[None, :], [self.phi_absMin], [self.phi_metaMin],
+                                       alpha=self.alpha, phi_eps=self._phi_eps_rel, return_profiles=return_profiles,
+                                       **knobs)
+
+    def findProfile(self, xguess=None, xtol=1e-4, phitol=1e-4, thinCutoff=.01, npoints=500, rmin=1e-4, rmax=1e4,
+                    max_interior_pts=None):
+        r = self._solve(return_profiles=True, xguess=xguess, xtol=xtol, phitol=phitol, thinCutoff=thinCutoff,
+                        npoints=npoints, rmin=rmin, rmax=rmax, max_interior_pts=max_interior_pts)
+        raise_for_status(r["status"][0])
+        n = int(r["n_points"][0])
+        prof = self.profile_rval(r["R"][0, :n].numpy().copy(), r["Phi"][0, :n].numpy().copy(),
+                                 r["dPhi"][0, :n].numpy().copy(), None)
+        self._last = (prof, float(r["S"][0]))
+        return prof
+
+    def findAction(self, profile):
+        """Euclidean action of `profile` (tunneling1D.py:763-791).  For the profile findProfile just
+        returned this is the value the kernel accumulated while producing it (fused quadrature)."""
+        if self._last is not None and profile is self._last[0]:
+            return self._last[1]
+        raise NotImplementedError("findAction is fused with findProfile on the device; pass the Profile1D "
+                                  "returned by the most recent findProfile() call")
+
+    def evenlySpacedPhi(self, phi, dphi, npoints=100, k=1, fixAbs=True):
+        raise NotImplementedError("evenlySpacedPhi belongs to the multi-field caller (SURVEY.md s.8f, next row)")

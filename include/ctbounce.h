@@ -1,0 +1,158 @@
+/*
+ * ctbounce.h -- C ABI of libctbounce.so: the B200 (sm_100a) batched bounce solver.
+ *
+ * Drop-in boundary for ONE hot path of CosmoTransitions (all file:line into the reference):
+ *   tunneling1D.SingleFieldInstanton.__init__ / findProfile / findAction   tunneling1D.py:128-149,615-791
+ *   helper_functions.rkqs / _rkck / cubicInterpFunction                   helper_functions.py:113-236,583-599
+ *   finiteT.Jb_spline / Jf_spline                                          finiteT.py:167-174,197-204
+ *   generic_potential.Vtot (V0 + V1 + V1T) for examples/testModel1.py      generic_potential.py:240-337
+ *
+ * The reference is pure Python and has no FFI; these entry points are what a ctypes binding of that
+ * path binds (see INTEGRATION.md for the reference-side stub).  Conventions:
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller
+ *     (contiguous FP64 / int32), on the device that is current when the call is made;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
+ *     with respect to the host unless stated otherwise;
+ *   - the library keeps no state between calls and allocates nothing;
+ *   - return value: 0 on success, CTB_ERR_* (<0) for argument errors, or a positive cudaError_t;
+ *   - numerical failures are reported PER INSTANCE in the status array (CTB_ST_*), never as a
+ *     process-level error.  The Python host maps them back to the reference's exceptions.
+ */
+#ifndef CTBOUNCE_H
+#define CTBOUNCE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CTB_API __attribute__((visibility("default")))
+#else
+#define CTB_API
+#endif
+
+/* ---- return codes --------------------------------------------------------------------------- */
+#define CTB_OK 0
+#define CTB_ERR_BAD_ARG (-1)      /* NULL pointer, n < 0, bad enum ...                       */
+#define CTB_ERR_UNSUPPORTED (-2)  /* alpha not in {2,3}, npoints out of range, unknown kind   */
+#define CTB_ERR_NO_DEVICE (-3)    /* no CUDA device / not an sm_100 device                   */
+
+/* ---- per-instance status (int32) ------------------------------------------------------------ */
+#define CTB_ST_CONVERGED 0       /* last shot ended "converged"            tunneling1D.py:717   */
+#define CTB_ST_XTOL 1            /* bracket narrower than xtol             tunneling1D.py:726   */
+#define CTB_ST_STABLE 2          /* PotentialError "stable, not metastable" tunneling1D.py:133-135 */
+#define CTB_ST_NO_BARRIER 3      /* PotentialError "no barrier"            tunneling1D.py:266-283 */
+#define CTB_ST_RMAX 4            /* IntegrationError "r > rmax"            tunneling1D.py:506   */
+#define CTB_ST_DRMIN 5           /* IntegrationError "dr < drmin"          tunneling1D.py:508   */
+#define CTB_ST_STEP_UNDERFLOW 6  /* IntegrationError "Stepsize rounds down to zero." helper_functions.py:173 */
+#define CTB_ST_NONFINITE 7       /* ValueError from brentq on a NaN value  tunneling1D.py:432   */
+#define CTB_ST_BRENT_SIGN 8      /* ValueError from brentq: same signs     tunneling1D.py:432,519,523 */
+#define CTB_ST_FIRST_SHOT 9      /* AssertionError                         tunneling1D.py:710   */
+#define CTB_ST_NOT_RUN 10
+
+/* ---- potential functors (device-side V(phi); parameters are rows of d_params) --------------- */
+/* V = c0 + c1 phi + c2 phi^2 + c3 phi^3 + c4 phi^4 ; analytic dV, d2V.  params[5] = c0..c4        */
+#define CTB_POT_POLY4 0
+/* examples/testModel1.py model1 along the line X(phi) = x0 + phi*nhat at temperature T;
+ * dV, d2V by the 5-point stencils of tunneling1D.py:151-161,191-201.
+ * params[13] = l1, l2, mu2, Y1, Y2, n_boson, renormScaleSq, v2, T, x0[0], x0[1], nhat[0], nhat[1]   */
+#define CTB_POT_MODEL1_LINE 1
+/* one-field model1-style generic_potential: V0 = lam/4 (phi^2-v2)^2, bosons m^2 =
+ * {lam(3phi^2-v2), Y phi^2}, dof (1, n), c = 3/2.  params[6] = lam, v2, Y, n, renormScaleSq, T      */
+#define CTB_POT_MODEL1F 2
+
+#define CTB_NPARAM_POLY4 5
+#define CTB_NPARAM_MODEL1_LINE 13
+#define CTB_NPARAM_MODEL1F 6
+
+/* ---- Jb / Jf spline table in piecewise-polynomial form (device memory) ----------------------
+ * The reference evaluates scipy's (t, c, k=3) B-spline (finiteT.py:166,196).  The host converts it
+ * once to one cubic per knot interval: value = c0 + dx (c1 + dx (c2 + dx c3)), dx = theta - brk[j].  */
+typedef struct ctb_jtable {
+    const double *d_brk;  /* [nint + 1] strictly increasing breakpoints                           */
+    const double *d_coef; /* [nint * 4] c0..c3 per interval, 32-byte aligned                       */
+    int32_t nint;
+    int32_t reserved;
+    double xmin;          /* theta < xmin  -> value (or derivative) at xmin   finiteT.py:172,202   */
+    double xmax;          /* theta > xmax  -> 0                               finiteT.py:173,203   */
+} ctb_jtable;
+
+/* ---- findProfile knobs (tunneling1D.py:128-130, 615-617); same defaults as the reference ---- */
+typedef struct ctb_opts {
+    double xtol;              /* 1e-4 */
+    double phitol;            /* 1e-4 */
+    double thinCutoff;        /* 0.01 */
+    double rmin;              /* 1e-4 (relative to rscale) */
+    double rmax;              /* 1e4  (relative to rscale) */
+    double phi_eps;           /* 1e-3 (relative to |phi_absMin - phi_metaMin|) */
+    double xguess;            /* NaN = None */
+    int32_t npoints;          /* 500; 2 <= npoints <= 4096 */
+    int32_t max_interior_pts; /* -1 = None (npoints/2) */
+    int32_t alpha;            /* 2 (O(3), finite T) or 3 (O(4), zero T) */
+    int32_t block_threads;    /* 0 = library default */
+} ctb_opts;
+
+/* ---- outputs of the batched solve: structure of arrays, any pointer may be NULL ------------- */
+typedef struct ctb_bounce_out {
+    double *d_S;         /* Euclidean action            findAction, tunneling1D.py:763-791          */
+    double *d_phi0;      /* phi(r=0) = phi_absMin + exp(-x) (phi_metaMin - phi_absMin)              */
+    double *d_r0;        /* radius where the integration started (profile.R[n_interior])            */
+    double *d_rf;        /* radius where it ended (profile.R[-1])                                    */
+    double *d_x;         /* shooting parameter of the last shot                                      */
+    double *d_phi_bar;   /* findBarrierLocation                                                      */
+    double *d_rscale;    /* findRScale                                                               */
+    int32_t *d_status;   /* CTB_ST_*                                                                 */
+    int32_t *d_n_shots;  /* integrateProfile calls                                                   */
+    int32_t *d_n_rkck;   /* Cash-Karp step attempts (shooting + save pass)                           */
+    int32_t *d_n_points; /* profile length                                                           */
+    /* optional profile dump (Profile1D.R / .Phi / .dPhi): row i holds n_points[i] entries          */
+    double *d_prof_R;
+    double *d_prof_Phi;
+    double *d_prof_dPhi;
+    int64_t prof_stride; /* row length in doubles (>= npoints + npoints/2)                           */
+} ctb_bounce_out;
+
+CTB_API int ctb_abi_version(void);
+CTB_API const char *ctb_strerror(int code);
+CTB_API const char *ctb_status_string(int status);
+
+/* Device check: returns CTB_OK if the current device can run the sm_100a kernels. */
+CTB_API int ctb_device_ok(void);
+
+/* SingleFieldInstanton(phi_absMin, phi_metaMin, V, dV, d2V, phi_eps, alpha).findProfile(**knobs)
+ * followed by .findAction(profile), for n independent instances (tunneling1D.py:128-791).
+ * d_params: [n, nparam] row-major; d_phi_abs, d_phi_meta: [n].  jb/jf may be NULL for POLY4. */
+CTB_API int ctb_bounce_batch(int pot_kind, const double *d_params, const double *d_phi_abs, const double *d_phi_meta,
+                     int64_t n, const ctb_opts *opts, const ctb_jtable *jb, const ctb_jtable *jf,
+                     const ctb_bounce_out *out, void *stream);
+
+/* finiteT.Jb_spline(theta, n=deriv) / Jf_spline (finiteT.py:167-174,197-204): out[i] = J^(deriv)(theta[i]).
+ * deriv in 0..3. */
+CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta, double *d_out, int64_t n, void *stream);
+
+/* generic_potential.Vtot (generic_potential.py:312-337) for model1 (examples/testModel1.py:62-116):
+ * pointwise, d_X [n,2], d_T [n] -> d_out [n].  model[8] = l1,l2,mu2,Y1,Y2,n_boson,renormScaleSq,v2 (host). */
+CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const double *d_X, const double *d_T,
+                    double *d_out, int64_t n, void *stream);
+
+/* Same on the outer-product grid X_i = x0 + s_i * nhat, T_j:  d_out[i * nT + j]  (row-major [ns, nT]).
+ * line4 = x0[0], x0[1], nhat[0], nhat[1] (host). */
+CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, const ctb_jtable *jb, const double *d_s,
+                         int64_t ns, const double *d_T, int64_t nT, double *d_out, void *stream);
+
+/* Potential functor evaluation V(phi_j) for one parameter row (debug / parity aid). */
+CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                  const double *d_phi, double *d_out, int64_t n, void *stream);
+
+/* Register-resident FP64 FMA loop used to measure the FP64 roofline denominator.
+ * Runs iters * 16 dependent-chain-free FMAs per thread; returns elapsed ms via *ms_out (synchronous). */
+CTB_API int ctb_fp64_peak(int64_t iters, int blocks, int threads, double *d_sink, float *ms_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTBOUNCE_H */

@@ -1,0 +1,111 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the table conversion is exact, option marshalling, partitioning, loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cosmotransitions_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "ctbounce.h")).read()
+    declared = re.findall(r"CTB_API\s+(?:const\s+)?\w+\s*\*?\s*(ctb_\w+)\s*\(", hdr)
+    assert len(declared) >= 10
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(declared) == sorted(_lib.EXPORTS)
+    assert lib.ctb_abi_version() == _lib.ABI_VERSION
+    assert lib.ctb_strerror(-1) == b"bad argument"
+    assert lib.ctb_status_string(3) == b"no barrier"
+
+
+def test_struct_layout_matches_header():
+    import ctypes as C
+    from cosmotransitions_b200 import _lib
+    assert C.sizeof(_lib.JTable) == 40
+    assert C.sizeof(_lib.Opts) == 7 * 8 + 4 * 4
+    assert C.sizeof(_lib.BounceOut) == 15 * 8
+
+
+def test_bspline_to_pp_matches_scipy():
+    from scipy import interpolate
+    from cosmotransitions_b200 import _tables
+    h = _tables.host_tables()
+    rng = np.random.default_rng(0)
+    for t, c, brk, coef in ((h.tb, h.cb, h.brk_b, h.coef_b), (h.tf, h.cf, h.brk_f, h.coef_f)):
+        assert len(brk) == coef.shape[0] + 1 == 998
+        assert np.all(np.diff(brk) > 0)
+        x = np.concatenate([rng.uniform(brk[0], brk[-1], 5000), rng.uniform(-5, 5, 5000), brk[:-1]])
+        x = x[(x >= brk[0]) & (x < brk[-1])]
+        j = np.searchsorted(brk, x, side="right") - 1
+        dx = x - brk[j]
+        for der in range(4):
+            ref = interpolate.splev(x, (t, c, 3), der=der)
+            cc = coef[j]
+            if der == 0:
+                got = cc[:, 0] + dx * (cc[:, 1] + dx * (cc[:, 2] + dx * cc[:, 3]))
+            elif der == 1:
+                got = cc[:, 1] + dx * (2 * cc[:, 2] + dx * 3 * cc[:, 3])
+            elif der == 2:
+                got = 2 * cc[:, 2] + dx * 6 * cc[:, 3]
+            else:
+                got = 6 * cc[:, 3]
+            assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 2e-12, der
+
+
+def test_opts_marshalling_and_defaults():
+    from cosmotransitions_b200 import batch
+    o = batch.make_opts()
+    assert (o.xtol, o.phitol, o.thinCutoff, o.npoints, o.rmin, o.rmax) == (1e-4, 1e-4, .01, 500, 1e-4, 1e4)
+    assert o.max_interior_pts == -1 and np.isnan(o.xguess) and o.alpha == 2 and o.phi_eps == 1e-3
+    assert batch.profile_capacity(o) == 750
+    o = batch.make_opts(alpha=3, npoints=200, max_interior_pts=0, xguess=2.5)
+    assert batch.profile_capacity(o) == 200 and o.xguess == 2.5
+    with pytest.raises(TypeError):
+        batch.make_opts(bogus=1)
+    with pytest.raises(NotImplementedError):
+        batch.make_opts(alpha=4)
+
+
+def test_partition_roundtrip():
+    import torch
+    from cosmotransitions_b200 import multigpu
+    n, world = 1003, 8
+    vals = torch.arange(n, dtype=torch.float64) * 1.5
+    shards = [vals[torch.from_numpy(multigpu.partition(n, world, r))] for r in range(world)]
+    assert sum(len(s) for s in shards) == n
+    assert torch.equal(multigpu.gather_strided(shards, n, world), vals)
+
+
+def test_no_silent_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cosmotransitions_b200 import _lib, finiteT, find_bounce_batch, potentials
+    with pytest.raises(_lib.CtbError):
+        find_bounce_batch(_lib.POT_POLY4, potentials.quartic_family_params([0.2]), 1.0, 0.0)
+    with pytest.raises(_lib.CtbError):
+        finiteT.Jb_spline(np.array([0.0]))
+
+
+def test_status_to_exception_mapping():
+    from cosmotransitions_b200 import tunneling1D as t1, helper_functions as hf, _lib
+    with pytest.raises(t1.PotentialError) as e:
+        t1.raise_for_status(_lib.ST_STABLE)
+    assert e.value.args[1] == "stable, not metastable"
+    with pytest.raises(t1.PotentialError) as e:
+        t1.raise_for_status(_lib.ST_NO_BARRIER)
+    assert e.value.args[1] == "no barrier"
+    for st, msg in ((_lib.ST_RMAX, "r > rmax"), (_lib.ST_DRMIN, "dr < drmin"),
+                    (_lib.ST_STEP_UNDERFLOW, "Stepsize rounds down to zero.")):
+        with pytest.raises(hf.IntegrationError) as e:
+            t1.raise_for_status(st)
+        assert e.value.args[0] == msg
+    with pytest.raises(ValueError):
+        t1.raise_for_status(_lib.ST_NONFINITE)
+    t1.raise_for_status(0)
+    t1.raise_for_status(1)
