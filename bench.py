@@ -154,6 +154,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "sorted", "natural"],
+                    help="instance scheduling inside the library (see batch.launch_bounce)")
+    ap.add_argument("--order", default="natural", choices=["natural", "reversed", "shuffled"],
+                    help="instance order inside the batch (SURVEY.md s.8d: shuffled exposes divergence sensitivity)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -176,7 +180,12 @@ def main():
     assert _lib.load().ctb_device_ok() == 0, "not an sm_100 device"
 
     n = wl["n"]
+    sorted_sched = args.schedule == "sorted" or (args.schedule == "auto" and n >= batch.SORT_THRESHOLD)
     c = sweep_c(n, rank, world)
+    if args.order == "reversed":
+        c = c[::-1].copy()
+    elif args.order == "shuffled":
+        c = c[np.random.default_rng(1234).permutation(n)]
     params_h = torch.from_numpy(quartic_params(c)).pin_memory()
     abs_h = torch.ones(n, dtype=torch.float64).pin_memory()
     meta_h = torch.zeros(n, dtype=torch.float64).pin_memory()
@@ -186,7 +195,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
-        batch.launch_bounce(_lib.POT_POLY4, d_params, d_abs, d_meta, opts, out)
+        batch.launch_bounce(_lib.POT_POLY4, d_params, d_abs, d_meta, opts, out, schedule=args.schedule)
 
     def barrier():
         if world > 1:
@@ -227,7 +236,7 @@ def main():
         dp = params_h.to(dev, non_blocking=True)
         da = abs_h.to(dev, non_blocking=True)
         dm = meta_h.to(dev, non_blocking=True)
-        batch.launch_bounce(_lib.POT_POLY4, dp, da, dm, opts, out)
+        batch.launch_bounce(_lib.POT_POLY4, dp, da, dm, opts, out, schedule=args.schedule)
         S_h.copy_(out["S"], non_blocking=True)
         st_h.copy_(out["status"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -280,7 +289,9 @@ def main():
         "metric": "bounce actions/sec", "value": value, "unit": "bounces/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "instances_per_gpu": n, "alpha": wl["alpha"],
+        "config": {"workload": wl["name"], "instances_per_gpu": n, "alpha": wl["alpha"], "order": args.order,
+                   "schedule": "work-sorted (setup kernel + device argsort + solve kernel, all inside the timed "
+                               "step)" if sorted_sched else "natural",
                    "timing": "CUDA events around each step's kernel on torch's current stream; 256 MiB L2 flush "
                              "between timed iterations", "wall_s_timed_region": t_wall},
         "solved_fraction": float((status <= 1).mean()),
@@ -292,7 +303,7 @@ def main():
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "bytes_per_bounce": BYTES_PER_BOUNCE}},
         "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps * (2 if sorted_sched else 1),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:

@@ -11,13 +11,14 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F = 0, 1, 2
 NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6}
 (ST_CONVERGED, ST_XTOL, ST_STABLE, ST_NO_BARRIER, ST_RMAX, ST_DRMIN, ST_STEP_UNDERFLOW, ST_NONFINITE,
  ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN) = range(11)
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
+           "ctb_bounce_setup",
            "ctb_jspline", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
 
 
@@ -30,6 +31,11 @@ class Opts(C.Structure):
     _fields_ = [("xtol", C.c_double), ("phitol", C.c_double), ("thinCutoff", C.c_double), ("rmin", C.c_double),
                 ("rmax", C.c_double), ("phi_eps", C.c_double), ("xguess", C.c_double), ("npoints", C.c_int32),
                 ("max_interior_pts", C.c_int32), ("alpha", C.c_int32), ("block_threads", C.c_int32)]
+
+
+class BounceIn(C.Structure):
+    _fields_ = [("d_params", C.c_void_p), ("d_phi_abs", C.c_void_p), ("d_phi_meta", C.c_void_p),
+                ("d_phi_bar", C.c_void_p), ("d_rscale", C.c_void_p), ("d_order", C.c_void_p), ("n", C.c_int64)]
 
 
 class BounceOut(C.Structure):
@@ -66,8 +72,11 @@ def load():
     lib.ctb_status_string.argtypes = [C.c_int]
     lib.ctb_device_ok.restype = C.c_int
     lib.ctb_bounce_batch.restype = C.c_int
-    lib.ctb_bounce_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Opts),
-                                     C.POINTER(JTable), C.POINTER(JTable), C.POINTER(BounceOut), C.c_void_p]
+    lib.ctb_bounce_batch.argtypes = [C.c_int, C.POINTER(BounceIn), C.POINTER(Opts), C.POINTER(JTable),
+                                     C.POINTER(JTable), C.POINTER(BounceOut), C.c_void_p]
+    lib.ctb_bounce_setup.restype = C.c_int
+    lib.ctb_bounce_setup.argtypes = [C.c_int, C.POINTER(BounceIn), C.POINTER(JTable), C.POINTER(JTable),
+                                     C.POINTER(BounceOut), C.c_void_p, C.c_void_p]
     lib.ctb_jspline.restype = C.c_int
     lib.ctb_jspline.argtypes = [C.POINTER(JTable), C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ctb_vtot_model1.restype = C.c_int

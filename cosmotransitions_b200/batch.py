@@ -47,25 +47,82 @@ def _as_device(torch, x, device, shape=None):
     return t.contiguous()
 
 
-def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=None, stream=None):
-    """Lowest-level call: device tensors in, device tensors (pre-allocated dict `out`) filled.
-    Asynchronous on `stream` (default: torch's current stream)."""
-    torch = _lib.require_cuda()
-    lib = _lib.load()
-    n = d_phi_abs.numel()
-    dev = d_phi_abs.device
-    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+def _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar=None, rscale=None, order=None):
+    bi = _lib.BounceIn()
+    bi.d_params, bi.d_phi_abs, bi.d_phi_meta = d_params.data_ptr(), d_phi_abs.data_ptr(), d_phi_meta.data_ptr()
+    bi.d_phi_bar = phi_bar.data_ptr() if phi_bar is not None else None
+    bi.d_rscale = rscale.data_ptr() if rscale is not None else None
+    bi.d_order = order.data_ptr() if order is not None else None
+    bi.n = d_phi_abs.numel()
+    return bi
+
+
+def _bounce_out(out, profiles=None):
     bo = _lib.BounceOut()
     for k in _F64_OUT + _I32_OUT:
         setattr(bo, "d_" + k, out[k].data_ptr() if k in out else None)
     if profiles is not None:
         bo.d_prof_R, bo.d_prof_Phi, bo.d_prof_dPhi = (profiles[k].data_ptr() for k in ("R", "Phi", "dPhi"))
         bo.prof_stride = profiles["R"].shape[1]
+    return bo
+
+
+# batches at least this large are solved in work-sorted order (two extra tiny launches + a sort)
+SORT_THRESHOLD = 4096
+
+
+def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=None, stream=None, schedule="auto",
+                  phi_bar=None, rscale=None):
+    """Lowest-level call: device tensors in, device tensors (pre-allocated dict `out`) filled.
+    Asynchronous on `stream` (default: torch's current stream).
+
+    schedule: "natural" = thread t solves instance t;  "sorted" = a setup kernel computes phi_bar,
+    rscale and a work predictor per instance, the instances are sorted heavy-first (so that lanes of a
+    warp follow similar trajectories and the longest-running warps start first), and the solve kernel
+    walks that permutation.  Results do not depend on the schedule (instances are independent).
+    "auto" = sorted for batches of SORT_THRESHOLD or more."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    n = d_phi_abs.numel()
+    dev = d_phi_abs.device
+    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    jb, jf = (tabs.jb, tabs.jf) if tabs else (None, None)
+    bo = _bounce_out(out, profiles)
     st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    if schedule == "auto":
+        schedule = "sorted" if n >= SORT_THRESHOLD else "natural"
     with torch.cuda.device(dev):
-        _lib.check(lib.ctb_bounce_batch(kind, d_params.data_ptr(), d_phi_abs.data_ptr(), d_phi_meta.data_ptr(), n,
-                                        opts, tabs.jb if tabs else None, tabs.jf if tabs else None, bo, st),
-                   "ctb_bounce_batch")
+        order = None
+        if schedule == "sorted":
+            key = torch.empty(n, dtype=torch.float64, device=dev)
+            bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale)
+            _lib.check(lib.ctb_bounce_setup(kind, bi, jb, jf, bo, key.data_ptr(), st), "ctb_bounce_setup")
+            order = torch.argsort(key, descending=True).to(torch.int32)
+            # the solve kernel reuses what the setup kernel found (NaN where __init__ failed: the solve
+            # kernel then re-derives the same PotentialError status)
+            phi_bar, rscale = out["phi_bar"], out["rscale"]
+        elif schedule != "natural":
+            raise ValueError("schedule must be 'auto', 'sorted' or 'natural'")
+        bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale, order)
+        _lib.check(lib.ctb_bounce_batch(kind, bi, opts, jb, jf, bo, st), "ctb_bounce_batch")
+
+
+def bounce_setup(kind, params, phi_absMin, phi_metaMin, phi_bar=None, rscale=None):
+    """SingleFieldInstanton.__init__ for one instance: returns (status, phi_bar, rscale)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_params = _as_device(torch, params, dev).reshape(-1, _lib.NPARAM[kind])
+    n = d_params.shape[0]
+    d_abs, d_meta = _as_device(torch, phi_absMin, dev, (n,)), _as_device(torch, phi_metaMin, dev, (n,))
+    d_bar = _as_device(torch, [phi_bar], dev, (n,)) if phi_bar is not None else None
+    d_rs = _as_device(torch, [rscale], dev, (n,)) if rscale is not None else None
+    out = alloc_out(torch, n, dev)
+    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    _lib.check(lib.ctb_bounce_setup(kind, _bounce_in(d_params, d_abs, d_meta, d_bar, d_rs),
+                                    tabs.jb if tabs else None, tabs.jf if tabs else None, _bounce_out(out), None,
+                                    torch.cuda.current_stream(dev).cuda_stream), "ctb_bounce_setup")
+    return int(out["status"][0]), float(out["phi_bar"][0]), float(out["rscale"][0])
 
 
 def alloc_out(torch, n, device):
@@ -75,13 +132,16 @@ def alloc_out(torch, n, device):
 
 
 def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, phi_eps=1e-3, device=None,
-                      return_profiles=False, block_threads=0, **findProfile_knobs):
+                      return_profiles=False, block_threads=0, schedule="auto", phi_bar=None, rscale=None,
+                      **findProfile_knobs):
     """Solve N independent bounces.
 
     potential_kind : one of _lib.POT_* (or a DevicePotential subclass / instance, whose kind is used)
     params         : [N, K] tensor/array of potential coefficients (K = _lib.NPARAM[kind])
     phi_absMin, phi_metaMin : [N] (or scalars, broadcast)
     alpha, phi_eps : as SingleFieldInstanton.__init__ (tunneling1D.py:128-130)
+    phi_bar, rscale : optional [N] overrides, as in __init__ (NaN entries = compute)
+    schedule       : "auto" | "sorted" | "natural" (see launch_bounce); does not change results
     findProfile_knobs : xguess, xtol, phitol, thinCutoff, npoints, rmin, rmax, max_interior_pts
                         with the reference's defaults (tunneling1D.py:615-617)
 
@@ -108,8 +168,10 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
     if return_profiles:
         cap = profile_capacity(opts)
         prof = {k: torch.full((n, cap), float("nan"), dtype=torch.float64, device=device) for k in ("R", "Phi", "dPhi")}
+    d_bar = _as_device(torch, phi_bar, device, (n,)) if phi_bar is not None else None
+    d_rs = _as_device(torch, rscale, device, (n,)) if rscale is not None else None
     if n:
-        launch_bounce(kind, d_params, d_abs, d_meta, opts, out, prof)
+        launch_bounce(kind, d_params, d_abs, d_meta, opts, out, prof, schedule=schedule, phi_bar=d_bar, rscale=d_rs)
     if prof is not None:
         out.update(prof)
     if on_host:

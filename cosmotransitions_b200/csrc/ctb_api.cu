@@ -123,28 +123,38 @@ CTB_API int ctb_device_ok(void)
     return (p.major == 10) ? CTB_OK : CTB_ERR_NO_DEVICE;
 }
 
-CTB_API int ctb_bounce_batch(int pot_kind, const double *d_params, const double *d_phi_abs, const double *d_phi_meta,
-                     int64_t n, const ctb_opts *o, const ctb_jtable *jb, const ctb_jtable *jf,
-                     const ctb_bounce_out *out, void *stream)
+static int fill_args(BounceArgs &a, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
+                     const ctb_bounce_out *out)
 {
-    if (!o || !out || n < 0) return CTB_ERR_BAD_ARG;
-    if (n == 0) return CTB_OK;
-    if (!d_params || !d_phi_abs || !d_phi_meta) return CTB_ERR_BAD_ARG;
+    if (!in || !out || in->n < 0) return CTB_ERR_BAD_ARG;
+    if (in->n > 0 && (!in->d_params || !in->d_phi_abs || !in->d_phi_meta)) return CTB_ERR_BAD_ARG;
+    if (in->n > 2147483647LL && in->d_order) return CTB_ERR_UNSUPPORTED;
+    a.params = in->d_params; a.phi_abs = in->d_phi_abs; a.phi_meta = in->d_phi_meta; a.n = in->n;
+    a.phi_bar_in = in->d_phi_bar; a.rscale_in = in->d_rscale; a.order = in->d_order; a.work_key = nullptr;
+    a.jb = to_jtab(jb); a.jf = to_jtab(jf);
+    a.out = *out;
+    return CTB_OK;
+}
+
+CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_opts *o, const ctb_jtable *jb,
+                             const ctb_jtable *jf, const ctb_bounce_out *out, void *stream)
+{
+    BounceArgs a;
+    if (!o) return CTB_ERR_BAD_ARG;
+    int rc = fill_args(a, in, jb, jf, out);
+    if (rc) return rc;
+    if (a.n == 0) return CTB_OK;
     if (o->npoints < 2 || o->npoints > 4096) return CTB_ERR_UNSUPPORTED;
     if (out->d_prof_R) {
         if (!out->d_prof_Phi || !out->d_prof_dPhi) return CTB_ERR_BAD_ARG;
         int64_t maxint = o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts;
         if (out->prof_stride < o->npoints + maxint) return CTB_ERR_BAD_ARG;
     }
-    BounceArgs a;
-    a.params = d_params; a.phi_abs = d_phi_abs; a.phi_meta = d_phi_meta; a.n = n;
     a.knobs.xtol = o->xtol; a.knobs.phitol = o->phitol; a.knobs.thinCutoff = o->thinCutoff; a.knobs.rmin = o->rmin;
     a.knobs.rmax = o->rmax; a.knobs.phi_eps = o->phi_eps; a.knobs.xguess = o->xguess;
     a.knobs.npoints = o->npoints; a.knobs.max_interior_pts = o->max_interior_pts;
-    a.jb = to_jtab(jb); a.jf = to_jtab(jf);
-    a.out = *out;
     cudaStream_t st = (cudaStream_t)stream;
-    int block = o->block_threads ? o->block_threads : 64;
+    int block = o->block_threads ? o->block_threads : 128;
     switch (pot_kind) {
     case CTB_POT_POLY4: return ctb::launch_bounce_poly4(a, o->alpha, block, st);
     case CTB_POT_MODEL1_LINE:
@@ -153,6 +163,28 @@ CTB_API int ctb_bounce_batch(int pot_kind, const double *d_params, const double 
     case CTB_POT_MODEL1F:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
         return ctb::launch_bounce_model1f(a, o->alpha, block, st);
+    }
+    return CTB_ERR_UNSUPPORTED;
+}
+
+CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
+                             const ctb_bounce_out *out, double *d_work_key, void *stream)
+{
+    BounceArgs a;
+    int rc = fill_args(a, in, jb, jf, out);
+    if (rc) return rc;
+    if (a.n == 0) return CTB_OK;
+    a.work_key = d_work_key;
+    a.knobs = Knobs{};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pot_kind) {
+    case CTB_POT_POLY4: return ctb::launch_setup_poly4(a, st);
+    case CTB_POT_MODEL1_LINE:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        return ctb::launch_setup_model1_line(a, st);
+    case CTB_POT_MODEL1F:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        return ctb::launch_setup_model1f(a, st);
     }
     return CTB_ERR_UNSUPPORTED;
 }

@@ -8,13 +8,16 @@
 #define CTB_MAX_BLOCK 128
 #endif
 #ifndef CTB_MIN_BLOCKS
-#define CTB_MIN_BLOCKS 1
+#define CTB_MIN_BLOCKS 3
 #endif
 
 namespace ctb {
 
 struct BounceArgs {
     const double *params, *phi_abs, *phi_meta;
+    const double *phi_bar_in, *rscale_in; // optional overrides (NaN entry = compute)
+    const int32_t *order;                 // optional permutation: thread t solves instance order[t]
+    double *work_key;                     // setup kernel only
     int64_t n;
     Knobs knobs;
     JTab jb, jf;
@@ -24,23 +27,29 @@ struct BounceArgs {
 // One thread = one instance.  Adjacent instances (adjacent model parameters) share a warp, so that
 // lanes follow similar trajectories; blocks are small so that the hardware block scheduler balances
 // the 4x spread in work per instance across the 148 SMs.
-template <class Pot, int ALPHA>
+template <class Pot, int ALPHA, bool PROFILE>
 __global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(const BounceArgs a)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    // every lane of every warp runs the solver (it votes warp-wide); lanes past the end of the batch
+    // carry a dummy instance that is never integrated
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < a.n;
+    const int64_t i = valid ? (a.order ? (int64_t)a.order[t] : t) : 0;
     Sfi<Pot, ALPHA> s;
     s.pot.load(a.params + i * Pot::nparam, &a.jb, &a.jf);
     s.phi_abs = a.phi_abs[i];
     s.phi_meta = a.phi_meta[i];
     InstanceResult r;
     ProfileSink sink{nullptr, nullptr, nullptr};
-    if (a.out.d_prof_R) {
+    if (PROFILE) {
         sink.R = a.out.d_prof_R + i * a.out.prof_stride;
         sink.Phi = a.out.d_prof_Phi + i * a.out.prof_stride;
         sink.dPhi = a.out.d_prof_dPhi + i * a.out.prof_stride;
     }
-    solve_instance<Pot, ALPHA>(s, a.knobs, r, sink);
+    const double qn = nan("");
+    solve_instance<Pot, ALPHA, PROFILE>(s, a.knobs, valid, a.phi_bar_in ? a.phi_bar_in[i] : qn,
+                                        a.rscale_in ? a.rscale_in[i] : qn, r, sink);
+    if (!valid) return;
     if (a.out.d_S) a.out.d_S[i] = r.S;
     if (a.out.d_phi0) a.out.d_phi0[i] = r.phi0;
     if (a.out.d_r0) a.out.d_r0[i] = r.r0;
@@ -54,14 +63,41 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(c
     if (a.out.d_n_points) a.out.d_n_points[i] = r.n_points;
 }
 
+// __init__ only: phi_bar, rscale, status (0 / STABLE / NO_BARRIER) and the work predictor.
+template <class Pot>
+__global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Pot pot;
+    pot.load(a.params + i * Pot::nparam, &a.jb, &a.jf);
+    const double pa = a.phi_abs[i], pm = a.phi_meta[i];
+    double phi_bar = a.phi_bar_in ? a.phi_bar_in[i] : nan(""), rscale = a.rscale_in ? a.rscale_in[i] : nan("");
+    int st = sfi_init(pot, pa, pm, pot.V(pm), phi_bar, rscale);
+    if (st) rscale = nan("");
+    if (a.out.d_phi_bar) a.out.d_phi_bar[i] = phi_bar;
+    if (a.out.d_rscale) a.out.d_rscale[i] = rscale;
+    if (a.out.d_status) a.out.d_status[i] = st;
+    if (a.work_key) a.work_key[i] = st ? -INFINITY : work_key(pa, pm, phi_bar);
+}
+
+template <class Pot>
+int launch_setup_any(const BounceArgs &a, cudaStream_t st)
+{
+    setup_kernel<Pot><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
 
 template <class Pot>
 int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st)
 {
     if (block < 32 || block > CTB_MAX_BLOCK || (block & 31)) return CTB_ERR_UNSUPPORTED;
     unsigned grid = (unsigned)((a.n + block - 1) / block);
-    if (alpha == 2) bounce_kernel<Pot, 2><<<grid, block, 0, st>>>(a);
-    else if (alpha == 3) bounce_kernel<Pot, 3><<<grid, block, 0, st>>>(a);
+    const bool prof = a.out.d_prof_R != nullptr;
+    if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false><<<grid, block, 0, st>>>(a);
+    else if (alpha == 3 && !prof) bounce_kernel<Pot, 3, false><<<grid, block, 0, st>>>(a);
+    else if (alpha == 2) bounce_kernel<Pot, 2, true><<<grid, block, 0, st>>>(a);
+    else if (alpha == 3) bounce_kernel<Pot, 3, true><<<grid, block, 0, st>>>(a);
     else return CTB_ERR_UNSUPPORTED;
     return (int)cudaGetLastError();
 }
@@ -69,5 +105,8 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
 int launch_bounce_poly4(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_bounce_model1_line(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_bounce_model1f(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+int launch_setup_poly4(const BounceArgs &a, cudaStream_t st);
+int launch_setup_model1_line(const BounceArgs &a, cudaStream_t st);
+int launch_setup_model1f(const BounceArgs &a, cudaStream_t st);
 
 } // namespace ctb

@@ -1,0 +1,9 @@
+// TUNING ONLY (not part of the product build): stubs for the thermal-potential launchers so that
+// poly4-only experiment builds link quickly.
+#include "ctb_bounce.cuh"
+namespace ctb {
+int launch_bounce_model1_line(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_bounce_model1f(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_setup_model1_line(const BounceArgs &, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_setup_model1f(const BounceArgs &, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+} // namespace ctb

@@ -71,6 +71,7 @@ struct PotPoly4 {
         v = __dadd_rn(c1, __dmul_rn(x, v));
         return __dadd_rn(c0, __dmul_rn(x, v));
     }
+    CTB_DEV double V_quad(double x) const { return c0 + x * (c1 + x * (c2 + x * (c3 + x * c4))); } // integrand only
     CTB_DEV double dV(double x) const { return c1 + x * (2 * c2 + x * (3 * c3 + x * 4 * c4)); }
     CTB_DEV double d2V(double x) const { return 2 * c2 + x * (6 * c3 + x * 12 * c4); }
 };
@@ -116,6 +117,7 @@ struct PotModel1Line {
     {
         return vtot_model1(l1, l2, mu2, Y1, Y2, nb, rs, v2, jb, x0 + phi * n0, x1 + phi * n1, T);
     }
+    CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
 
 struct PotModel1F {
@@ -143,6 +145,7 @@ struct PotModel1F {
         r += yt * T4 / (2 * CTB_PI * CTB_PI);
         return r;
     }
+    CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -159,6 +162,20 @@ CTB_DEV double rcp_fast(double x)
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
+    return y;
+}
+
+// x^(-1/5) for x in (1e-5, 1]: FP32 seed (ex2/lg2 MUFU, ~1e-6 relative) + two Newton steps on
+// y -> y (6 - x y^5) / 5 in FP64 (quadratic: 1e-6 -> 1e-12 -> rounding).  Replaces pow(errmax, -0.2).
+CTB_DEV double inv_fifth_root(double x)
+{
+    double y = (double)exp2f(-0.2f * __log2f((float)x));
+    double y2 = y * y;
+    double y5 = y2 * y2 * y;
+    y = y * fma(-0.2 * x, y5, 1.2);
+    y2 = y * y;
+    y5 = y2 * y2 * y;
+    y = y * fma(-0.2 * x, y5, 1.2);
     return y;
 }
 
@@ -290,14 +307,16 @@ CTB_DEV double fminbound(F func, double x1, double x2, double xatol)
 // scipy.integrate.simpson on a non-uniform grid, as a STREAM: points are fed in order and only the
 // last three are kept.  N (total number of points) must be known up front.   T1D:787 + scipy
 struct SimpsonStream {
-    double xa, ya, xb, yb, xc, yc; // oldest .. newest
+    // (xa, ya): first point of the open pair; (xb, yb): its middle point; (xp, yp): middle point of
+    // the previous pair (needed by the even-N end correction)
+    double xa, ya, xb, yb, xp, yp;
     double sum;
     int idx, nbasic;
     CTB_DEV void init(int N)
     {
         sum = 0.0; idx = 0;
         nbasic = (N & 1) ? N : N - 1; // even N: composite rule on the first N-1 points
-        xa = ya = xb = yb = xc = yc = 0.0;
+        xa = ya = xb = yb = xp = yp = 0.0;
     }
     static CTB_DEV double pair(double x0, double y0, double x1, double y1, double x2, double y2)
     {
@@ -315,15 +334,20 @@ struct SimpsonStream {
     }
     CTB_DEV void feed(double x, double y)
     {
-        xa = xb; ya = yb; xb = xc; yb = yc; xc = x; yc = y;
-        if (idx >= 2 && !(idx & 1) && idx < nbasic) sum += pair(xa, ya, xb, yb, xc, yc);
+        if (idx & 1) { // odd index: middle (or, for even N, the very last) point
+            xb = x; yb = y;
+        } else {
+            if (idx >= 2 && idx < nbasic) { sum += pair(xa, ya, xb, yb, x, y); xp = xb; yp = yb; }
+            xa = x; ya = y;
+        }
         idx++;
     }
     CTB_DEV double finish(int N) const
     {
         if (N & 1) return sum;
-        if (N == 2) return 0.5 * (xc - xb) * (yc + yb);
-        double h0 = xb - xa, h1 = xc - xb;
+        if (N == 2) return 0.5 * (xb - xa) * (yb + ya);
+        // points N-3, N-2, N-1 = (xp, yp), (xa, ya), (xb, yb)
+        double h0 = xa - xp, h1 = xb - xa;
         double num, den, al, be, et;
         num = 2 * h1 * h1 + 3 * h0 * h1; den = 6 * (h1 + h0);
         al = (den != 0) ? num / den : 0.0;
@@ -331,7 +355,7 @@ struct SimpsonStream {
         be = (den != 0) ? num / den : 0.0;
         num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1);
         et = (den != 0) ? num / den : 0.0;
-        return sum + (al * yc + be * yb - et * ya);
+        return sum + (al * yb + be * ya - et * yp);
     }
 };
 
@@ -347,6 +371,65 @@ struct ProfileSink { // optional Profile1D dump
 };
 
 enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
+
+// T1D:294-373  phi(r), phi'(r) of the linearised equation of motion around phi0.
+// nu = (ALPHA-1)/2: closed forms for nu = 1/2, I0/I1/J0/J1 + recurrences for nu = 1.
+// ONE out-of-line copy per ALPHA: the transcendental bodies (exp, sinh, sincos, Bessel) are large and
+// every call site sharing them keeps the kernel's hot code inside the instruction cache.
+template <int ALPHA>
+__device__ __noinline__ double2 exact_solution(double r, double phi0, double dv, double d2v)
+{
+    double phi, dphi;
+    double beta = sqrt(fabs(d2v));
+    double z = beta * r;
+    if (z < 1e-2) {
+        const double s = (d2v > 0) ? 1.0 : -1.0;
+        // Gamma(k+1) Gamma(k+1+nu), k = 1..3 ; Gamma(nu+1)
+        const double G1 = (ALPHA == 2) ? 1.3293403881791370 : 2.0;
+        const double G2 = (ALPHA == 2) ? 2.0 * 3.3233509704478426 : 12.0;
+        const double G3 = (ALPHA == 2) ? 6.0 * 11.631728396567448 : 144.0;
+        const double g = (ALPHA == 2) ? 0.88622692545275801 : 1.0;
+        double h2 = (0.5 * z) * (0.5 * z);
+        double t1 = s / G1, t2 = h2 / G2, t3 = h2 * h2 * s / G3;
+        double p = t1 + t2 + t3;
+        double dp = t1 * 2 + t2 * 4 + t3 * 6;
+        phi = p * (0.25 * g * (r * r) * dv * s) + phi0;
+        dphi = dp * (0.25 * g * r * dv * s);
+        return make_double2(phi, dphi);
+    }
+    const bool modified = d2v > 0;
+    double ratio = dv / d2v;
+    if (ALPHA == 2) {
+        // Gamma(3/2) (z/2)^(-1/2) I_{1/2}(z) = sinh(z)/z ; J: sin(z)/z
+        double sh, ch;
+        if (modified) {
+            if (z < 1.0) { sh = sinh(z); ch = cosh(z); }
+            else if (z < 700.0) { // one exp for both; no cancellation for z >= 1
+                double ez = exp(z), emz = rcp_fast(ez);
+                sh = 0.5 * (ez - emz); ch = 0.5 * (ez + emz);
+            } else { double e2 = exp(0.5 * z); sh = (0.5 * e2) * e2; ch = sh; } // overflows with I_nu
+        } else {
+            sincos(z, &sh, &ch);
+        }
+        phi = (sh / z - 1.0) * ratio + phi0;
+        dphi = ((ch - sh / z) / r) * ratio;
+    } else {
+        double hp = 2.0 / z; // (z/2)^-1, Gamma(2) = 1
+        double Inu, Im, Ip, sg;
+        if (modified) {
+            double i0 = cyl_bessel_i0(z), i1 = cyl_bessel_i1(z);
+            Inu = i1; Im = i0; Ip = i0 - 2.0 * i1 / z; sg = 1.0;
+        } else {
+            double j0_ = j0(z), j1_ = j1(z);
+            Inu = j1_; Im = j0_; Ip = 2.0 * j1_ / z - j0_; sg = -1.0;
+        }
+        phi = (hp * Inu - 1) * dv / d2v + phi0;
+        double d = -1.0 * (hp / r) * Inu;
+        d += hp * 0.5 * beta * (Im + sg * Ip);
+        dphi = d * ratio;
+    }
+    return make_double2(phi, dphi);
+}
 
 template <class Pot, int ALPHA>
 struct Sfi {
@@ -389,78 +472,13 @@ struct Sfi {
         return dv;
     }
 
-    // T1D:294-373.  nu = (ALPHA-1)/2: closed forms for nu = 1/2, I0/I1/J0/J1 + recurrences for nu = 1.
-    template <bool WANT_DPHI>
-    CTB_DEV void exact_solution(double r, double phi0, double dv, double d2v, double &phi, double &dphi) const
+    // T1D:377-434, given dV_from_absMin(delta_phi0) and d2V(phi0); returns 0 or a CTB_ST_* error
+    CTB_DEV int initial_conditions(double delta_phi0, double dv, double d2v, double rmin, double cutoff, double &r0,
+                                   double &phi_r0, double &dphi_r0) const
     {
-        double beta = sqrt(fabs(d2v));
-        double z = beta * r;
-        if (z < 1e-2) {
-            const double s = (d2v > 0) ? 1.0 : -1.0;
-            // Gamma(k+1) Gamma(k+1+nu), k = 1..3 ; Gamma(nu+1)
-            const double G1 = (ALPHA == 2) ? 1.3293403881791370 : 2.0;
-            const double G2 = (ALPHA == 2) ? 2.0 * 3.3233509704478426 : 12.0;
-            const double G3 = (ALPHA == 2) ? 6.0 * 11.631728396567448 : 144.0;
-            const double g = (ALPHA == 2) ? 0.88622692545275801 : 1.0;
-            double h2 = (0.5 * z) * (0.5 * z);
-            double t1 = s / G1, t2 = h2 / G2, t3 = h2 * h2 * s / G3;
-            double p = t1 + t2 + t3;
-            double dp = t1 * 2 + t2 * 4 + t3 * 6;
-            phi = p * (0.25 * g * (r * r) * dv * s) + phi0;
-            dphi = dp * (0.25 * g * r * dv * s);
-            return;
-        }
-        const bool modified = d2v > 0;
-        double ratio = dv / d2v;
-        if (ALPHA == 2) {
-            // Gamma(3/2) (z/2)^(-1/2) I_{1/2}(z) = sinh(z)/z ; J: sin(z)/z
-            double sh, ch;
-            if (modified) {
-                if (z < 1.0) { sh = sinh(z); ch = cosh(z); }
-                else if (z < 700.0) { // one exp for both; no cancellation for z >= 1
-                    double ez = exp(z), emz = rcp_fast(ez);
-                    sh = 0.5 * (ez - emz); ch = 0.5 * (ez + emz);
-                } else { double e2 = exp(0.5 * z); sh = (0.5 * e2) * e2; ch = sh; } // overflows with I_nu
-                phi = (sh / z - 1.0) * ratio + phi0;
-                if (WANT_DPHI) dphi = ((ch - sh / z) / r) * ratio;
-            } else {
-                sincos(z, &sh, &ch);
-                phi = (sh / z - 1.0) * ratio + phi0;
-                if (WANT_DPHI) dphi = ((ch - sh / z) / r) * ratio;
-            }
-        } else {
-            double hp = 2.0 / z; // (z/2)^-1, Gamma(2) = 1
-            double Inu, Im, Ip;
-            if (modified) {
-                double i0 = cyl_bessel_i0(z), i1 = cyl_bessel_i1(z);
-                Inu = i1; Im = i0; Ip = i0 - 2.0 * i1 / z;
-                phi = (hp * Inu - 1) * dv / d2v + phi0;
-                if (WANT_DPHI) {
-                    double d = -1.0 * (hp / r) * Inu;
-                    d += hp * 0.5 * beta * (Im + Ip);
-                    dphi = d * ratio;
-                }
-            } else {
-                double j0_ = j0(z), j1_ = j1(z);
-                Inu = j1_; Im = j0_; Ip = 2.0 * j1_ / z - j0_;
-                phi = (hp * Inu - 1) * dv / d2v + phi0;
-                if (WANT_DPHI) {
-                    double d = -1.0 * (hp / r) * Inu;
-                    d += hp * 0.5 * beta * (Im - Ip);
-                    dphi = d * ratio;
-                }
-            }
-        }
-    }
-
-    // T1D:377-434; returns 0 or a CTB_ST_* error
-    CTB_DEV int initial_conditions(double delta_phi0, double rmin, double cutoff, double &r0, double &phi_r0,
-                                   double &dphi_r0) const
-    {
-        double phi0 = phi_abs + delta_phi0;
-        double dv = dV_from_absMin(delta_phi0);
-        double d2v = d2V(phi0);
-        exact_solution<true>(rmin, phi0, dv, d2v, phi_r0, dphi_r0);
+        const double phi0 = phi_abs + delta_phi0;
+        double2 e = exact_solution<ALPHA>(rmin, phi0, dv, d2v);
+        phi_r0 = e.x; dphi_r0 = e.y;
         r0 = rmin;
         if (fabs(phi_r0 - phi_abs) > fabs(cutoff)) return 0;
         if (isnan(dphi_r0) || isnan(delta_phi0) || sgn(dphi_r0) != sgn(delta_phi0)) return 0;
@@ -468,23 +486,18 @@ struct Sfi {
         while (isfinite(r)) {
             rlast = r;
             r *= 10;
-            double p, dp;
-            exact_solution<false>(r, phi0, dv, d2v, p, dp);
+            double p = exact_solution<ALPHA>(r, phi0, dv, d2v).x;
             if (fabs(p - phi_abs) > fabs(cutoff)) break;
         }
         int err;
         const double pa = phi_abs, ac = fabs(cutoff);
-        double rr = brentq(
-            [&](double r_) {
-                double p, dp;
-                exact_solution<false>(r_, phi0, dv, d2v, p, dp);
-                return fabs(p - pa) - ac;
-            },
-            rlast, r, err);
+        double rr = brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, phi0, dv, d2v).x - pa) - ac; },
+                           rlast, r, err);
         if (err == 2) return CTB_ST_NONFINITE;
         if (err == 1) return CTB_ST_BRENT_SIGN;
         r0 = rr;
-        exact_solution<true>(r0, phi0, dv, d2v, phi_r0, dphi_r0);
+        e = exact_solution<ALPHA>(r0, phi0, dv, d2v);
+        phi_r0 = e.x; dphi_r0 = e.y;
         return 0;
     }
 
@@ -537,7 +550,7 @@ struct Sfi {
             double m0 = (a0 < b0) ? a0 : b0, m1 = (a1 < b1) ? a1 : b1;
             errmax = (m0 > m1) ? m0 : m1;
             // numpy min/max propagate NaN; nan_to_num: NaN -> 0, +inf -> DBL_MAX
-            if (isnan(a0) || isnan(b0) || isnan(a1) || isnan(b1)) errmax = 0.0;
+            if (isnan((a0 + b0) + (a1 + b1))) errmax = 0.0; // all four are >= 0: the sum is NaN iff one is
             else if (isinf(errmax)) errmax = 1.7976931348623157e308;
             if (errmax < 1.0) break;
             double dttemp = 0.9 * dt * rsqrt(sqrt(errmax));
@@ -545,7 +558,7 @@ struct Sfi {
             else dt = (dt * .1 < dttemp) ? dt * .1 : dttemp;
             if (t + dt == t) return CTB_ST_STEP_UNDERFLOW;
         }
-        if (errmax > 1.89e-4) dtnext = 0.9 * dt * exp2(-.2 * log2(errmax));
+        if (errmax > 1.89e-4) dtnext = 0.9 * dt * inv_fifth_root(errmax);
         else dtnext = 5 * dt;
         return 0;
     }
@@ -566,11 +579,8 @@ struct Cubic {
         A3 = (y1 - y0) + 3.0 * (Y1 - Y2);
         Yend = y1;
     }
-    CTB_DEV double operator()(double t) const
-    {
-        double v = fma(t, fma(t, fma(t, A3, A2), A1), A0);
-        return (t == 1.0) ? Yend : v; // exact end point, as in the Bezier form
-    }
+    CTB_DEV double operator()(double t) const { return fma(t, fma(t, fma(t, A3, A2), A1), A0); }
+    CTB_DEV double at(double t) const { return (t == 1.0) ? Yend : (*this)(t); } // exact end point (root bracketing)
 };
 
 struct InstanceResult {
@@ -578,23 +588,13 @@ struct InstanceResult {
     int status, n_shots, n_rkck, n_points;
 };
 
-// __init__ + findProfile + findAction for one instance.                        T1D:128-149, 615-791
-template <class Pot, int ALPHA>
-__device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, InstanceResult &res, const ProfileSink &sink)
+// SingleFieldInstanton.__init__ (T1D:128-149): metastability check, findBarrierLocation (T1D:203-226)
+// and findRScale (T1D:228-285).  phi_bar / rscale come in as NaN ("None") or as overrides.
+template <class Pot>
+__device__ int sfi_init(const Pot &pot, double phi_abs, double phi_meta, double V_meta, double &phi_bar, double &rscale)
 {
-    const double qnan = nan("");
-    res.S = res.phi0 = res.r0 = res.rf = res.x = res.phi_bar = res.rscale = qnan;
-    res.n_shots = res.n_rkck = res.n_points = 0;
-    s.n_rkck = 0;
-    s.phi_eps = 0.0;
-    const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
-    const Pot &pot = s.pot;
-
-    // ---- __init__ : T1D:128-149 ----
-    const double V_meta = pot.V(phi_meta);
-    if (V_meta <= pot.V(phi_abs)) { res.status = CTB_ST_STABLE; return; }
-    double phi_bar;
-    { // findBarrierLocation T1D:203-226
+    if (V_meta <= pot.V(phi_abs)) { phi_bar = rscale = nan(""); return CTB_ST_STABLE; }
+    if (isnan(phi_bar)) { // findBarrierLocation
         double phi_tol = fabs(phi_meta - phi_abs) * 1e-12;
         double phi1 = phi_meta, phi2 = phi_abs, phi0 = 0.5 * (phi1 + phi2);
         while (fabs(phi1 - phi2) > phi_tol) {
@@ -604,22 +604,65 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, InstanceResul
         }
         phi_bar = phi0;
     }
-    res.phi_bar = phi_bar;
-    double rscale;
-    { // findRScale T1D:228-285
+    if (isnan(rscale)) { // findRScale
         double phi_tol = fabs(phi_bar - phi_meta) * 1e-6;
         double x1 = fmin(phi_bar, phi_meta), x2 = fmax(phi_bar, phi_meta);
         double top = fminbound([&](double x) { return -pot.V(x); }, x1, x2, phi_tol);
-        if (top + phi_tol > x2 || top - phi_tol < x1) { res.status = CTB_ST_NO_BARRIER; return; }
+        if (top + phi_tol > x2 || top - phi_tol < x1) return CTB_ST_NO_BARRIER;
         double Vtop = pot.V(top) - V_meta;
         double xtop = top - phi_meta;
-        if (Vtop <= 0) { res.status = CTB_ST_NO_BARRIER; return; }
+        if (Vtop <= 0) return CTB_ST_NO_BARRIER;
         rscale = fabs(xtop) / sqrt(fabs(6 * Vtop));
     }
-    res.rscale = rscale;
+    return 0;
+}
+
+// Work predictor used to order instances (heavy first, similar neighbours): the starting value of the
+// shooting variable x = -log|(phi_bar - phi_abs)/(phi_meta - phi_abs)| (T1D:682-683).  Thin walls
+// (phi_bar close to phi_meta) have large x: more x5 growth shots, more steps, 250 interior points.
+CTB_DEV double work_key(double phi_abs, double phi_meta, double phi_bar)
+{
+    return -log(fabs((phi_bar - phi_abs) / (phi_meta - phi_abs)));
+}
+
+// __init__ + findProfile + findAction for one instance.                        T1D:128-149, 615-791
+//
+// Control flow.  ONE integration loop serves both the shooting passes (integrateProfile, T1D:489-536)
+// and the final dense-output pass (integrateAndSaveProfile, T1D:578-613): a single copy of the
+// Cash-Karp step keeps the kernel's hot code inside the instruction cache.  Every lane of the warp
+// takes part in every trip of the outer loop (lanes without an instance, failed instances and lanes
+// that finished shooting early just idle): the save pass -- 500 dense-output points, up to 250 interior
+// points and the quadrature -- starts for the whole warp at once, on a warp vote, so its long uniform
+// code runs once per warp instead of once per group of lanes that happen to finish together.
+enum { PH_SHOOT = 0, PH_WAIT = 1, PH_SAVE = 2, PH_DONE = 3 };
+
+template <class Pot, int ALPHA, bool PROFILE>
+__device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, double phi_bar_in, double rscale_in,
+                               InstanceResult &res, const ProfileSink &sink)
+{
+    const unsigned FULL = 0xffffffffu;
+    const double qnan = nan("");
+    res.S = res.phi0 = res.r0 = res.rf = res.x = res.phi_bar = res.rscale = qnan;
+    res.n_shots = res.n_rkck = res.n_points = 0;
+    res.status = CTB_ST_NOT_RUN;
+    s.n_rkck = 0;
+    s.phi_eps = 0.0;
+    const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
+    const Pot &pot = s.pot;
+    int phase = valid ? PH_SHOOT : PH_DONE;
+
+    // ---- __init__ : T1D:128-149 ----
+    double V_meta = 0.0, phi_bar = phi_bar_in, rscale = rscale_in;
+    if (valid) {
+        V_meta = pot.V(phi_meta);
+        int st = sfi_init(pot, phi_abs, phi_meta, V_meta, phi_bar, rscale);
+        res.phi_bar = phi_bar;
+        res.rscale = rscale;
+        if (st) { res.status = st; phase = PH_DONE; rscale = 1.0; phi_bar = 0.5 * (phi_abs + phi_meta); }
+    }
     s.phi_eps = k.phi_eps * fabs(phi_abs - phi_meta);
 
-    // ---- findProfile : T1D:676-727 ----
+    // ---- findProfile : T1D:676-700 ----
     const double xtol = k.xtol, phitol = k.phitol;
     double xmin = xtol * 10, xmax = INFINITY, x;
     if (!isnan(k.xguess)) x = k.xguess;
@@ -631,174 +674,177 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, InstanceResul
     const double epsfrac = phitol;
     const double inv_ea0 = 1.0 / ea0, inv_ea1 = 1.0 / ea1;
     const double cutoff = k.thinCutoff * delta_phi;
-    bool have_rf = false;
-    double rf = qnan, r0 = qnan, y00 = qnan, y01 = qnan, delta_phi0 = qnan;
-    int status = CTB_ST_XTOL, nshots = 0;
+    const int npoints = k.npoints;
+    const double afac = (ALPHA == 2) ? 12.566370614359172 : 19.739208802178716; // 2 pi^(d/2) / Gamma(d/2)
+    const double vfac = (ALPHA == 2) ? 4.1887902047863905 : 4.934802200544679;  // pi^(d/2) / Gamma(d/2+1)
 
-    for (;;) {
-        delta_phi0 = exp(-x) * delta_phi;
-        double r0_, p0, dp0;
-        int e = s.initial_conditions(delta_phi0, rmin, cutoff, r0_, p0, dp0);
-        if (e) { res.status = e; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
-        if (!isfinite(r0_) || !isfinite(x)) {
-            if (!have_rf) { res.status = CTB_ST_FIRST_SHOT; res.n_rkck = s.n_rkck; return; }
-            status = CTB_ST_XTOL;
-            break;
+    bool have_rf = false;
+    double rf = qnan, r0 = qnan, y00 = qnan, y01 = qnan, delta_phi0 = qnan, dv0 = qnan, d2v0 = qnan;
+    int status = CTB_ST_XTOL, nshots = 0;
+    // dense-output state (save pass only)
+    SimpsonStream simp;
+    int N = 0, i_pt = 1, pidx = 0;
+    double step = 0.0, di = 1.0, Ri = 0.0, R_first = 0.0, Phi_first = 0.0;
+
+    auto emit = [&](double r, double phi, double dphi) {
+        double ra = (ALPHA == 2) ? r * r : r * r * r;
+        double integrand = (0.5 * (dphi * dphi) + pot.V_quad(phi) - V_meta) * (ra * afac);
+        simp.feed(r, integrand);
+        if (PROFILE) { sink.R[pidx] = r; sink.Phi[pidx] = phi; sink.dPhi[pidx] = dphi; pidx++; }
+    };
+    auto fail = [&](int st) { res.status = st; phase = PH_DONE; };
+
+    for (;;) { // one trip = one shot (T1D:702-727) or, once for the whole warp, the save pass (T1D:729-761)
+        if (__all_sync(FULL, phase != PH_SHOOT)) {
+            if (__all_sync(FULL, phase == PH_DONE)) break;
+            if (phase == PH_WAIT) phase = PH_SAVE;
         }
-        r0 = r0_; y00 = p0; y01 = dp0;
-        // ---- integrateProfile : T1D:489-536 ----
-        int ctype;
-        {
+        if (phase == PH_SHOOT) {
+            delta_phi0 = exp(-x) * delta_phi;
+            dv0 = s.dV_from_absMin(delta_phi0);
+            d2v0 = s.d2V(phi_abs + delta_phi0);
+            double r0_, p0, dp0;
+            int e = s.initial_conditions(delta_phi0, dv0, d2v0, rmin, cutoff, r0_, p0, dp0);
+            if (e) fail(e);
+            else if (!isfinite(r0_) || !isfinite(x)) {
+                // "use the last finite values instead" (T1D:707-712); note delta_phi0 stays the new one
+                if (!have_rf) fail(CTB_ST_FIRST_SHOT);
+                else { status = CTB_ST_XTOL; phase = PH_WAIT; }
+            } else {
+                r0 = r0_; y00 = p0; y01 = dp0;
+            }
+        }
+        if (phase == PH_SAVE) { // grid, interior points (T1D:734-760) and the first dense-output point
+            res.r0 = r0; res.rf = rf;
+            res.phi0 = phi_abs + delta_phi0;
+            step = (rf - r0) / (npoints - 1);
+            const double Rl1 = (npoints == 2) ? rf : __dadd_rn(__dmul_rn(1.0, step), r0);
+            int nint = 0;
+            double a_int = 0.0, dx0 = Rl1 - r0, st_int = 0.0;
+            bool lin_int = true;
+            const int max_interior = (k.max_interior_pts < 0) ? npoints / 2 : k.max_interior_pts;
+            if (max_interior > 0) {
+                if (r0 / dx0 <= max_interior) {
+                    nint = (int)ceil(r0 / dx0);
+                    st_int = r0 / nint;
+                } else {
+                    nint = max_interior;
+                    lin_int = false;
+                    a_int = (r0 / dx0 - nint) * 2 / ((double)nint * (nint + 1));
+                }
+            }
+            N = nint + npoints;
+            res.n_points = N;
+            simp.init(N);
+            const double phi_c = phi_abs + delta_phi0;
+            // first profile point: r = 0 when there are interior points, else the start of the integration
+            R_first = (nint > 0) ? 0.0 : r0;
+            Phi_first = (nint > 0) ? phi_c : y00;
+            if (nint > 0) {
+                emit(0.0, phi_c, 0.0);
+                for (int i = 1; i < nint; i++) {
+                    double ri;
+                    if (lin_int) ri = __dadd_rn(__dmul_rn((double)i, st_int), 0.0);
+                    else {
+                        double Nv = (double)(nint - i);
+                        ri = r0 - dx0 * (Nv + 0.5 * a_int * Nv * (Nv + 1));
+                    }
+                    double2 e = exact_solution<ALPHA>(ri, phi_c, dv0, d2v0);
+                    emit(ri, e.x, e.y);
+                }
+            }
+            emit(r0, y00, y01);
+            i_pt = 1; di = 1.0;
+            Ri = Rl1;
+        }
+
+        // ---- integrate from (r0, y00, y01): T1D:489-536 (shooting) / T1D:578-613 (saving) ----
+        if (phase == PH_SHOOT || phase == PH_SAVE) {
+            const bool saving = phase == PH_SAVE;
+            int ctype = -1;
             double r_ = r0, ya = y00, yb = y01, dr = dr0, da, db;
             s.eom(ya, yb, r_, da, db);
             const double ysign = sgn(ya - phi_meta);
             const double rmax = rmax_rel + r0;
-            double yf0, yf1;
+            double yf0 = qnan, yf1 = qnan;
             for (;;) {
                 double dy0, dy1, drnext;
-                e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
-                if (e) { res.status = e; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
-                double r1 = r_ + dr, na = ya + dy0, nb = yb + dy1, nda, ndb;
+                int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
+                if (e) { fail(e); break; }
+                double r1, na, nb;
+                if (saving && dr < drmin) { // T1D:594-597
+                    na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;
+                    dr = drnext = drmin;
+                    r1 = r_ + dr;
+                } else {
+                    r1 = r_ + dr; na = ya + dy0; nb = yb + dy1;
+                }
+                double nda, ndb;
                 s.eom(na, nb, r1, nda, ndb);
-                if (r1 > rmax) { res.status = CTB_ST_RMAX; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
-                else if (dr < drmin) { res.status = CTB_ST_DRMIN; res.n_shots = nshots; res.n_rkck = s.n_rkck; return; }
-                else if (fabs(na - phi_meta) < 3 * ea0 && fabs(nb) < 3 * ea1) {
-                    rf = r1; yf0 = na; yf1 = nb; ctype = CT_CONVERGED;
-                    break;
-                } else if (nb * ysign > 0 || (na - phi_meta) * ysign < 0) {
-                    Cubic f0, f1;
-                    f0.init(ya, dr * da, na, dr * nda);
-                    f1.init(yb, dr * db, nb, dr * ndb);
-                    double xx;
-                    int berr;
-                    if (nb * ysign > 0) {
-                        xx = brentq([&](double t) { return f1(t); }, 0.0, 1.0, berr);
-                        ctype = CT_UNDERSHOOT;
-                    } else {
-                        const double pm = phi_meta;
-                        xx = brentq([&](double t) { return f0(t) - pm; }, 0.0, 1.0, berr);
-                        ctype = CT_OVERSHOOT;
+                if (!saving) {
+                    if (r1 > rmax) { fail(CTB_ST_RMAX); break; }
+                    else if (dr < drmin) { fail(CTB_ST_DRMIN); break; }
+                    else if (fabs(na - phi_meta) < 3 * ea0 && fabs(nb) < 3 * ea1) {
+                        rf = r1; yf0 = na; yf1 = nb; ctype = CT_CONVERGED;
+                        break;
+                    } else if (nb * ysign > 0 || (na - phi_meta) * ysign < 0) {
+                        Cubic f0, f1;
+                        f0.init(ya, dr * da, na, dr * nda);
+                        f1.init(yb, dr * db, nb, dr * ndb);
+                        // undershoot (phi' = 0) is tested first, as in the reference; one root find serves both
+                        const bool under = nb * ysign > 0;
+                        ctype = under ? CT_UNDERSHOOT : CT_OVERSHOOT;
+                        const Cubic &fr = under ? f1 : f0;
+                        const double off = under ? 0.0 : phi_meta;
+                        int berr;
+                        double xx = brentq([&](double t) { return fr.at(t) - off; }, 0.0, 1.0, berr);
+                        if (berr == 1 || berr == 2) { fail((berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN); break; }
+                        rf = r_ + dr * xx;
+                        yf0 = f0.at(xx); yf1 = f1.at(xx);
+                        break;
                     }
-                    if (berr == 1 || berr == 2) {
-                        res.status = (berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN;
-                        res.n_shots = nshots; res.n_rkck = s.n_rkck;
-                        return;
+                } else {
+                    if (r_ < Ri && Ri <= r1) { // T1D:601-606
+                        Cubic f0, f1;
+                        f0.init(ya, dr * da, na, dr * nda);
+                        f1.init(yb, dr * db, nb, dr * ndb);
+                        const double inv_dr = rcp_fast(dr);
+                        while (i_pt < npoints && r_ < Ri && Ri <= r1) {
+                            double t = (Ri - r_) * inv_dr;
+                            emit(Ri, f0(t), f1(t));
+                            i_pt++;
+                            di += 1.0;
+                            Ri = (i_pt == npoints - 1) ? rf : __dadd_rn(__dmul_rn(di, step), r0);
+                        }
                     }
-                    rf = r_ + dr * xx;
-                    yf0 = f0(xx); yf1 = f1(xx);
-                    break;
+                    if (i_pt >= npoints) break;
                 }
                 r_ = r1; ya = na; yb = nb; da = nda; db = ndb;
                 dr = drnext;
             }
-            if (fabs(yf0 - phi_meta) < 3 * ea0 && fabs(yf1) < 3 * ea1) ctype = CT_CONVERGED;
-        }
-        have_rf = true;
-        nshots++;
-        res.x = x;
-        if (ctype == CT_CONVERGED) { status = CTB_ST_CONVERGED; break; }
-        else if (ctype == CT_UNDERSHOOT) { xmin = x; x = (xmax == INFINITY) ? x * 5.0 : .5 * (xmin + xmax); }
-        else { xmax = x; x = .5 * (xmin + xmax); }
-        if ((xmax - xmin) < xtol) { status = CTB_ST_XTOL; break; }
-    }
-    res.n_shots = nshots;
-    res.r0 = r0; res.rf = rf;
-    res.phi0 = phi_abs + delta_phi0;
-
-    // ---- second pass with dense output, interior points and the action, fused: T1D:729-791 ----
-    const int npoints = k.npoints;
-    const double step = (rf - r0) / (npoints - 1);
-    const double Rl1 = (npoints == 2) ? rf : __dadd_rn(__dmul_rn(1.0, step), r0);
-    int nint = 0;
-    double a_int = 0.0, dx0 = Rl1 - r0, st_int = 0.0;
-    bool lin_int = true;
-    const int max_interior = (k.max_interior_pts < 0) ? npoints / 2 : k.max_interior_pts;
-    if (max_interior > 0) {
-        if (r0 / dx0 <= max_interior) {
-            nint = (int)ceil(r0 / dx0);
-            st_int = r0 / nint;
-        } else {
-            nint = max_interior;
-            lin_int = false;
-            a_int = (r0 / dx0 - nint) * 2 / ((double)nint * (nint + 1));
-        }
-    }
-    const int N = nint + npoints;
-    res.n_points = N;
-    const double afac = (ALPHA == 2) ? 12.566370614359172 : 19.739208802178716;  // 2 pi^(d/2) / Gamma(d/2)
-    const double vfac = (ALPHA == 2) ? 4.1887902047863905 : 4.934802200544679;   // pi^(d/2) / Gamma(d/2+1)
-    SimpsonStream simp;
-    simp.init(N);
-    double R_first = 0.0, Phi_first = 0.0;
-    int pidx = 0;
-    auto emit = [&](double r, double phi, double dphi) {
-        double ra = (ALPHA == 2) ? r * r : r * r * r;
-        double integrand = (0.5 * (dphi * dphi) + pot.V(phi) - V_meta) * (ra * afac);
-        simp.feed(r, integrand);
-        if (pidx == 0) { R_first = r; Phi_first = phi; }
-        if (sink.R) { sink.R[pidx] = r; sink.Phi[pidx] = phi; sink.dPhi[pidx] = dphi; }
-        pidx++;
-    };
-    if (nint > 0) { // T1D:734-760
-        const double phi_c = phi_abs + delta_phi0;
-        const double dv = s.dV_from_absMin(delta_phi0);
-        const double d2v = s.d2V(phi_c);
-        emit(0.0, phi_c, 0.0);
-        for (int i = 1; i < nint; i++) {
-            double ri;
-            if (lin_int) ri = __dadd_rn(__dmul_rn((double)i, st_int), 0.0);
-            else {
-                double Nv = (double)(nint - i);
-                ri = r0 - dx0 * (Nv + 0.5 * a_int * Nv * (Nv + 1));
-            }
-            double p, dp;
-            s.template exact_solution<true>(ri, phi_c, dv, d2v, p, dp);
-            emit(ri, p, dp);
-        }
-    }
-    { // integrateAndSaveProfile T1D:578-613
-        double r_ = r0, ya = y00, yb = y01, dr = dr0, da, db;
-        s.eom(ya, yb, r_, da, db);
-        emit(r0, ya, yb);
-        int i = 1;
-        double Ri = (npoints == 2) ? rf : __dadd_rn(__dmul_rn(1.0, step), r0);
-        while (i < npoints) {
-            double dy0, dy1, drnext;
-            int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
-            if (e) { res.status = e; res.n_rkck = s.n_rkck; return; }
-            double r1, na, nb;
-            if (dr >= drmin) {
-                r1 = r_ + dr; na = ya + dy0; nb = yb + dy1;
-            } else {
-                na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;
-                dr = drnext = drmin;
-                r1 = r_ + dr;
-            }
-            double nda, ndb;
-            s.eom(na, nb, r1, nda, ndb);
-            if (r_ < Ri && Ri <= r1) {
-                Cubic f0, f1;
-                f0.init(ya, dr * da, na, dr * nda);
-                f1.init(yb, dr * db, nb, dr * ndb);
-                const double inv_dr = rcp_fast(dr);
-                while (i < npoints && r_ < Ri && Ri <= r1) {
-                    double t = (Ri - r_) * inv_dr;
-                    emit(Ri, f0(t), f1(t));
-                    i++;
-                    Ri = (i == npoints - 1) ? rf : __dadd_rn(__dmul_rn((double)i, step), r0);
+            if (phase == PH_SAVE) { // findAction : T1D:780-791
+                double S = simp.finish(N);
+                double Rd = (ALPHA == 2) ? R_first * R_first * R_first : (R_first * R_first) * (R_first * R_first);
+                S += (Rd * vfac) * (pot.V_quad(Phi_first) - V_meta);
+                res.S = S;
+                res.status = status;
+                phase = PH_DONE;
+            } else if (phase == PH_SHOOT) { // bracket update: T1D:716-727
+                if (fabs(yf0 - phi_meta) < 3 * ea0 && fabs(yf1) < 3 * ea1) ctype = CT_CONVERGED;
+                have_rf = true;
+                nshots++;
+                res.x = x;
+                if (ctype == CT_CONVERGED) { status = CTB_ST_CONVERGED; phase = PH_WAIT; }
+                else {
+                    if (ctype == CT_UNDERSHOOT) { xmin = x; x = (xmax == INFINITY) ? x * 5.0 : .5 * (xmin + xmax); }
+                    else { xmax = x; x = .5 * (xmin + xmax); }
+                    if ((xmax - xmin) < xtol) { status = CTB_ST_XTOL; phase = PH_WAIT; }
                 }
             }
-            r_ = r1; ya = na; yb = nb; da = nda; db = ndb;
-            dr = drnext;
         }
     }
-    // findAction T1D:780-791
-    double S = simp.finish(N);
-    double Rd = (ALPHA == 2) ? R_first * R_first * R_first : (R_first * R_first) * (R_first * R_first);
-    S += (Rd * vfac) * (pot.V(Phi_first) - V_meta);
-    res.S = S;
+    res.n_shots = nshots;
     res.n_rkck = s.n_rkck;
-    res.status = status;
 }
 
 } // namespace ctb

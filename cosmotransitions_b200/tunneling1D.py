@@ -65,26 +65,24 @@ class SingleFieldInstanton:
         if not isinstance(V, DevicePotential):
             raise TypeError("V must be a cosmotransitions_b200.potentials.DevicePotential (device functor); "
                             "arbitrary Python callables cannot run on the GPU and there is no CPU fallback")
-        if phi_bar is not None or rscale is not None:
-            raise NotImplementedError("phi_bar / rscale overrides are not supported by the device solver")
         self.phi_absMin, self.phi_metaMin = float(phi_absMin), float(phi_metaMin)
         self.V = V
         self.alpha = alpha
         self._phi_eps_rel = phi_eps
         self.phi_eps = phi_eps * abs(self.phi_absMin - self.phi_metaMin)
         self._last = None
+        self._phi_bar_in, self._rscale_in = phi_bar, rscale
         # the reference validates the potential in __init__ (tunneling1D.py:133-147): do the same
-        r = self._solve(npoints=2)
-        st = int(r["status"][0])
+        st, self.phi_bar, self.rscale = batch.bounce_setup(V.kind, V.params[None, :], [self.phi_absMin],
+                                                          [self.phi_metaMin], phi_bar=phi_bar, rscale=rscale)
         if st in (_lib.ST_STABLE, _lib.ST_NO_BARRIER):
             raise_for_status(st)
-        self.phi_bar = float(r["phi_bar"][0])
-        self.rscale = float(r["rscale"][0])
 
     def _solve(self, return_profiles=False, **knobs):
         return batch.find_bounce_batch(self.V.kind, self.V.params[None, :], [self.phi_absMin], [self.phi_metaMin],
                                        alpha=self.alpha, phi_eps=self._phi_eps_rel, return_profiles=return_profiles,
-                                       **knobs)
+                                       phi_bar=None if self._phi_bar_in is None else [self._phi_bar_in],
+                                       rscale=None if self._rscale_in is None else [self._rscale_in], **knobs)
 
     def findProfile(self, xguess=None, xtol=1e-4, phitol=1e-4, thinCutoff=.01, npoints=500, rmin=1e-4, rmax=1e4,
                     max_interior_pts=None):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 1
+#define CTB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -96,6 +96,19 @@ typedef struct ctb_opts {
     int32_t block_threads;    /* 0 = library default */
 } ctb_opts;
 
+/* ---- inputs of the batched solve: one row / entry per instance ------------------------------ */
+typedef struct ctb_bounce_in {
+    const double *d_params;   /* [n, nparam] row-major potential parameters                          */
+    const double *d_phi_abs;  /* [n] phi_absMin                                                      */
+    const double *d_phi_meta; /* [n] phi_metaMin                                                     */
+    const double *d_phi_bar;  /* optional [n]: the phi_bar= override of __init__ (tunneling1D.py:140-143);
+                                 NULL or a NaN entry = findBarrierLocation                           */
+    const double *d_rscale;   /* optional [n]: the rscale= override (tunneling1D.py:144-147)         */
+    const int32_t *d_order;   /* optional [n] permutation: GPU thread t solves instance d_order[t]
+                                 (results are always written at the instance's own index)           */
+    int64_t n;
+} ctb_bounce_in;
+
 /* ---- outputs of the batched solve: structure of arrays, any pointer may be NULL ------------- */
 typedef struct ctb_bounce_out {
     double *d_S;         /* Euclidean action            findAction, tunneling1D.py:763-791          */
@@ -125,10 +138,16 @@ CTB_API int ctb_device_ok(void);
 
 /* SingleFieldInstanton(phi_absMin, phi_metaMin, V, dV, d2V, phi_eps, alpha).findProfile(**knobs)
  * followed by .findAction(profile), for n independent instances (tunneling1D.py:128-791).
- * d_params: [n, nparam] row-major; d_phi_abs, d_phi_meta: [n].  jb/jf may be NULL for POLY4. */
-CTB_API int ctb_bounce_batch(int pot_kind, const double *d_params, const double *d_phi_abs, const double *d_phi_meta,
-                     int64_t n, const ctb_opts *opts, const ctb_jtable *jb, const ctb_jtable *jf,
-                     const ctb_bounce_out *out, void *stream);
+ * jb/jf may be NULL for POLY4. */
+CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_opts *opts, const ctb_jtable *jb,
+                             const ctb_jtable *jf, const ctb_bounce_out *out, void *stream);
+
+/* SingleFieldInstanton.__init__ alone (tunneling1D.py:128-149): metastability check,
+ * findBarrierLocation, findRScale.  Fills out->d_phi_bar, d_rscale, d_status (0, CTB_ST_STABLE or
+ * CTB_ST_NO_BARRIER) and, if d_work_key != NULL, a per-instance work predictor (larger = more
+ * shooting work) that the host sorts on to build ctb_bounce_in.d_order. */
+CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
+                             const ctb_bounce_out *out, double *d_work_key, void *stream);
 
 /* finiteT.Jb_spline(theta, n=deriv) / Jf_spline (finiteT.py:167-174,197-204): out[i] = J^(deriv)(theta[i]).
  * deriv in 0..3. */

@@ -860,6 +860,8 @@ static int sfi_setup(sfi_t *s, const pot_t *pot, double phi_absMin, double phi_m
 
 /* findProfile + findAction.  prof_* may be NULL; otherwise arrays of capacity prof_cap.
  * shot_x / shot_type (capacity shot_cap) log the shooting sequence when non-NULL. */
+static double g_phi_bar_override = NAN, g_rscale_override = NAN; /* test hook, see ctbo_set_overrides */
+
 static void solve_one(const pot_t *pot, double phi_absMin, double phi_metaMin, const opts_t *o, result_t *res,
                       double *prof_R, double *prof_Phi, double *prof_dPhi, int prof_cap, double *shot_x,
                       int *shot_type, int shot_cap)
@@ -867,7 +869,7 @@ static void solve_one(const pot_t *pot, double phi_absMin, double phi_metaMin, c
     sfi_t S_, *s = &S_;
     memset(res, 0, sizeof(*res));
     res->S = res->phi0 = res->r0 = res->rf = res->x = res->yf0 = res->yf1 = NAN;
-    int st = sfi_setup(s, pot, phi_absMin, phi_metaMin, o, NAN, NAN);
+    int st = sfi_setup(s, pot, phi_absMin, phi_metaMin, o, g_phi_bar_override, g_rscale_override);
     res->phi_bar = s->phi_bar; res->rscale = s->rscale;
     if (st) { res->status = st; return; }
     int npoints = o->npoints;
@@ -1151,6 +1153,13 @@ CTBO_API int ctbo_rkqs_poly4(const double *coef5, int alpha, const double y[2], 
     int e = rkqs(&s, y, dydt, t, dt_try, epsfrac, epsabs, dy, &dtu, &dtn);
     out4[0] = dy[0]; out4[1] = dy[1]; out4[2] = dtu; out4[3] = dtn;
     return e;
+}
+
+/* phi_bar= / rscale= overrides of __init__ for subsequent calls (NaN = None). Not thread-safe: tests only. */
+CTBO_API void ctbo_set_overrides(double phi_bar, double rscale)
+{
+    g_phi_bar_override = phi_bar;
+    g_rscale_override = rscale;
 }
 
 CTBO_API int ctbo_abi_version(void) { return 1; }

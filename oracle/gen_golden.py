@@ -181,6 +181,13 @@ def gen_quartic():
         r.update(kind="knobs", c=float(c), alpha=2, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0, phi_meta=0.0,
                  opts=dict(phi_eps=1e-2))
         cases.append(r)
+    # phi_bar / rscale overrides of __init__ (tunneling1D.py:140-147)
+    for c, ikw in ((0.3, dict(rscale=2.0)), (0.45, dict(phi_bar=0.8)), (0.2, dict(phi_bar=0.35, rscale=2.5))):
+        V, dV, d2V = quartic_lambdas(c)
+        r = run_case(V, dV, d2V, 1.0, 0.0, 2, init_kw=ikw)
+        r.update(kind="init", c=float(c), alpha=2, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0, phi_meta=0.0,
+                 opts={}, init=ikw)
+        cases.append(r)
     # shifted / scaled / mirrored quartics, driven through np.polyval so that V, dV, d2V come from
     # the same coefficient vector the device functor receives
     rng = np.random.default_rng(11)

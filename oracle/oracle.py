@@ -120,6 +120,13 @@ def bounce_batch(cfg, params, phi_abs, phi_meta, nthreads=1):
     return out
 
 
+def set_overrides(phi_bar=None, rscale=None):
+    """phi_bar= / rscale= of SingleFieldInstanton.__init__ for the following calls (None = compute)."""
+    nan = float("nan")
+    lib().ctbo_set_overrides(C.c_double(nan if phi_bar is None else phi_bar),
+                             C.c_double(nan if rscale is None else rscale))
+
+
 def bounce_one(cfg, params, phi_abs, phi_meta, prof_cap=4096, shot_cap=256):
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(cfg.nparam)
     out9 = np.zeros(9)

@@ -40,7 +40,8 @@ def test_quartic_golden(ctb, gold_dir):
         opts = dict(case.get("opts", {}))
         phi_eps = opts.pop("phi_eps", 1e-3)
         r = _np(batch.find_bounce_batch(_lib.POT_POLY4, np.array([case["coef"]]), [case["phi_abs"]], [case["phi_meta"]],
-                                        alpha=case["alpha"], phi_eps=phi_eps, return_profiles=True, **opts))
+                                        alpha=case["alpha"], phi_eps=phi_eps, return_profiles=True,
+                                        **{k: [v] for k, v in case.get("init", {}).items()}, **opts))
         st = int(r["status"][0])
         if case["error"] is not None:
             if case["error"] in ERR2STATUS:
@@ -130,6 +131,28 @@ def test_quartic_sweep_vs_oracle(ctb, oracle, alpha):
         assert np.array_equal(gs[k], g[k][perm], equal_nan=True), k
     for k in ("status", "n_shots", "n_rkck", "n_points"):
         assert np.array_equal(gs[k], g[k][perm]), k
+
+
+def test_schedules_agree(ctb):
+    """Work-sorted and natural schedules are the same function of the inputs, bit for bit."""
+    from cosmotransitions_b200 import _lib, batch, potentials
+    N = 6000
+    c = 0.02 + 0.475 * np.random.default_rng(5).random(N)
+    p = potentials.quartic_family_params(c)
+    p[17] = [0, 0, -0.1, -0.8 / 3, 0.25]     # a no-barrier instance in the middle of the batch
+    a = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, schedule="natural"))
+    b = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, schedule="sorted"))
+    assert a["status"][17] == 3 and b["status"][17] == 3
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_scalar_api_overrides(ctb):
+    from cosmotransitions_b200 import tunneling1D as t1, potentials
+    inst = t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(0.3), rscale=2.0)
+    assert inst.rscale == 2.0 and 0.3 < inst.phi_bar < 1.0
+    inst = t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(0.45), phi_bar=0.8)
+    assert inst.phi_bar == 0.8
 
 
 def test_edge_batches(ctb):

@@ -29,6 +29,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.JTable) == 40
     assert C.sizeof(_lib.Opts) == 7 * 8 + 4 * 4
     assert C.sizeof(_lib.BounceOut) == 15 * 8
+    assert C.sizeof(_lib.BounceIn) == 7 * 8
 
 
 def test_bspline_to_pp_matches_scipy():

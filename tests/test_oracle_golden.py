@@ -35,7 +35,9 @@ def test_quartic_cases(oracle, gold_dir):
     worst = 0.0
     for case in cases:
         cfg = _cfg(oracle, case)
+        oracle.set_overrides(**case.get("init", {}))
         r = oracle.bounce_one(cfg, case["coef"], case["phi_abs"], case["phi_meta"])
+        oracle.set_overrides()
         if case["error"] is not None:
             assert r["status"] == _status_for(case["error"]), (case, r["status"])
             continue
