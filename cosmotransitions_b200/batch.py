@@ -94,10 +94,10 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
     with torch.cuda.device(dev):
         order = None
         if schedule == "sorted":
-            key = torch.empty(n, dtype=torch.float64, device=dev)
+            key = torch.empty(n, dtype=torch.float32, device=dev)
             bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale)
             _lib.check(lib.ctb_bounce_setup(kind, bi, jb, jf, bo, key.data_ptr(), st), "ctb_bounce_setup")
-            order = torch.argsort(key, descending=True).to(torch.int32)
+            order = torch.argsort(key, descending=True)
             # the solve kernel reuses what the setup kernel found (NaN where __init__ failed: the solve
             # kernel then re-derives the same PotentialError status)
             phi_bar, rscale = out["phi_bar"], out["rscale"]

@@ -128,7 +128,6 @@ static int fill_args(BounceArgs &a, const ctb_bounce_in *in, const ctb_jtable *j
 {
     if (!in || !out || in->n < 0) return CTB_ERR_BAD_ARG;
     if (in->n > 0 && (!in->d_params || !in->d_phi_abs || !in->d_phi_meta)) return CTB_ERR_BAD_ARG;
-    if (in->n > 2147483647LL && in->d_order) return CTB_ERR_UNSUPPORTED;
     a.params = in->d_params; a.phi_abs = in->d_phi_abs; a.phi_meta = in->d_phi_meta; a.n = in->n;
     a.phi_bar_in = in->d_phi_bar; a.rscale_in = in->d_rscale; a.order = in->d_order; a.work_key = nullptr;
     a.jb = to_jtab(jb); a.jf = to_jtab(jf);
@@ -168,7 +167,7 @@ CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_op
 }
 
 CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
-                             const ctb_bounce_out *out, double *d_work_key, void *stream)
+                             const ctb_bounce_out *out, float *d_work_key, void *stream)
 {
     BounceArgs a;
     int rc = fill_args(a, in, jb, jf, out);

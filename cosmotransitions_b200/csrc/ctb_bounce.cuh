@@ -16,8 +16,8 @@ namespace ctb {
 struct BounceArgs {
     const double *params, *phi_abs, *phi_meta;
     const double *phi_bar_in, *rscale_in; // optional overrides (NaN entry = compute)
-    const int32_t *order;                 // optional permutation: thread t solves instance order[t]
-    double *work_key;                     // setup kernel only
+    const int64_t *order;                 // optional permutation: thread t solves instance order[t]
+    float *work_key;                      // setup kernel only
     int64_t n;
     Knobs knobs;
     JTab jb, jf;
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(c
     // carry a dummy instance that is never integrated
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < a.n;
-    const int64_t i = valid ? (a.order ? (int64_t)a.order[t] : t) : 0;
+    const int64_t i = valid ? (a.order ? a.order[t] : t) : 0;
     Sfi<Pot, ALPHA> s;
     s.pot.load(a.params + i * Pot::nparam, &a.jb, &a.jf);
     s.phi_abs = a.phi_abs[i];
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
     if (a.out.d_phi_bar) a.out.d_phi_bar[i] = phi_bar;
     if (a.out.d_rscale) a.out.d_rscale[i] = rscale;
     if (a.out.d_status) a.out.d_status[i] = st;
-    if (a.work_key) a.work_key[i] = st ? -INFINITY : work_key(pa, pm, phi_bar);
+    if (a.work_key) a.work_key[i] = st ? -INFINITY : (float)work_key(pa, pm, phi_bar);
 }
 
 template <class Pot>

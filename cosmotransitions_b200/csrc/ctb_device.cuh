@@ -311,10 +311,12 @@ struct SimpsonStream {
     // the previous pair (needed by the even-N end correction)
     double xa, ya, xb, yb, xp, yp;
     double sum;
+    double usum, h_uniform; // pairs on the uniform part of the grid: usum * h/3 (see feed_uniform)
     int idx, nbasic;
     CTB_DEV void init(int N)
     {
         sum = 0.0; idx = 0;
+        usum = 0.0; h_uniform = 0.0;
         nbasic = (N & 1) ? N : N - 1; // even N: composite rule on the first N-1 points
         xa = ya = xb = yb = xp = yp = 0.0;
     }
@@ -342,9 +344,23 @@ struct SimpsonStream {
         }
         idx++;
     }
+    // Same as feed() for a point whose pair lies entirely on the uniform part of the grid
+    // (R = linspace(r0, rf, npoints), T1D:730): there h0 = h1 = h up to the rounding of i*step + r0
+    // (|h0/h1 - 1| ~ 1e-13), and the unequal-spacing weights collapse to h/3 (1, 4, 1).
+    CTB_DEV void feed_uniform(double x, double y, double h)
+    {
+        if (idx & 1) {
+            xb = x; yb = y;
+        } else {
+            if (idx < nbasic) { usum += (ya + y) + 4.0 * yb; h_uniform = h; xp = xb; yp = yb; }
+            xa = x; ya = y;
+        }
+        idx++;
+    }
     CTB_DEV double finish(int N) const
     {
-        if (N & 1) return sum;
+        const double total = sum + usum * (h_uniform * (1.0 / 3.0));
+        if (N & 1) return total;
         if (N == 2) return 0.5 * (xb - xa) * (yb + ya);
         // points N-3, N-2, N-1 = (xp, yp), (xa, ya), (xb, yb)
         double h0 = xa - xp, h1 = xb - xa;
@@ -355,7 +371,7 @@ struct SimpsonStream {
         be = (den != 0) ? num / den : 0.0;
         num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1);
         et = (den != 0) ? num / den : 0.0;
-        return sum + (al * yb + be * ya - et * yp);
+        return total + (al * yb + be * ya - et * yp);
     }
 };
 
@@ -376,11 +392,21 @@ enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
 // nu = (ALPHA-1)/2: closed forms for nu = 1/2, I0/I1/J0/J1 + recurrences for nu = 1.
 // ONE out-of-line copy per ALPHA: the transcendental bodies (exp, sinh, sincos, Bessel) are large and
 // every call site sharing them keeps the kernel's hot code inside the instruction cache.
+// (beta = sqrt|V''| and ratio = V'/V'' are constant over the ~16 evaluations of a root find and the up
+// to 250 interior points: the caller computes them once, see exact_coef)
+struct ExactCoef {
+    double phi0, dv, d2v, beta, ratio;
+};
+CTB_DEV ExactCoef exact_coef(double phi0, double dv, double d2v)
+{
+    return ExactCoef{phi0, dv, d2v, sqrt(fabs(d2v)), dv / d2v};
+}
+
 template <int ALPHA>
-__device__ __noinline__ double2 exact_solution(double r, double phi0, double dv, double d2v)
+__device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
 {
     double phi, dphi;
-    double beta = sqrt(fabs(d2v));
+    const double phi0 = c.phi0, dv = c.dv, d2v = c.d2v, beta = c.beta;
     double z = beta * r;
     if (z < 1e-2) {
         const double s = (d2v > 0) ? 1.0 : -1.0;
@@ -398,7 +424,7 @@ __device__ __noinline__ double2 exact_solution(double r, double phi0, double dv,
         return make_double2(phi, dphi);
     }
     const bool modified = d2v > 0;
-    double ratio = dv / d2v;
+    const double ratio = c.ratio;
     if (ALPHA == 2) {
         // Gamma(3/2) (z/2)^(-1/2) I_{1/2}(z) = sinh(z)/z ; J: sin(z)/z
         double sh, ch;
@@ -476,8 +502,8 @@ struct Sfi {
     CTB_DEV int initial_conditions(double delta_phi0, double dv, double d2v, double rmin, double cutoff, double &r0,
                                    double &phi_r0, double &dphi_r0) const
     {
-        const double phi0 = phi_abs + delta_phi0;
-        double2 e = exact_solution<ALPHA>(rmin, phi0, dv, d2v);
+        const ExactCoef ec = exact_coef(phi_abs + delta_phi0, dv, d2v);
+        double2 e = exact_solution<ALPHA>(rmin, ec);
         phi_r0 = e.x; dphi_r0 = e.y;
         r0 = rmin;
         if (fabs(phi_r0 - phi_abs) > fabs(cutoff)) return 0;
@@ -486,17 +512,17 @@ struct Sfi {
         while (isfinite(r)) {
             rlast = r;
             r *= 10;
-            double p = exact_solution<ALPHA>(r, phi0, dv, d2v).x;
+            double p = exact_solution<ALPHA>(r, ec).x;
             if (fabs(p - phi_abs) > fabs(cutoff)) break;
         }
         int err;
         const double pa = phi_abs, ac = fabs(cutoff);
-        double rr = brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, phi0, dv, d2v).x - pa) - ac; },
+        double rr = brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; },
                            rlast, r, err);
         if (err == 2) return CTB_ST_NONFINITE;
         if (err == 1) return CTB_ST_BRENT_SIGN;
         r0 = rr;
-        e = exact_solution<ALPHA>(r0, phi0, dv, d2v);
+        e = exact_solution<ALPHA>(r0, ec);
         phi_r0 = e.x; dphi_r0 = e.y;
         return 0;
     }
@@ -686,10 +712,11 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     int N = 0, i_pt = 1, pidx = 0;
     double step = 0.0, di = 1.0, Ri = 0.0, R_first = 0.0, Phi_first = 0.0;
 
-    auto emit = [&](double r, double phi, double dphi) {
+    auto emit = [&](double r, double phi, double dphi, bool uniform) {
         double ra = (ALPHA == 2) ? r * r : r * r * r;
         double integrand = (0.5 * (dphi * dphi) + pot.V_quad(phi) - V_meta) * (ra * afac);
-        simp.feed(r, integrand);
+        if (uniform) simp.feed_uniform(r, integrand, step);
+        else simp.feed(r, integrand);
         if (PROFILE) { sink.R[pidx] = r; sink.Phi[pidx] = phi; sink.dPhi[pidx] = dphi; pidx++; }
     };
     auto fail = [&](int st) { res.status = st; phase = PH_DONE; };
@@ -741,7 +768,8 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
             R_first = (nint > 0) ? 0.0 : r0;
             Phi_first = (nint > 0) ? phi_c : y00;
             if (nint > 0) {
-                emit(0.0, phi_c, 0.0);
+                const ExactCoef ec = exact_coef(phi_c, dv0, d2v0);
+                emit(0.0, phi_c, 0.0, false);
                 for (int i = 1; i < nint; i++) {
                     double ri;
                     if (lin_int) ri = __dadd_rn(__dmul_rn((double)i, st_int), 0.0);
@@ -749,11 +777,11 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                         double Nv = (double)(nint - i);
                         ri = r0 - dx0 * (Nv + 0.5 * a_int * Nv * (Nv + 1));
                     }
-                    double2 e = exact_solution<ALPHA>(ri, phi_c, dv0, d2v0);
-                    emit(ri, e.x, e.y);
+                    double2 e = exact_solution<ALPHA>(ri, ec);
+                    emit(ri, e.x, e.y, false);
                 }
             }
-            emit(r0, y00, y01);
+            emit(r0, y00, y01, false);
             i_pt = 1; di = 1.0;
             Ri = Rl1;
         }
@@ -811,7 +839,9 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                         const double inv_dr = rcp_fast(dr);
                         while (i_pt < npoints && r_ < Ri && Ri <= r1) {
                             double t = (Ri - r_) * inv_dr;
-                            emit(Ri, f0(t), f1(t));
+                            // dense-output point i_pt closes / sits inside a pair that started at a
+                            // dense-output point (index >= 0 of the uniform grid) iff i_pt >= 2
+                            emit(Ri, f0(t), f1(t), i_pt >= 2);
                             i_pt++;
                             di += 1.0;
                             Ri = (i_pt == npoints - 1) ? rf : __dadd_rn(__dmul_rn(di, step), r0);

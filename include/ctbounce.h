@@ -104,7 +104,7 @@ typedef struct ctb_bounce_in {
     const double *d_phi_bar;  /* optional [n]: the phi_bar= override of __init__ (tunneling1D.py:140-143);
                                  NULL or a NaN entry = findBarrierLocation                           */
     const double *d_rscale;   /* optional [n]: the rscale= override (tunneling1D.py:144-147)         */
-    const int32_t *d_order;   /* optional [n] permutation: GPU thread t solves instance d_order[t]
+    const int64_t *d_order;   /* optional [n] permutation: GPU thread t solves instance d_order[t]
                                  (results are always written at the instance's own index)           */
     int64_t n;
 } ctb_bounce_in;
@@ -144,10 +144,10 @@ CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_op
 
 /* SingleFieldInstanton.__init__ alone (tunneling1D.py:128-149): metastability check,
  * findBarrierLocation, findRScale.  Fills out->d_phi_bar, d_rscale, d_status (0, CTB_ST_STABLE or
- * CTB_ST_NO_BARRIER) and, if d_work_key != NULL, a per-instance work predictor (larger = more
- * shooting work) that the host sorts on to build ctb_bounce_in.d_order. */
+ * CTB_ST_NO_BARRIER) and, if d_work_key != NULL, a per-instance work predictor (float32, larger =
+ * more shooting work) that the host sorts on to build ctb_bounce_in.d_order. */
 CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
-                             const ctb_bounce_out *out, double *d_work_key, void *stream);
+                             const ctb_bounce_out *out, float *d_work_key, void *stream);
 
 /* finiteT.Jb_spline(theta, n=deriv) / Jf_spline (finiteT.py:167-174,197-204): out[i] = J^(deriv)(theta[i]).
  * deriv in 0..3. */
