@@ -47,3 +47,29 @@ def gather_strided(local, n, world):
     for r, shard in enumerate(local):
         out[r::world] = shard[: len(range(r, n, world))]
     return out
+
+
+def find_bounce_batch_distributed(kind, params, phi_absMin, phi_metaMin, solve=None, **kw):
+    """One-process-per-GPU driver (torch.distributed already initialised, any backend): every rank
+    solves the instances `partition(n, world, rank)` of the SAME global batch on its own device and
+    rank 0 receives the gathered result (other ranks get None).  The only communication is the final
+    gather of the per-instance results (~64 B per instance); there is no collective on the solve path.
+
+    `solve(kind, params, phi_abs, phi_meta, **kw) -> dict of tensors` defaults to find_bounce_batch
+    (the CPU tests substitute a stand-in so that the sharding / gather logic runs under gloo)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64)).reshape(-1, _lib.NPARAM[kind])
+    n = params.shape[0]
+    pa = np.broadcast_to(np.asarray(phi_absMin, dtype=np.float64), (n,))
+    pm = np.broadcast_to(np.asarray(phi_metaMin, dtype=np.float64), (n,))
+    idx = partition(n, world, rank)
+    solve = solve or batch.find_bounce_batch
+    local = solve(kind, params[idx], np.ascontiguousarray(pa[idx]), np.ascontiguousarray(pm[idx]), **kw)
+    local = {k: torch.as_tensor(v).cpu() for k, v in local.items()}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(local, gathered, dst=0)
+    if rank != 0:
+        return None
+    return {k: gather_strided([g[k] for g in gathered], n, world) for k in local}

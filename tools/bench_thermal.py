@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Secondary measurements (BASELINE.json configs[3], configs[4]): Jb/Jf spline kernel, model1 Vtot on
+the 4096 x 1024 (phi, T) grid, and finite-temperature bounces.  Prints one JSON object.
+usage: python tools/bench_thermal.py [--nbounce N]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import torch  # noqa: E402
+from cosmotransitions_b200 import _lib, batch, finiteT, generic_potential as gp  # noqa: E402
+
+dev = torch.device("cuda", 0)
+peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(
+    os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+HBM = peaks.get("hbm_gbs", 6650.0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts)), float(np.min(ts))
+
+
+out = {}
+# --- Jb spline on 2^26 thetas (512 MiB in, 512 MiB out: larger than L2)
+n = 1 << 26
+theta = (torch.rand(n, dtype=torch.float64, device=dev) * 2010.0) - 10.0
+ms, mn = timeit(lambda: finiteT.Jb_spline(theta))
+out["jb_spline"] = {"n": n, "ms": ms, "evals_per_s": n / ms * 1e3, "GBps": 16.0 * n / ms * 1e-6,
+                    "hbm_frac": 16.0 * n / ms * 1e-6 / HBM, "bytes_per_eval": 16}
+# --- model1 Vtot grid 4096 x 1024 (config C4)
+m = gp.model1()
+x_low = np.array([286.39824989, 382.19727238]); x_high = np.array([231.10296383, -136.82260069])
+L = np.linalg.norm(x_high - x_low); nhat = (x_high - x_low) / L
+s = torch.linspace(-0.2 * L, 1.2 * L, 4096, dtype=torch.float64, device=dev)
+T = torch.linspace(1, 250, 1024, dtype=torch.float64, device=dev)
+buf = torch.empty((4096, 1024), dtype=torch.float64, device=dev)
+ms, mn = timeit(lambda: m.Vtot_grid(x_low, nhat, s, T, out=buf))
+npts = 4096 * 1024
+out["vtot_grid"] = {"points": npts, "ms": ms, "pts_per_s": npts / ms * 1e3, "GBps": 8.0 * npts / ms * 1e-6,
+                    "hbm_frac": 8.0 * npts / ms * 1e-6 / HBM, "tflops_at_300flop_per_pt": 300.0 * npts / ms * 1e-9}
+# --- finite-T bounces, one-field model (config C5 family): P parameter points x 256 temperatures
+nb = 25600
+for a in sys.argv[1:]:
+    if a.startswith("--nbounce="):
+        nb = int(a.split("=")[1])
+rng = np.random.default_rng(20260101)
+P = nb // 256
+lam = 0.12 * rng.uniform(.8, 1.2, P); Y = 0.35 * rng.uniform(.8, 1.2, P); nn = 30. * rng.uniform(.8, 1.2, P)
+v2 = 246. ** 2
+# window (T0, Tc) from the golden generator's default point scales roughly with the couplings; use a
+# fixed fractional window around a cheap estimate: phi = 0 becomes metastable where the thermal mass
+# turns positive.  Instances that are not metastable / have no barrier just report status 2 / 3.
+T0 = 90.0 * np.sqrt(lam / 0.12) / np.sqrt((Y * nn) / (0.35 * 30)) * 1.0
+Ts = T0[:, None] * (1.0 + 0.22 * (np.arange(256)[None, :] + 0.5) / 256)
+params = np.stack([np.repeat(lam, 256), np.full(P * 256, v2), np.repeat(Y, 256), np.repeat(nn, 256),
+                   np.full(P * 256, v2), Ts.reshape(-1)], axis=1)
+# phi_abs by a crude scan + Newton polish on the device potential is the caller's job (SURVEY s.8f);
+# here: scan on a coarse grid per instance using the potential kernel through torch
+d_par = torch.from_numpy(params).to(dev)
+phis = np.linspace(120.0, 420.0, 601)
+from cosmotransitions_b200.potentials import Model1FPotential  # noqa: E402
+pa = np.empty(P * 256)
+lib = _lib.load()
+from cosmotransitions_b200 import _tables  # noqa: E402
+tabs = _tables.device_tables(dev)
+d_phi = torch.from_numpy(phis).to(dev); d_out = torch.empty_like(d_phi)
+t0 = time.perf_counter()
+for i in range(0, P * 256, 1):
+    if i % 256 and i % 8:   # reuse neighbours' minima between temperatures (coarse: every 8th is rescanned)
+        pa[i] = pa[i - 1]
+        continue
+    _lib.check(lib.ctb_potential(_lib.POT_MODEL1F, d_par[i].contiguous().data_ptr(), tabs.jb, tabs.jf, d_phi.data_ptr(),
+                                 d_out.data_ptr(), d_phi.numel(), None), "pot")
+    v = d_out.cpu().numpy()
+    pa[i] = phis[int(np.argmin(v))]
+t_min = time.perf_counter() - t0
+d_abs = torch.from_numpy(pa).to(dev); d_meta = torch.zeros(P * 256, dtype=torch.float64, device=dev)
+opts = batch.make_opts(alpha=2)
+res = batch.alloc_out(torch, P * 256, dev)
+ms, mn = timeit(lambda: batch.launch_bounce(_lib.POT_MODEL1F, d_par, d_abs, d_meta, opts, res), reps=3)
+st = res["status"].cpu().numpy()
+out["finiteT_bounce_model1f"] = {"instances": P * 256, "ms": ms, "bounces_per_s": P * 256 / ms * 1e3,
+                                 "solved": int((st <= 1).sum()), "status_hist": np.bincount(st, minlength=11).tolist(),
+                                 "tflops_at_1.8e6_flop": 1.8e6 * (st <= 1).sum() / ms * 1e-9,
+                                 "host_minimum_scan_s": t_min}
+print(json.dumps(out))
