@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F = 0, 1, 2
 NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6}
 (ST_CONVERGED, ST_XTOL, ST_STABLE, ST_NO_BARRIER, ST_RMAX, ST_DRMIN, ST_STEP_UNDERFLOW, ST_NONFINITE,
@@ -24,7 +24,8 @@ EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_o
 
 class JTable(C.Structure):
     _fields_ = [("d_brk", C.c_void_p), ("d_coef", C.c_void_p), ("nint", C.c_int32), ("reserved", C.c_int32),
-                ("xmin", C.c_double), ("xmax", C.c_double)]
+                ("xmin", C.c_double), ("xmax", C.c_double), ("loc_scale", C.c_double), ("loc_u0", C.c_double),
+                ("loc_inv_du", C.c_double)]
 
 
 class Opts(C.Structure):

@@ -58,6 +58,18 @@ class HostTables:
         self.tb, self.cb, self.tf, self.cf = d["tb"], d["cb"], d["tf"], d["cf"]
         self.brk_b, self.coef_b = bspline_to_pp(self.tb, self.cb)
         self.brk_f, self.coef_f = bspline_to_pp(self.tf, self.cf)
+        # closed-form locator: the samples sit at x_k = |xmin| sinh(u_k)/20, u_k uniform
+        # (finiteT.py:159-161,189-191) -> (scale, u0, 1/du) with u = asinh(x * scale)
+        self.loc_b = self._locator(d["xb"], self.xbmin)
+        self.loc_f = self._locator(d["xf"], self.xfmin)
+
+    @staticmethod
+    def _locator(x, xmin):
+        scale = 20.0 / abs(xmin)
+        u = np.arcsinh(x * scale)
+        du = (u[-1] - u[0]) / (len(x) - 1)
+        assert np.max(np.abs(np.diff(u) - du)) < 1e-9 * du, "sample grid is not sinh-uniform"
+        return scale, float(u[0]), 1.0 / du
 
 
 _host = None
@@ -79,15 +91,15 @@ class DeviceTables:
         h = host_tables()
         self.device = device
         self._keep = []
-        self.jb = self._make(torch, h.brk_b, h.coef_b, h.xbmin, h.xbmax)
-        self.jf = self._make(torch, h.brk_f, h.coef_f, h.xfmin, h.xfmax)
+        self.jb = self._make(torch, h.brk_b, h.coef_b, h.xbmin, h.xbmax, h.loc_b)
+        self.jf = self._make(torch, h.brk_f, h.coef_f, h.xfmin, h.xfmax, h.loc_f)
 
-    def _make(self, torch, brk, coef, xmin, xmax):
+    def _make(self, torch, brk, coef, xmin, xmax, loc):
         b = torch.from_numpy(np.ascontiguousarray(brk)).to(self.device)
         c = torch.from_numpy(np.ascontiguousarray(coef)).to(self.device)
         assert c.data_ptr() % 32 == 0
         self._keep += [b, c]
-        return _lib.JTable(b.data_ptr(), c.data_ptr(), coef.shape[0], 0, xmin, xmax)
+        return _lib.JTable(b.data_ptr(), c.data_ptr(), coef.shape[0], 0, xmin, xmax, *loc)
 
 
 def device_tables(device):

@@ -8,40 +8,96 @@ using namespace ctb;
 
 namespace {
 
+// Jb_spline / Jf_spline (finiteT.py:167-174,197-204).  HBM-streaming: 8 B in + 8 B out per element.
+// Persistent blocks stage the 40 KB table in shared memory once; each thread keeps UNROLL
+// independent elements in flight.
 template <int DER>
-__global__ void __launch_bounds__(256) jspline_kernel(JTab t, const double *__restrict__ theta,
+__global__ void __launch_bounds__(256) jspline_kernel(JTab g, const double *__restrict__ theta,
                                                       double *__restrict__ out, int64_t n)
 {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = jtab_eval<DER>(t, theta[i]);
+    extern __shared__ double smem[];
+    const JTab t = stage_table(g, smem);
+    __syncthreads();
+    constexpr int UNROLL = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
+        double x[UNROLL], y[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) x[u] = __ldcs(theta + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) y[u] = jtab_eval<DER>(t, x[u]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) __stcs(out + i + u * stride, y[u]);
+    }
+    for (; i < n; i += stride) out[i] = jtab_eval<DER>(t, theta[i]);
 }
 
 struct Model8 { double l1, l2, mu2, Y1, Y2, nb, rs, v2; };
 
-__global__ void __launch_bounds__(256) vtot_model1_kernel(Model8 m, JTab jb, const double *__restrict__ X,
+CTB_DEV double model1_thermal(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
+{
+    double yt = jtab_eval<0>(jb, f.m0 * inv_T2) + jtab_eval<0>(jb, f.m1 * inv_T2) + nb * jtab_eval<0>(jb, f.mb * inv_T2);
+    return f.V01 + yt * T4c;
+}
+
+// Vtot(X_i, T_i) pointwise (generic_potential.py:312-337 for model1)
+__global__ void __launch_bounds__(256) vtot_model1_kernel(Model8 m, JTab g, const double *__restrict__ X,
                                                           const double *__restrict__ T, double *__restrict__ out,
                                                           int64_t n)
 {
+    extern __shared__ double smem[];
+    const JTab jb = stage_table(g, smem);
+    __syncthreads();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double2 x = reinterpret_cast<const double2 *>(X)[i];
-        out[i] = vtot_model1(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, jb, x.x, x.y, T[i]);
+        const double Ti = T[i];
+        const Model1Field f = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, x.x, x.y);
+        const double T2 = Ti * Ti + 1e-100;
+        out[i] = model1_thermal(f, m.nb, jb, 1.0 / T2, (Ti * Ti * Ti * Ti) / (2 * CTB_PI * CTB_PI));
     }
 }
 
-// grid version: thread -> (i = field point, j = temperature); j fastest so that stores coalesce
-__global__ void __launch_bounds__(256) vtot_model1_grid_kernel(Model8 m, double x0, double x1, double n0, double n1,
-                                                               JTab jb, const double *__restrict__ s, int64_t ns,
-                                                               const double *__restrict__ T, int64_t nT,
-                                                               double *__restrict__ out)
+// Vtot on the outer-product grid X_i = x0 + s_i nhat, T_j  (out[i * nT + j]).
+// Persistent blocks (4 per SM): each stages the Jb table in shared memory once and owns a contiguous
+// range of output points, so stores are coalesced and the 148 SMs are evenly loaded whatever the grid
+// shape.  The field-dependent part (three masses, V0 + V1: three logs and a sqrt) is computed once per
+// field point touched by the block and shared through shared memory.
+#define VG_THREADS 256
+#define VG_ROWCAP 64
+__global__ void __launch_bounds__(VG_THREADS) vtot_model1_grid_kernel(Model8 m, double x0, double x1, double n0,
+                                                                      double n1, JTab g, const double *__restrict__ s,
+                                                                      int64_t ns, const double *__restrict__ T,
+                                                                      int64_t nT, double *__restrict__ out,
+                                                                      int64_t chunk)
 {
-    int64_t total = ns * nT;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        int64_t i = idx / nT, j = idx - i * nT;
-        double si = s[i];
-        out[idx] = vtot_model1(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, jb, x0 + si * n0, x1 + si * n1, T[j]);
+    extern __shared__ double smem[];
+    Model1Field *rowc = reinterpret_cast<Model1Field *>(smem);
+    const JTab jb = stage_table(g, smem + VG_ROWCAP * 4);
+    const int64_t total = ns * nT;
+    const int64_t p0 = (int64_t)blockIdx.x * chunk;
+    const int64_t p1 = (p0 + chunk < total) ? p0 + chunk : total;
+    if (p0 < p1) {
+        const int64_t i_first = p0 / nT, i_last = (p1 - 1) / nT;
+        for (int64_t r = threadIdx.x; r <= i_last - i_first; r += VG_THREADS) {
+            const double si = s[i_first + r];
+            rowc[r] = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, x0 + si * n0, x1 + si * n1);
+        }
+        __syncthreads();
+        int64_t p = p0 + threadIdx.x;
+        int64_t i = p / nT, j = p - i * nT;
+        for (; p < p1; p += VG_THREADS) {
+            const double Tj = __ldg(T + j);
+            const double T2 = Tj * Tj;
+            const double inv_T2 = 1.0 / (T2 + 1e-100);
+            const double T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
+            __stcs(out + p, model1_thermal(rowc[i - i_first], m.nb, jb, inv_T2, T4c));
+            j += VG_THREADS;
+            while (j >= nT) { j -= nT; i++; }
+        }
+    } else {
+        __syncthreads();
     }
 }
 
@@ -49,6 +105,11 @@ template <class Pot>
 __global__ void potential_kernel(const double *params, JTab jb, JTab jf, const double *__restrict__ phi,
                                  double *__restrict__ out, int64_t n)
 {
+    extern __shared__ double smem[];
+    if (!Pot::analytic) {
+        jb = stage_table(jb, smem);
+        __syncthreads();
+    }
     Pot pot;
     pot.load(params, &jb, &jf);
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -73,17 +134,22 @@ __global__ void fp64_peak_kernel(int64_t iters, double *sink)
 
 JTab to_jtab(const ctb_jtable *t)
 {
-    JTab j{nullptr, nullptr, 0, 0.0, 0.0};
-    if (t) { j.brk = t->d_brk; j.coef = t->d_coef; j.nint = t->nint; j.xmin = t->xmin; j.xmax = t->xmax; }
+    JTab j{nullptr, nullptr, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f};
+    if (t) {
+        j.brk = t->d_brk; j.coef = t->d_coef; j.nint = t->nint; j.xmin = t->xmin; j.xmax = t->xmax;
+        j.loc_scale = (float)t->loc_scale; j.loc_u0 = (float)t->loc_u0; j.loc_inv_du = (float)t->loc_inv_du;
+    }
     return j;
 }
 
-bool jtab_ok(const ctb_jtable *t) { return t && t->d_brk && t->d_coef && t->nint >= 1; }
+size_t table_bytes(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES(t->nint) * sizeof(double) : 0; }
+
+bool jtab_ok(const ctb_jtable *t) { return t && t->d_brk && t->d_coef && t->nint >= 1 && t->nint <= 5000; }
 
 int grid_for(int64_t n, int block)
 {
     int64_t g = (n + block - 1) / block;
-    const int64_t cap = 148LL * 32; // persistent-style grid-stride for the streaming kernels
+    const int64_t cap = 148LL * 5; // persistent grid-stride blocks (5 x 40 KB table copies per SM)
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
@@ -195,12 +261,14 @@ CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta,
     if (!d_theta || !d_out) return CTB_ERR_BAD_ARG;
     JTab t = to_jtab(tab);
     cudaStream_t st = (cudaStream_t)stream;
-    int g = grid_for(n, 256);
+    const size_t sm = table_bytes(tab);
+    int64_t gneed = (n + 256 * 4 - 1) / (256 * 4);
+    int g = (int)(gneed < 148 * 5 ? (gneed < 1 ? 1 : gneed) : 148 * 5); // persistent: 5 blocks x 40 KB per SM
     switch (deriv) {
-    case 0: jspline_kernel<0><<<g, 256, 0, st>>>(t, d_theta, d_out, n); break;
-    case 1: jspline_kernel<1><<<g, 256, 0, st>>>(t, d_theta, d_out, n); break;
-    case 2: jspline_kernel<2><<<g, 256, 0, st>>>(t, d_theta, d_out, n); break;
-    case 3: jspline_kernel<3><<<g, 256, 0, st>>>(t, d_theta, d_out, n); break;
+    case 0: jspline_kernel<0><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
+    case 1: jspline_kernel<1><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
+    case 2: jspline_kernel<2><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
+    case 3: jspline_kernel<3><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
     default: return CTB_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();
@@ -213,7 +281,7 @@ CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const do
     if (n == 0) return CTB_OK;
     if (!d_X || !d_T || !d_out) return CTB_ERR_BAD_ARG;
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
-    vtot_model1_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(m, to_jtab(jb), d_X, d_T, d_out, n);
+    vtot_model1_kernel<<<grid_for(n, 256), 256, table_bytes(jb), (cudaStream_t)stream>>>(m, to_jtab(jb), d_X, d_T, d_out, n);
     return (int)cudaGetLastError();
 }
 
@@ -224,8 +292,16 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     if (ns == 0 || nT == 0) return CTB_OK;
     if (!d_s || !d_T || !d_out) return CTB_ERR_BAD_ARG;
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
-    vtot_model1_grid_kernel<<<grid_for(ns * nT, 256), 256, 0, (cudaStream_t)stream>>>(
-        m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns, d_T, nT, d_out);
+    // persistent grid: 4 blocks per SM unless that would make a block span more than VG_ROWCAP field points
+    const int64_t total = ns * nT;
+    int64_t nblk = 148 * 4;
+    const int64_t min_blocks = (total + (VG_ROWCAP - 2) * nT - 1) / ((VG_ROWCAP - 2) * nT);
+    if (nblk < min_blocks) nblk = min_blocks;
+    if (nblk > (total + VG_THREADS - 1) / VG_THREADS) nblk = (total + VG_THREADS - 1) / VG_THREADS;
+    const int64_t chunk = (total + nblk - 1) / nblk;
+    vtot_model1_grid_kernel<<<(unsigned)nblk, VG_THREADS, table_bytes(jb) + VG_ROWCAP * 4 * sizeof(double),
+                              (cudaStream_t)stream>>>(m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns,
+                                                      d_T, nT, d_out, chunk);
     return (int)cudaGetLastError();
 }
 
@@ -241,11 +317,11 @@ CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable
     case CTB_POT_POLY4: potential_kernel<PotPoly4><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n); break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotModel1Line><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        potential_kernel<PotModel1Line><<<g, 256, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     case CTB_POT_MODEL1F:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotModel1F><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        potential_kernel<PotModel1F><<<g, 256, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     default: return CTB_ERR_UNSUPPORTED;
     }

@@ -35,8 +35,15 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(c
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < a.n;
     const int64_t i = valid ? (a.order ? a.order[t] : t) : 0;
+    // thermal potentials: the Jb table lives in shared memory for the lifetime of the block
+    extern __shared__ double ctb_smem[];
+    JTab jb = a.jb;
+    if (!Pot::analytic) {
+        jb = stage_table(a.jb, ctb_smem);
+        __syncthreads();
+    }
     Sfi<Pot, ALPHA> s;
-    s.pot.load(a.params + i * Pot::nparam, &a.jb, &a.jf);
+    s.pot.load(a.params + i * Pot::nparam, &jb, &a.jf);
     s.phi_abs = a.phi_abs[i];
     s.phi_meta = a.phi_meta[i];
     InstanceResult r;
@@ -67,10 +74,16 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(c
 template <class Pot>
 __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
 {
+    extern __shared__ double ctb_smem[];
+    JTab jb = a.jb;
+    if (!Pot::analytic) {
+        jb = stage_table(a.jb, ctb_smem);
+        __syncthreads();
+    }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     Pot pot;
-    pot.load(a.params + i * Pot::nparam, &a.jb, &a.jf);
+    pot.load(a.params + i * Pot::nparam, &jb, &a.jf);
     const double pa = a.phi_abs[i], pm = a.phi_meta[i];
     double phi_bar = a.phi_bar_in ? a.phi_bar_in[i] : nan(""), rscale = a.rscale_in ? a.rscale_in[i] : nan("");
     int st = sfi_init(pot, pa, pm, pot.V(pm), phi_bar, rscale);
@@ -84,7 +97,8 @@ __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
 template <class Pot>
 int launch_setup_any(const BounceArgs &a, cudaStream_t st)
 {
-    setup_kernel<Pot><<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a);
+    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double);
+    setup_kernel<Pot><<<(unsigned)((a.n + 127) / 128), 128, sm, st>>>(a);
     return (int)cudaGetLastError();
 }
 
@@ -94,10 +108,11 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     if (block < 32 || block > CTB_MAX_BLOCK || (block & 31)) return CTB_ERR_UNSUPPORTED;
     unsigned grid = (unsigned)((a.n + block - 1) / block);
     const bool prof = a.out.d_prof_R != nullptr;
-    if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false><<<grid, block, 0, st>>>(a);
-    else if (alpha == 3 && !prof) bounce_kernel<Pot, 3, false><<<grid, block, 0, st>>>(a);
-    else if (alpha == 2) bounce_kernel<Pot, 2, true><<<grid, block, 0, st>>>(a);
-    else if (alpha == 3) bounce_kernel<Pot, 3, true><<<grid, block, 0, st>>>(a);
+    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double);
+    if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false><<<grid, block, sm, st>>>(a);
+    else if (alpha == 3 && !prof) bounce_kernel<Pot, 3, false><<<grid, block, sm, st>>>(a);
+    else if (alpha == 2) bounce_kernel<Pot, 2, true><<<grid, block, sm, st>>>(a);
+    else if (alpha == 3) bounce_kernel<Pot, 3, true><<<grid, block, sm, st>>>(a);
     else return CTB_ERR_UNSUPPORTED;
     return (int)cudaGetLastError();
 }

@@ -16,19 +16,47 @@ namespace ctb {
 // ------------------------------------------------------------------------------------------------
 // Jb / Jf spline tables (piecewise cubic, see ctbounce.h)                      FT:167-174,197-204
 struct JTab {
-    const double *__restrict__ brk;
-    const double *__restrict__ coef;
+    const double *brk;  // [nint + 1]; global or (after stage_table) shared memory
+    const double *coef; // [nint * 4]
     int nint;
     double xmin, xmax;
+    float loc_scale, loc_u0, loc_inv_du; // closed-form locator (see ctbounce.h); loc_inv_du == 0: bisection
 };
+
+#define CTB_TABLE_DOUBLES(nint) ((size_t)(nint) * 5 + 2) // brk (nint+1, padded to even) + coef (4 nint)
+
+// Copies a table into shared memory (whole block cooperates; caller syncs) and returns a JTab that
+// points at the copy.  coef lands 16-byte aligned.
+CTB_DEV JTab stage_table(const JTab &g, double *smem)
+{
+    const int nb = (g.nint + 2) & ~1;
+    for (int i = threadIdx.x; i < g.nint + 1; i += blockDim.x) smem[i] = g.brk[i];
+    for (int i = threadIdx.x; i < 4 * g.nint; i += blockDim.x) smem[nb + i] = g.coef[i];
+    JTab t = g;
+    t.brk = smem;
+    t.coef = smem + nb;
+    return t;
+}
 
 CTB_DEV int jtab_locate(const JTab &t, double x)
 {
     // largest j in [0, nint-1] with brk[j] <= x  (j = 0 below the table: first piece extrapolates)
-    int lo = 0, hi = t.nint - 1;
+    const int last = t.nint - 1;
+    if (t.loc_inv_du != 0.0f) {
+        // FP32 guess from the sinh spacing of the reference's sample grid, then exact fix-up in FP64
+        float z = (float)x * t.loc_scale;
+        float a = fabsf(z);
+        float u = copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), z);
+        float kf = floorf((u - t.loc_u0) * t.loc_inv_du) - 1.0f;
+        int j = (int)fminf(fmaxf(kf, 0.0f), (float)last);
+        while (j > 0 && x < t.brk[j]) --j;
+        while (j < last && x >= t.brk[j + 1]) ++j;
+        return j;
+    }
+    int lo = 0, hi = last;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
-        if (x >= __ldg(t.brk + mid)) lo = mid; else hi = mid - 1;
+        if (x >= t.brk[mid]) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
@@ -38,9 +66,9 @@ CTB_DEV double jtab_eval(const JTab &t, double theta)
 {
     double x = (theta < t.xmin) ? t.xmin : theta;
     int j = jtab_locate(t, x);
-    double dx = x - __ldg(t.brk + j);
-    const double2 c01 = __ldg(reinterpret_cast<const double2 *>(t.coef) + 2 * j);
-    const double2 c23 = __ldg(reinterpret_cast<const double2 *>(t.coef) + 2 * j + 1);
+    double dx = x - t.brk[j];
+    const double2 c01 = reinterpret_cast<const double2 *>(t.coef)[2 * j];
+    const double2 c23 = reinterpret_cast<const double2 *>(t.coef)[2 * j + 1];
     struct { double x, y, z, w; } c = {c01.x, c01.y, c23.x, c23.y};
     double v;
     if (DER == 0) v = c.x + dx * (c.y + dx * (c.z + dx * c.w));
@@ -75,6 +103,29 @@ struct PotPoly4 {
     CTB_DEV double dV(double x) const { return c1 + x * (2 * c2 + x * (3 * c3 + x * 4 * c4)); }
     CTB_DEV double d2V(double x) const { return 2 * c2 + x * (6 * c3 + x * 12 * c4); }
 };
+
+// Field-dependent part of model1's Vtot: the three boson masses (examples/testModel1.py:89-93) and
+// V0 + V1 (examples/testModel1.py:78-80, GP:240-256).  Independent of T.
+struct Model1Field { double m0, m1, mb, V01; };
+CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, double Y2, double nb, double rs, double v2,
+                                 double phi1, double phi2)
+{
+    double a = l1 * (3 * phi1 * phi1 - v2);
+    double b = l2 * (3 * phi2 * phi2 - v2);
+    double A = .5 * (a + b);
+    double B = sqrt(.25 * (a - b) * (a - b) + mu2 * mu2);
+    Model1Field f;
+    f.mb = Y1 * (phi1 * phi1 + phi2 * phi2) + Y2 * phi1 * phi2;
+    f.m0 = A + B; f.m1 = A - B;
+    double r = .25 * l1 * (phi1 * phi1 - v2) * (phi1 * phi1 - v2) + .25 * l2 * (phi2 * phi2 - v2) * (phi2 * phi2 - v2);
+    r -= mu2 * phi1 * phi2;
+    double y1 = 0.0;
+    y1 += 1.0 * f.m0 * f.m0 * (log(fabs(f.m0 / rs) + 1e-100) - 1.5);
+    y1 += 1.0 * f.m1 * f.m1 * (log(fabs(f.m1 / rs) + 1e-100) - 1.5);
+    y1 += nb * f.mb * f.mb * (log(fabs(f.mb / rs) + 1e-100) - 1.5);
+    f.V01 = r + y1 / (64 * CTB_PI * CTB_PI);
+    return f;
+}
 
 // examples/testModel1.py:62-116 through GP:312-337, on the line X = x0 + phi*nhat
 CTB_DEV double vtot_model1(double l1, double l2, double mu2, double Y1, double Y2, double nb, double rs, double v2,
@@ -113,7 +164,9 @@ struct PotModel1Line {
         x0 = p[9]; x1 = p[10]; n0 = p[11]; n1 = p[12];
         jb = *jb_;
     }
-    CTB_DEV double V(double phi) const
+    // out of line: V is called from ~15 places (5-point stencils, bisection, fminbound, integrand);
+    // one copy keeps the kernel inside the instruction cache
+    __device__ __noinline__ double V(double phi) const
     {
         return vtot_model1(l1, l2, mu2, Y1, Y2, nb, rs, v2, jb, x0 + phi * n0, x1 + phi * n1, T);
     }
@@ -130,7 +183,7 @@ struct PotModel1F {
         lam = p[0]; v2 = p[1]; Y = p[2]; nb = p[3]; rs = p[4]; T = p[5];
         jb = *jb_;
     }
-    CTB_DEV double V(double phi) const
+    __device__ __noinline__ double V(double phi) const // out of line, see PotModel1Line::V
     {
         double m0 = lam * (3 * phi * phi - v2), m1 = Y * phi * phi;
         double r = .25 * lam * (phi * phi - v2) * (phi * phi - v2);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 2
+#define CTB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -79,6 +79,12 @@ typedef struct ctb_jtable {
     int32_t reserved;
     double xmin;          /* theta < xmin  -> value (or derivative) at xmin   finiteT.py:172,202   */
     double xmax;          /* theta > xmax  -> 0                               finiteT.py:173,203   */
+    /* Optional closed-form interval locator.  The reference samples both functions at
+     * x_k = |xmin| sinh(u_k) / 20 with u_k uniform (finiteT.py:159-161,189-191), so
+     * k ~ (asinh(theta * loc_scale) - loc_u0) * loc_inv_du and the knot interval is k - 1 (not-a-knot
+     * spline: x_1 and x_{n-2} are not breakpoints); the kernels correct the guess by comparing with
+     * d_brk.  loc_inv_du = 0 selects plain bisection.                                             */
+    double loc_scale, loc_u0, loc_inv_du;
 } ctb_jtable;
 
 /* ---- findProfile knobs (tunneling1D.py:128-130, 615-617); same defaults as the reference ---- */

@@ -39,8 +39,16 @@ out = {}
 n = 1 << 26
 theta = (torch.rand(n, dtype=torch.float64, device=dev) * 2010.0) - 10.0
 ms, mn = timeit(lambda: finiteT.Jb_spline(theta))
-out["jb_spline"] = {"n": n, "ms": ms, "evals_per_s": n / ms * 1e3, "GBps": 16.0 * n / ms * 1e-6,
-                    "hbm_frac": 16.0 * n / ms * 1e-6 / HBM, "bytes_per_eval": 16}
+out["jb_spline_random_theta"] = {"n": n, "ms": ms, "evals_per_s": n / ms * 1e3, "GBps": 16.0 * n / ms * 1e-6,
+                                 "hbm_frac": 16.0 * n / ms * 1e-6 / HBM, "bytes_per_eval": 16}
+# the shape generic_potential produces: m^2(phi_i) / T_j^2 over a (phi, T) grid -- smooth in memory order
+phi_g = torch.linspace(0.0, 400.0, 8192, dtype=torch.float64, device=dev)
+T_g = torch.linspace(20.0, 250.0, 8192, dtype=torch.float64, device=dev)
+theta_g = ((0.1 * phi_g * phi_g)[:, None] / (T_g * T_g)[None, :]).contiguous().reshape(-1)
+ms, mn = timeit(lambda: finiteT.Jb_spline(theta_g))
+out["jb_spline_grid_theta"] = {"n": n, "ms": ms, "evals_per_s": n / ms * 1e3, "GBps": 16.0 * n / ms * 1e-6,
+                               "hbm_frac": 16.0 * n / ms * 1e-6 / HBM, "bytes_per_eval": 16}
+del theta_g
 # --- model1 Vtot grid 4096 x 1024 (config C4)
 m = gp.model1()
 x_low = np.array([286.39824989, 382.19727238]); x_high = np.array([231.10296383, -136.82260069])
