@@ -55,6 +55,10 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.windows = {}
+
+    def mark(self, name, t0, t1):
+        self.windows[name] = (t0, t1)
 
     def start(self):
         try:
@@ -68,7 +72,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -79,17 +83,30 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        # prefer samples taken inside the timed region; a region shorter than a few sampling periods
+        # falls back to every sample taken while the same kernel loop kept the GPU busy
+        # (warm-up + timed region + end-to-end loop)
+        window = "timed region"
+        t0, t1 = self.windows.get("timed", (0, 0))
+        sm, mx, reasons = summarise([x for x in self.rows if t0 <= x[0] <= t1])
+        if len(sm) < 3:
+            window = "under load (warm-up + timed region + end-to-end loop of the same step)"
+            t0, t1 = self.windows.get("load", (0, float("inf")))
+            sm, mx, reasons = summarise([x for x in self.rows if t0 <= x[0] <= t1])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_oracle_rate(wl, threads, sample_stride, c=None):
@@ -202,11 +219,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    t_load0 = time.perf_counter()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # keep the same step running (untimed) until the clocks have settled and the sampler is reporting
+    while time.perf_counter() - t_load0 < 0.6:
+        step()
+        torch.cuda.synchronize()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -217,7 +240,7 @@ def main():
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    sampler.mark("timed", t_wall0, t_wall0 + t_wall)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(kern_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -252,6 +275,8 @@ def main():
     e1.record()
     barrier()
     e2e_wall = time.perf_counter() - t0
+    sampler.mark("load", t_load0, time.perf_counter())
+    clocks = sampler.stop()
     e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -18,7 +18,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6}
  ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN) = range(11)
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
-           "ctb_bounce_setup",
+           "ctb_bounce_setup", "ctb_potential_batch", "ctb_minimize_1d",
            "ctb_jspline", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
 
 
@@ -89,6 +89,12 @@ def load():
     lib.ctb_potential.restype = C.c_int
     lib.ctb_potential.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p]
+    lib.ctb_potential_batch.restype = C.c_int
+    lib.ctb_potential_batch.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_void_p]
+    lib.ctb_minimize_1d.restype = C.c_int
+    lib.ctb_minimize_1d.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
+                                    C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ctb_fp64_peak.restype = C.c_int
     lib.ctb_fp64_peak.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     if lib.ctb_abi_version() != ABI_VERSION:

@@ -116,6 +116,32 @@ __global__ void potential_kernel(const double *params, JTab jb, JTab jf, const d
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = pot.V(phi[i]);
 }
 
+// V_i(phi_i) for n parameter rows / fminbound of V_i on [lo_i, hi_i]: one thread per row
+template <class Pot, bool MINIMIZE>
+__global__ void __launch_bounds__(128) rows_kernel(const double *__restrict__ params, JTab jb, JTab jf,
+                                                   const double *__restrict__ a, const double *__restrict__ b,
+                                                   double xtol_rel, double *__restrict__ out0,
+                                                   double *__restrict__ out1, int64_t n)
+{
+    extern __shared__ double smem[];
+    if (!Pot::analytic) {
+        jb = stage_table(jb, smem);
+        __syncthreads();
+    }
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pot pot;
+    pot.load(params + i * Pot::nparam, &jb, &jf);
+    if (!MINIMIZE) {
+        out0[i] = pot.V(a[i]);
+    } else {
+        const double lo = a[i], hi = b[i];
+        const double x = fminbound([&](double p) { return pot.V(p); }, lo, hi, xtol_rel * (hi - lo));
+        out0[i] = x;
+        if (out1) out1[i] = pot.V(x);
+    }
+}
+
 __global__ void fp64_peak_kernel(int64_t iters, double *sink)
 {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -145,6 +171,31 @@ JTab to_jtab(const ctb_jtable *t)
 size_t table_bytes(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES(t->nint) * sizeof(double) : 0; }
 
 bool jtab_ok(const ctb_jtable *t) { return t && t->d_brk && t->d_coef && t->nint >= 1 && t->nint <= 5000; }
+
+template <bool MINIMIZE>
+int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf, const double *a,
+                const double *b, double xtol_rel, double *o0, double *o1, int64_t n, cudaStream_t st)
+{
+    unsigned g = (unsigned)((n + 127) / 128);
+    switch (pot_kind) {
+    case CTB_POT_POLY4:
+        rows_kernel<PotPoly4, MINIMIZE><<<g, 128, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b, xtol_rel, o0, o1, n);
+        break;
+    case CTB_POT_MODEL1_LINE:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        rows_kernel<PotModel1Line, MINIMIZE><<<g, 128, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+                                                                             xtol_rel, o0, o1, n);
+        break;
+    case CTB_POT_MODEL1F:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        rows_kernel<PotModel1F, MINIMIZE><<<g, 128, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+                                                                          xtol_rel, o0, o1, n);
+        break;
+    default: return CTB_ERR_UNSUPPORTED;
+    }
+    return (int)cudaGetLastError();
+}
+
 
 int grid_for(int64_t n, int block)
 {
@@ -326,6 +377,25 @@ CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable
     default: return CTB_ERR_UNSUPPORTED;
     }
     return (int)cudaGetLastError();
+}
+
+CTB_API int ctb_potential_batch(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                                const double *d_phi, double *d_out, int64_t n, void *stream)
+{
+    if (n < 0) return CTB_ERR_BAD_ARG;
+    if (n == 0) return CTB_OK;
+    if (!d_params || !d_phi || !d_out) return CTB_ERR_BAD_ARG;
+    return launch_rows<false>(pot_kind, d_params, jb, jf, d_phi, nullptr, 0.0, d_out, nullptr, n, (cudaStream_t)stream);
+}
+
+CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                            const double *d_lo, const double *d_hi, double xtol_rel, int64_t n, double *d_xmin,
+                            double *d_vmin, void *stream)
+{
+    if (n < 0 || !(xtol_rel > 0)) return CTB_ERR_BAD_ARG;
+    if (n == 0) return CTB_OK;
+    if (!d_params || !d_lo || !d_hi || !d_xmin) return CTB_ERR_BAD_ARG;
+    return launch_rows<true>(pot_kind, d_params, jb, jf, d_lo, d_hi, xtol_rel, d_xmin, d_vmin, n, (cudaStream_t)stream);
 }
 
 CTB_API int ctb_fp64_peak(int64_t iters, int blocks, int threads, double *d_sink, float *ms_out, void *stream)

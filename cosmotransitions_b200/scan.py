@@ -1,0 +1,126 @@
+"""Batched helpers around the bounce solver for finite-temperature parameter scans (BASELINE.json
+configs[4]): per-instance potential evaluation, bounded 1-D
+minimisation (phi_absMin(T)), the temperature window (T0, Tc) of the one-field thermal model, and the
+S3(T)/T sweep with the nucleation criterion S3/T = 140 (transitionFinder.py:773).
+
+Everything numerical runs on the device in batches; torch is the container and does the bookkeeping
+(bisection brackets, interpolation of the crossing)."""
+import numpy as np
+
+from . import _lib, _tables, batch
+
+
+def _prep(torch, kind, params, *vecs):
+    dev = params.device if isinstance(params, torch.Tensor) and params.is_cuda else torch.device(
+        "cuda", torch.cuda.current_device())
+    p = batch._as_device(torch, params, dev).reshape(-1, _lib.NPARAM[kind])
+    n = p.shape[0]
+    return dev, p, n, [batch._as_device(torch, v, dev, (n,)) for v in vecs]
+
+
+def potential_batch(kind, params, phi):
+    """V_i(phi_i) for N parameter rows (device tensor [N])."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev, p, n, (ph,) = _prep(torch, kind, params, phi)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.ctb_potential_batch(kind, p.data_ptr(), tabs.jb if tabs else None, tabs.jf if tabs else None,
+                                           ph.data_ptr(), out.data_ptr(), n,
+                                           torch.cuda.current_stream(dev).cuda_stream), "ctb_potential_batch")
+    return out
+
+
+def minimize_1d(kind, params, lo, hi, xtol_rel=1e-10):
+    """argmin of V_i on [lo_i, hi_i] (scipy.optimize.fminbound's algorithm, one thread per row).
+    Returns (x, V(x)) as device tensors."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev, p, n, (a, b) = _prep(torch, kind, params, lo, hi)
+    x = torch.empty(n, dtype=torch.float64, device=dev)
+    v = torch.empty(n, dtype=torch.float64, device=dev)
+    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.ctb_minimize_1d(kind, p.data_ptr(), tabs.jb if tabs else None, tabs.jf if tabs else None,
+                                       a.data_ptr(), b.data_ptr(), float(xtol_rel), n, x.data_ptr(), v.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream), "ctb_minimize_1d")
+    return x, v
+
+
+# ---- one-field thermal model (CTB_POT_MODEL1F): params = [lam, v2, Y, n, renormScaleSq, T] -------------
+
+def model1f_params(lam, Y, n, T, v2=246. ** 2):
+    torch = _lib.require_cuda()
+    lam, Y, n, T = (torch.as_tensor(x, dtype=torch.float64).cuda() for x in (lam, Y, n, T))
+    lam, Y, n, T = torch.broadcast_tensors(lam, Y, n, T)
+    v2t = torch.full_like(lam, v2)
+    return torch.stack([lam, v2t, Y, n, v2t, T], dim=-1).contiguous()
+
+
+def model1f_temperature_window(lam, Y, n, v2=246. ** 2, T_lo=20.0, T_hi=300.0, phi_box=(50.0, 500.0), iters=48):
+    """(T0, Tc) per parameter point, by batched bisection in T:
+    T0 -- phi = 0 turns into a local minimum (V(h) - V(0) changes sign at h = 0.5);
+    Tc -- the broken minimum becomes degenerate with phi = 0.  Device tensors [P]."""
+    torch = _lib.require_cuda()
+    lam, Y, n = (torch.as_tensor(x, dtype=torch.float64).cuda().reshape(-1) for x in (lam, Y, n))
+    P = lam.numel()
+    kind = _lib.POT_MODEL1F
+    zero = torch.zeros(P, dtype=torch.float64, device=lam.device)
+    half = torch.full_like(zero, 0.5)
+
+    def curv0(T):
+        p = model1f_params(lam, Y, n, T, v2)
+        return potential_batch(kind, p, half) - potential_batch(kind, p, zero)
+
+    def gap(T):
+        p = model1f_params(lam, Y, n, T, v2)
+        _, vmin = minimize_1d(kind, p, torch.full_like(zero, phi_box[0]), torch.full_like(zero, phi_box[1]))
+        return vmin - potential_batch(kind, p, zero)
+
+    def bisect(f, a, b):
+        fa = f(a)
+        for _ in range(iters):
+            m = 0.5 * (a + b)
+            fm = f(m)
+            left = (fm > 0) == (fa > 0)
+            a = torch.where(left, m, a)
+            fa = torch.where(left, fm, fa)
+            b = torch.where(left, b, m)
+        return 0.5 * (a + b)
+
+    T0 = bisect(curv0, torch.full_like(zero, T_lo), torch.full_like(zero, T_hi))
+    Tc = bisect(gap, T0 + 0.5, torch.full_like(zero, T_hi))
+    return T0, Tc
+
+
+def model1f_bounce_scan(lam, Y, n, nT=256, v2=246. ** 2, window=None, phi_box=(50.0, 500.0), alpha=2, **knobs):
+    """P parameter points x nT temperatures uniform in (T0, Tc): phi_absMin(T) by minimize_1d, then one
+    bounce per (point, T).  Returns a dict of device tensors shaped [P, nT]: T, phi_abs, S, status, plus
+    T0, Tc [P] and Tnuc [P] (first T, from above, where S/T crosses 140; NaN if it never does)."""
+    torch = _lib.require_cuda()
+    lam, Y, n = (torch.as_tensor(x, dtype=torch.float64).cuda().reshape(-1) for x in (lam, Y, n))
+    P = lam.numel()
+    T0, Tc = window if window is not None else model1f_temperature_window(lam, Y, n, v2, phi_box=phi_box)
+    frac = (torch.arange(nT, dtype=torch.float64, device=lam.device) + 0.5) / nT
+    T = T0[:, None] + frac[None, :] * (Tc - T0)[:, None]
+    params = model1f_params(lam[:, None], Y[:, None], n[:, None], T, v2).reshape(-1, 6)
+    lo = torch.full((P * nT,), phi_box[0], dtype=torch.float64, device=lam.device)
+    hi = torch.full((P * nT,), phi_box[1], dtype=torch.float64, device=lam.device)
+    phi_abs, _ = minimize_1d(_lib.POT_MODEL1F, params, lo, hi)
+    res = batch.find_bounce_batch(_lib.POT_MODEL1F, params, phi_abs, torch.zeros_like(phi_abs), alpha=alpha, **knobs)
+    S = res["S"].reshape(P, nT)
+    st = res["status"].reshape(P, nT)
+    soT = torch.where(st <= 1, S / T, torch.full_like(S, float("nan")))
+    # nucleation: S/T decreases as T falls below Tc; find the highest-T crossing of 140
+    above = soT[:, 1:] > 140.0
+    below = soT[:, :-1] <= 140.0
+    cross = above & below
+    idx = torch.where(cross.any(dim=1), (cross.to(torch.int64) * torch.arange(1, nT, device=S.device)).amax(dim=1),
+                      torch.zeros(P, dtype=torch.int64, device=S.device))
+    i0 = (idx - 1).clamp(min=0)
+    y0, y1 = soT.gather(1, i0[:, None])[:, 0], soT.gather(1, idx[:, None])[:, 0]
+    t0, t1 = T.gather(1, i0[:, None])[:, 0], T.gather(1, idx[:, None])[:, 0]
+    Tnuc = torch.where(cross.any(dim=1), t0 + (140.0 - y0) * (t1 - t0) / (y1 - y0), torch.full_like(t0, float("nan")))
+    return dict(T=T, phi_abs=phi_abs.reshape(P, nT), S=S, status=st, S_over_T=soT, T0=T0, Tc=Tc, Tnuc=Tnuc,
+                n_rkck=res["n_rkck"].reshape(P, nT))

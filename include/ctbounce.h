@@ -173,6 +173,18 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
 CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
                   const double *d_phi, double *d_out, int64_t n, void *stream);
 
+/* V_i(phi_i): one field value per parameter row (d_params [n, nparam], d_phi [n] -> d_out [n]).
+ * The batched form of calling the user's V(phi) (tunneling1D.py:132) for n different potentials. */
+CTB_API int ctb_potential_batch(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                                const double *d_phi, double *d_out, int64_t n, void *stream);
+
+/* Batched bounded 1-D minimisation: x_i = argmin V_i(phi) on [lo_i, hi_i] by scipy.optimize.fminbound's
+ * algorithm (the routine findRScale uses, tunneling1D.py:264-265) with xatol_i = xtol_rel * (hi_i - lo_i).
+ * Feeds phi_absMin(T) to the finite-temperature scans.  d_vmin may be NULL. */
+CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                            const double *d_lo, const double *d_hi, double xtol_rel, int64_t n, double *d_xmin,
+                            double *d_vmin, void *stream);
+
 /* Register-resident FP64 FMA loop used to measure the FP64 roofline denominator.
  * Runs iters * 16 dependent-chain-free FMAs per thread; returns elapsed ms via *ms_out (synchronous). */
 CTB_API int ctb_fp64_peak(int64_t iters, int blocks, int threads, double *d_sink, float *ms_out, void *stream);

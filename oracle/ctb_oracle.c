@@ -1155,6 +1155,33 @@ CTBO_API int ctbo_rkqs_poly4(const double *coef5, int alpha, const double y[2], 
     return e;
 }
 
+/* V_i(phi_i), one field value per parameter row */
+CTBO_API void ctbo_potential_rows(const ctbo_config *cfg, const double *params, const double *phi, double *out,
+                                  int64_t n)
+{
+    opts_t o; spline_t jb, jf;
+    cfg_to(cfg, &o, &jb, &jf);
+    for (int64_t i = 0; i < n; i++) {
+        pot_t pot = {cfg->kind, params + i * cfg->nparam, &jb, &jf};
+        out[i] = pot_V(&pot, phi[i]);
+    }
+}
+
+static double posV(double x, void *v) { return pot_V((const pot_t *)v, x); }
+
+/* fminbound of V_i on [lo_i, hi_i], xatol_i = xtol_rel (hi_i - lo_i)  (scipy.optimize.fminbound restated) */
+CTBO_API void ctbo_minimize_1d(const ctbo_config *cfg, const double *params, const double *lo, const double *hi,
+                               double xtol_rel, int64_t n, double *xmin, double *vmin)
+{
+    opts_t o; spline_t jb, jf;
+    cfg_to(cfg, &o, &jb, &jf);
+    for (int64_t i = 0; i < n; i++) {
+        pot_t pot = {cfg->kind, params + i * cfg->nparam, &jb, &jf};
+        xmin[i] = fminbound(posV, &pot, lo[i], hi[i], xtol_rel * (hi[i] - lo[i]), 500, NULL);
+        if (vmin) vmin[i] = pot_V(&pot, xmin[i]);
+    }
+}
+
 /* phi_bar= / rscale= overrides of __init__ for subsequent calls (NaN = None). Not thread-safe: tests only. */
 CTBO_API void ctbo_set_overrides(double phi_bar, double rscale)
 {

@@ -165,6 +165,24 @@ def potential(cfg, params, phi):
     return out
 
 
+def potential_rows(cfg, params, phi):
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, cfg.nparam)
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    out = np.empty_like(phi)
+    lib().ctbo_potential_rows(C.byref(cfg), _dp(params), _dp(phi), _dp(out), C.c_int64(phi.size))
+    return out
+
+
+def minimize_1d(cfg, params, lo, hi, xtol_rel):
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, cfg.nparam)
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    x, v = np.empty_like(lo), np.empty_like(lo)
+    lib().ctbo_minimize_1d(C.byref(cfg), _dp(params), _dp(lo), _dp(hi), C.c_double(xtol_rel), C.c_int64(lo.size),
+                           _dp(x), _dp(v))
+    return x, v
+
+
 def vtot_model1_grid(cfg, params, s, T):
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(13)
     s = np.ascontiguousarray(s, dtype=np.float64)

@@ -257,6 +257,66 @@ def test_model1f_golden_and_oracle(ctb, oracle, tables, gold_dir):
     assert np.abs(r["S"] - o["S"]).max() / S_ref.max() < S_RTOL
 
 
+def test_minimize_and_potential_batch_vs_oracle(ctb, oracle, tables):
+    from cosmotransitions_b200 import _lib, scan
+    rng = np.random.default_rng(8)
+    n = 500
+    params = np.stack([0.12 * rng.uniform(.8, 1.2, n), np.full(n, 246. ** 2), 0.35 * rng.uniform(.8, 1.2, n),
+                       30. * rng.uniform(.8, 1.2, n), np.full(n, 246. ** 2), rng.uniform(60, 140, n)], axis=1)
+    phi = rng.uniform(-50, 450, n)
+    cfg = oracle.make_config(kind=oracle.POT_MODEL1F, tables=tables)
+    V = scan.potential_batch(_lib.POT_MODEL1F, params, phi).cpu().numpy()
+    np.testing.assert_allclose(V, oracle.potential_rows(cfg, params, phi), rtol=1e-11, atol=1e-3)
+    lo, hi = np.full(n, 50.0), np.full(n, 500.0)
+    x, v = scan.minimize_1d(_lib.POT_MODEL1F, params, lo, hi, xtol_rel=1e-10)
+    xo, vo = oracle.minimize_1d(cfg, params, lo, hi, 1e-10)
+    # fminbound's floor is sqrt(eps) |x| ~ 5e-6 here; both follow the same algorithm
+    np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=0, atol=5e-5)
+    np.testing.assert_allclose(v.cpu().numpy(), vo, rtol=1e-12, atol=1e-3)
+    # polynomial rows (fminbound's own parabola arithmetic contracts to FMAs on the device: same
+    # algorithm, last-ulp differences in the iterates, both inside xatol of the minimum at phi = 1)
+    from cosmotransitions_b200 import potentials
+    c = rng.uniform(0.05, 0.45, n)
+    pp = potentials.quartic_family_params(c)
+    x, _ = scan.minimize_1d(_lib.POT_POLY4, pp, np.full(n, 0.6), np.full(n, 1.5), xtol_rel=1e-9)
+    xo, _ = oracle.minimize_1d(oracle.make_config(), pp, np.full(n, 0.6), np.full(n, 1.5), 1e-9)
+    np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=0, atol=2e-8)
+    assert np.abs(xo - 1.0).max() < 1e-6
+
+
+def test_model1f_scan_vs_golden(ctb, gold_dir):
+    """Config C5 pipeline on the golden parameter points: temperature window, phi_absMin(T) and the
+    bounce, all on the device, against the reference's brentq / minimize_scalar / findAction."""
+    from cosmotransitions_b200 import _lib, batch, scan
+    cases = json.load(open(os.path.join(gold_dir, "model1f.json")))
+    pts = {}
+    for c in cases:
+        pts.setdefault((c["lam"], c["Y"], c["n"]), []).append(c)
+    keys = list(pts)
+    lam, Y, n = (np.array([k[i] for k in keys]) for i in range(3))
+    T0, Tc = scan.model1f_temperature_window(lam, Y, n)
+    np.testing.assert_allclose(T0.cpu().numpy(), [pts[k][0]["T0"] for k in keys], rtol=1e-7)
+    np.testing.assert_allclose(Tc.cpu().numpy(), [pts[k][0]["Tc"] for k in keys], rtol=1e-7)
+    params = np.array([[c["lam"], c["v2"], c["Y"], c["n"], c["v2"], c["T"]] for c in cases])
+    m = len(cases)
+    x, _ = scan.minimize_1d(_lib.POT_MODEL1F, params, np.full(m, 50.0), np.full(m, 500.0))
+    np.testing.assert_allclose(x.cpu().numpy(), [c["phi_abs"] for c in cases], rtol=0, atol=2e-4)
+    r = batch.find_bounce_batch(_lib.POT_MODEL1F, params, x, np.zeros(m))
+    S_ref = np.array([c["S"] for c in cases])
+    rel = np.abs(r["S"].cpu().numpy() - S_ref) / S_ref
+    print("S with device-found phi_abs, max rel:", rel.max())
+    assert rel.max() < 1e-5
+    # the sweep itself: S/T falls monotonically from Tc towards T0 and crosses 140 once
+    out = scan.model1f_bounce_scan(lam[:2], Y[:2], n[:2], nT=64)
+    soT = out["S_over_T"].cpu().numpy()
+    assert np.isfinite(out["Tnuc"].cpu().numpy()).all()
+    for row, t0, tc, tn in zip(soT, out["T0"].cpu().numpy(), out["Tc"].cpu().numpy(), out["Tnuc"].cpu().numpy()):
+        ok = np.isfinite(row)
+        assert ok.mean() > 0.9
+        assert np.all(np.diff(row[ok]) > 0)
+        assert t0 < tn < tc
+
+
 def test_c2_full_size_properties(ctb):
     """BASELINE.json config C2 at full size (1e5 quartic instances, alpha=2): size-independent
     properties -- every instance solves, S(c) is strictly increasing along the thick->thin sweep,
