@@ -124,3 +124,43 @@ def model1f_bounce_scan(lam, Y, n, nT=256, v2=246. ** 2, window=None, phi_box=(5
     Tnuc = torch.where(cross.any(dim=1), t0 + (140.0 - y0) * (t1 - t0) / (y1 - y0), torch.full_like(t0, float("nan")))
     return dict(T=T, phi_abs=phi_abs.reshape(P, nT), S=S, status=st, S_over_T=soT, T0=T0, Tc=Tc, Tnuc=Tnuc,
                 n_rkck=res["n_rkck"].reshape(P, nT))
+
+
+# ---- model1 along a fixed straight line (BASELINE.json configs[3]) -------------------
+
+def model1_line_bounce_scan(model8, x_low, x_high, T, alpha=2, **knobs):
+    """Per-temperature 1-D bounce along the fixed line X(s) = x_low + s nhat, s in [-0.2 L, 1.2 L]:
+    for every T the two minima along the line are located on the device (minimize_1d on the two halves
+    of the line), then one bounce per T is solved from the deeper to the shallower one.
+    Returns device tensors [len(T)]: T, s_abs, s_meta, S, S_over_T, status and Tnuc (scalar tensor: the
+    S/T = 140 crossing, transitionFinder.py:773; NaN if there is none)."""
+    torch = _lib.require_cuda()
+    kind = _lib.POT_MODEL1_LINE
+    x_low, x_high = np.asarray(x_low, float), np.asarray(x_high, float)
+    L = float(np.linalg.norm(x_high - x_low))
+    nhat = (x_high - x_low) / L
+    T = torch.as_tensor(T, dtype=torch.float64).cuda().reshape(-1)
+    n = T.numel()
+    base = torch.tensor(list(model8) + [0.0] + list(x_low) + list(nhat), dtype=torch.float64, device=T.device)
+    params = base[None, :].repeat(n, 1)
+    params[:, 8] = T
+    full = lambda v: torch.full((n,), v, dtype=torch.float64, device=T.device)
+    sa, va = minimize_1d(kind, params, full(-0.2 * L), full(0.45 * L))
+    sm, vm = minimize_1d(kind, params, full(0.55 * L), full(1.2 * L))
+    # tunnel from the higher minimum (metastable) to the lower one
+    swap = va > vm
+    s_abs, s_meta = torch.where(swap, sm, sa), torch.where(swap, sa, sm)
+    res = batch.find_bounce_batch(kind, params, s_abs, s_meta, alpha=alpha, **knobs)
+    S, st = res["S"], res["status"]
+    soT = torch.where(st <= 1, S / T, torch.full_like(S, float("nan")))
+    Tn = torch.tensor(float("nan"), dtype=torch.float64, device=T.device)
+    order = torch.argsort(T)
+    y, t = soT[order], T[order]
+    good = torch.isfinite(y)
+    y, t = y[good], t[good]
+    if y.numel() > 1:
+        c = ((y[:-1] <= 140.0) & (y[1:] > 140.0)).nonzero()
+        if c.numel():
+            i = int(c[-1])
+            Tn = t[i] + (140.0 - y[i]) * (t[i + 1] - t[i]) / (y[i + 1] - y[i])
+    return dict(T=T, s_abs=s_abs, s_meta=s_meta, S=S, S_over_T=soT, status=st, Tnuc=Tn, L=L)
