@@ -19,7 +19,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6}
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_potential_batch", "ctb_minimize_1d",
-           "ctb_jspline", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
+           "ctb_jspline", "ctb_jseries", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
 
 
 class JTable(C.Structure):
@@ -80,6 +80,9 @@ def load():
                                      C.POINTER(BounceOut), C.c_void_p, C.c_void_p]
     lib.ctb_jspline.restype = C.c_int
     lib.ctb_jspline.argtypes = [C.POINTER(JTable), C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.ctb_jseries.restype = C.c_int
+    lib.ctb_jseries.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
+                                C.c_int64, C.c_void_p]
     lib.ctb_vtot_model1.restype = C.c_int
     lib.ctb_vtot_model1.argtypes = [C.POINTER(C.c_double), C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p]

@@ -56,6 +56,7 @@ class HostTables:
         self.xbmin, self.xbmax = float(d["xbmin"]), float(d["xbmax"])
         self.xfmin, self.xfmax = float(d["xfmin"]), float(d["xfmax"])
         self.tb, self.cb, self.tf, self.cf = d["tb"], d["cb"], d["tf"], d["cf"]
+        self.low_b, self.low_f = np.ascontiguousarray(d["low_b"]), np.ascontiguousarray(d["low_f"])
         self.brk_b, self.coef_b = bspline_to_pp(self.tb, self.cb)
         self.brk_f, self.coef_f = bspline_to_pp(self.tf, self.cf)
         # closed-form locator: the samples sit at x_k = |xmin| sinh(u_k)/20, u_k uniform

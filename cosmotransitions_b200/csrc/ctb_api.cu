@@ -33,6 +33,94 @@ __global__ void __launch_bounds__(256) jspline_kernel(JTab g, const double *__re
     for (; i < n; i += stride) out[i] = jtab_eval<DER>(t, theta[i]);
 }
 
+// ---- Jb / Jf series variants (finiteT.py:207-296) --------------------------------------------------------
+// K_0(z), K_1(z), z > 0, from K_nu(z) = int_0^inf exp(-z cosh t) cosh(nu t) dt with the trapezoidal rule:
+// the integrand is analytic in the strip |Im t| < pi/2, so step h = 1/4 gives ~exp(-pi^2/h) = 7e-18.
+CTB_DEV void bessel_k01(double z, double &k0, double &k1)
+{
+    const double h = 0.25, eh = 1.2840254166877414; // exp(1/4)
+    double f0 = exp(-z);
+    double s0 = 0.5 * f0, s1 = 0.5 * f0;
+    double E = 1.0;
+    for (int k = 1; k < 4096; k++) {
+        E *= eh;
+        const double ch = 0.5 * (E + 1.0 / E);
+        const double f = exp(-z * ch);
+        const double g = f * ch;
+        s0 += f;
+        s1 += g;
+        if (g <= 1e-18 * s1) break;
+    }
+    k0 = h * s0;
+    k1 = h * s1;
+}
+
+// nan_to_num for a product that is 0 * inf at x = 0 (finiteT.py:260,265,275)
+CTB_DEV double nan0(double y)
+{
+    if (isnan(y)) return 0.0;
+    if (isinf(y)) return y > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    return y;
+}
+
+// one term K(k, x) of Jb_high / Jf_high: x2K2, dx2K2, d2x2K2, d3x2K2 (finiteT.py:249-275)
+CTB_DEV double high_term(int deriv, double k, double x)
+{
+    double k0 = 0.0, k1 = 0.0;
+    const double ax = fabs(x);
+    if (deriv == 0) {
+        if (x == 0) return -2.0 / (k * k * k * k);
+        if (x < 0) return nan(""); // special.kn(2, negative) is NaN
+        bessel_k01(k * x, k0, k1);
+        const double k2 = k0 + 2.0 * k1 / (k * x);
+        return -x * x * k2 / (k * k);
+    }
+    if (ax > 0) bessel_k01(k * ax, k0, k1);
+    else { k0 = INFINITY; k1 = INFINITY; }
+    if (deriv == 1) return nan0(x * ax * k1 / k);
+    if (deriv == 2) return (ax == 0) ? 1.0 / (k * k) : nan0(ax * (k1 / k - ax * k0));
+    return nan0(x * (ax * k * k1 - 3 * k0));
+}
+
+struct LowCoef { double c[56]; };
+
+template <int WHICH, int APPROX>
+__global__ void __launch_bounds__(256) jseries_kernel(int deriv, int nterms, LowCoef lc, const double *__restrict__ xin,
+                                                      double *__restrict__ out, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = xin[i];
+        double y;
+        if (APPROX == CTB_APPROX_HIGH) { // finiteT.py:278-296
+            y = 0.0;
+            double sign = 1.0;
+            for (int k = 1; k <= nterms; k++) {
+                y += sign * high_term(deriv, (double)k, x);
+                if (WHICH == 1) sign = -sign;
+            }
+        } else { // finiteT.py:225-244
+            const double x2 = x * x;
+            double lg = log(x2);
+            lg = isnan(lg) ? 0.0 : (isinf(lg) ? (lg > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308) : lg);
+            const double *g;
+            if (WHICH == 0) {
+                y = lc.c[0] + x * x * (lc.c[1] + x * (lc.c[2] + lc.c[3] * x * (lg - lc.c[4])));
+                g = lc.c + 5;
+            } else {
+                y = lc.c[0] + x * x * (lc.c[1] + lc.c[2] * x * x * (lg - lc.c[3]));
+                g = lc.c + 4;
+            }
+            double p = x2 * x2 * x2; // x^(2i+4), i = 1
+            for (int k = 1; k <= nterms; k++) {
+                y += g[k - 1] * p;
+                p *= x2;
+            }
+        }
+        out[i] = y;
+    }
+}
+
 struct Model8 { double l1, l2, mu2, Y1, Y2, nb, rs, v2; };
 
 CTB_DEV double model1_thermal(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
@@ -322,6 +410,28 @@ CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta,
     case 3: jspline_kernel<3><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
     default: return CTB_ERR_UNSUPPORTED;
     }
+    return (int)cudaGetLastError();
+}
+
+CTB_API int ctb_jseries(int which, int approx, int deriv, int nterms, const double *lowcoef, const double *d_x,
+                        double *d_out, int64_t n, void *stream)
+{
+    if (n < 0 || (which != 0 && which != 1) || nterms < 0) return CTB_ERR_BAD_ARG;
+    if (approx == CTB_APPROX_HIGH && (deriv < 0 || deriv > 3)) return CTB_ERR_UNSUPPORTED;
+    if (approx == CTB_APPROX_LOW && (deriv != 0 || nterms > 50 || !lowcoef)) return CTB_ERR_UNSUPPORTED;
+    if (approx != CTB_APPROX_HIGH && approx != CTB_APPROX_LOW) return CTB_ERR_UNSUPPORTED;
+    if (n == 0) return CTB_OK;
+    if (!d_x || !d_out) return CTB_ERR_BAD_ARG;
+    LowCoef lc;
+    for (int i = 0; i < 56; i++) lc.c[i] = 0.0;
+    if (approx == CTB_APPROX_LOW)
+        for (int i = 0; i < (which == 0 ? 55 : 54); i++) lc.c[i] = lowcoef[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    int g = grid_for(n, 256);
+    if (which == 0 && approx == CTB_APPROX_HIGH) jseries_kernel<0, CTB_APPROX_HIGH><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
+    else if (which == 1 && approx == CTB_APPROX_HIGH) jseries_kernel<1, CTB_APPROX_HIGH><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
+    else if (which == 0) jseries_kernel<0, CTB_APPROX_LOW><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
+    else jseries_kernel<1, CTB_APPROX_LOW><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
     return (int)cudaGetLastError();
 }
 

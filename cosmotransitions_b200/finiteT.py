@@ -42,15 +42,78 @@ def Jf_spline(X, n=0):
     return _eval("f", X, n)
 
 
-def Jb(x, approx='spline', deriv=0, n=8):
-    """Front end mirroring finiteT.Jb (finiteT.py:302-337) for approx='spline' (the variant
-    generic_potential uses, generic_potential.py:20-21)."""
-    if approx == 'spline':
-        return Jb_spline(x, deriv)
-    raise NotImplementedError("approx=%r: only the spline branch runs on the device (SURVEY.md s.8f row 4)" % approx)
+def _series(which, approx, x, deriv, n):
+    import ctypes as C
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    is_tensor = isinstance(x, torch.Tensor)
+    if is_tensor and x.is_cuda:
+        dev, d_x = x.device, x.to(torch.float64).contiguous()
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        host = x.detach().cpu().numpy() if is_tensor else np.asarray(x, dtype=np.float64)
+        d_x = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float64)).to(dev)
+    out = torch.empty_like(d_x)
+    h = _tables.host_tables()
+    coef = h.low_b if which == 0 else h.low_f
+    with torch.cuda.device(dev):
+        _lib.check(lib.ctb_jseries(which, approx, int(deriv), int(n), coef.ctypes.data_as(C.POINTER(C.c_double)),
+                                   d_x.data_ptr(), out.data_ptr(), d_x.numel(),
+                                   torch.cuda.current_stream(dev).cuda_stream), "ctb_jseries")
+    if is_tensor:
+        return out if x.is_cuda else out.cpu()
+    res = out.cpu().numpy()
+    return float(res) if res.ndim == 0 else res
 
 
-def Jf(x, approx='spline', deriv=0, n=8):
-    if approx == 'spline':
-        return Jf_spline(x, deriv)
-    raise NotImplementedError("approx=%r: only the spline branch runs on the device (SURVEY.md s.8f row 4)" % approx)
+def Jb_high(x, deriv=0, n=8):
+    """Jb calculated using the high-x (low-T) expansion; x = m/T (finiteT.py:278-285)."""
+    return _series(0, 0, x, deriv, n)
+
+
+def Jf_high(x, deriv=0, n=8):
+    """Jf calculated using the high-x (low-T) expansion; x = m/T (finiteT.py:288-296)."""
+    return _series(1, 0, x, deriv, n)
+
+
+def Jb_low(x, n=20):
+    """Jb calculated using the low-x (high-T) expansion; x = m/T (finiteT.py:225-233)."""
+    return _series(0, 1, x, 0, n)
+
+
+def Jf_low(x, n=20):
+    """Jf calculated using the low-x (high-T) expansion; x = m/T (finiteT.py:236-244)."""
+    return _series(1, 1, x, 0, n)
+
+
+def _front(which, x, approx, deriv, n):
+    # same dispatch and the same ValueErrors as finiteT.Jb / Jf (finiteT.py:302-375)
+    if approx == 'exact':
+        raise NotImplementedError("approx='exact' is the adaptive-quadrature definition used offline to build the "
+                                  "spline tables (finiteT.py:40-147); it is not a device path")
+    elif approx == 'spline':
+        return _eval("bf"[which], x, deriv)
+    elif approx == 'low':
+        if n > 100:
+            raise ValueError("Must have n <= 100")
+        if deriv == 0:
+            if n > 50:
+                raise ValueError("the coefficient table holds 50 terms (finiteT.py:207-222)")
+            return _series(which, 1, x, 0, n)
+        raise ValueError("For approx=='low', deriv must be 0.")
+    elif approx == 'high':
+        if deriv > 3:
+            raise ValueError("For approx=='high', deriv must be 3 or less.")
+        return _series(which, 0, x, deriv, n)
+    raise ValueError("Unexpected value for 'approx'.")
+
+
+def Jb(x, approx='high', deriv=0, n=8):
+    """A shorthand for calling one of the Jb functions above; same signature and defaults as
+    finiteT.Jb (finiteT.py:302-337).  For approx='spline' the argument is theta = (m/T)^2."""
+    return _front(0, x, approx, deriv, n)
+
+
+def Jf(x, approx='high', deriv=0, n=8):
+    """Same for Jf (finiteT.py:340-375)."""
+    return _front(1, x, approx, deriv, n)

@@ -159,6 +159,17 @@ CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jt
  * deriv in 0..3. */
 CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta, double *d_out, int64_t n, void *stream);
 
+/* finiteT.Jb / Jf with approx = 'high' or 'low' (finiteT.py:225-296, front ends :302-375).  NOTE the
+ * argument is x = m/T here (not theta = x^2 as for the spline variant).
+ *   which: 0 = Jb, 1 = Jf;  approx: CTB_APPROX_HIGH (deriv 0..3, sum of nterms Bessel-K terms,
+ *   finiteT.py:249-296) or CTB_APPROX_LOW (deriv 0 only, polynomial + log + nterms <= 50 power terms,
+ *   finiteT.py:207-244).  lowcoef (HOST pointer, used for 'low' only): Jb: a, b, c, d, logab, g[50];
+ *   Jf: a, b, d, logaf, g[50] -- the reference's lowCoef_b / lowCoef_f. */
+#define CTB_APPROX_HIGH 0
+#define CTB_APPROX_LOW 1
+CTB_API int ctb_jseries(int which, int approx, int deriv, int nterms, const double *lowcoef, const double *d_x,
+                        double *d_out, int64_t n, void *stream);
+
 /* generic_potential.Vtot (generic_potential.py:312-337) for model1 (examples/testModel1.py:62-116):
  * pointwise, d_X [n,2], d_T [n] -> d_out [n].  model[8] = l1,l2,mu2,Y1,Y2,n_boson,renormScaleSq,v2 (host). */
 CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const double *d_X, const double *d_T,

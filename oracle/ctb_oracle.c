@@ -1155,6 +1155,65 @@ CTBO_API int ctbo_rkqs_poly4(const double *coef5, int alpha, const double y[2], 
     return e;
 }
 
+/* ---- finiteT.Jb / Jf, approx = 'high' and 'low' (finiteT.py:207-296) -------------------------------
+ * scipy.special.kn(0|1|2, z) restated through K_nu(z) = int_0^inf exp(-z cosh t) cosh(nu t) dt, trapezoidal
+ * rule with step 0.2 (error ~ exp(-pi^2/0.2)), K_2 = K_0 + 2 K_1 / z. */
+static void bessel_k01(double z, double *k0, double *k1)
+{
+    const double h = 0.2;
+    double s0 = 0.5 * exp(-z), s1 = s0;
+    for (int k = 1; k < 8192; k++) {
+        double ch = cosh(k * h);
+        double f = exp(-z * ch);
+        s0 += f; s1 += f * ch;
+        if (f * ch <= 1e-19 * s1) break;
+    }
+    *k0 = h * s0; *k1 = h * s1;
+}
+static double nan_to_num(double y)
+{
+    if (isnan(y)) return 0.0;
+    if (isinf(y)) return y > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    return y;
+}
+static double high_term(int deriv, double k, double x)
+{
+    double k0 = INFINITY, k1 = INFINITY, ax = fabs(x);
+    if (deriv == 0) { /* x2K2, finiteT.py:249-255 */
+        if (x == 0) return -2.0 / (k * k * k * k);
+        if (x < 0) return NAN;
+        bessel_k01(k * x, &k0, &k1);
+        return -x * x * (k0 + 2.0 * k1 / (k * x)) / (k * k);
+    }
+    if (ax > 0) bessel_k01(k * ax, &k0, &k1);
+    if (deriv == 1) return nan_to_num(x * ax * k1 / k);                             /* :258-260 */
+    if (deriv == 2) return (ax == 0) ? 1.0 / (k * k) : nan_to_num(ax * (k1 / k - ax * k0)); /* :263-270 */
+    return nan_to_num(x * (ax * k * k1 - 3 * k0));                                  /* :273-275 */
+}
+CTBO_API void ctbo_jseries(int which, int approx_low, int deriv, int nterms, const double *lowcoef, const double *x,
+                           double *out, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) {
+        double y = 0.0, xi = x[i];
+        if (!approx_low) { /* Jb_high / Jf_high, finiteT.py:278-296 */
+            double sg = 1.0;
+            for (int k = 1; k <= nterms; k++) { y += sg * high_term(deriv, (double)k, xi); if (which == 1) sg = -sg; }
+        } else {           /* Jb_low / Jf_low, finiteT.py:225-244 */
+            double lg = nan_to_num(log(xi * xi));
+            const double *g;
+            if (which == 0) {
+                y = lowcoef[0] + xi * xi * (lowcoef[1] + xi * (lowcoef[2] + lowcoef[3] * xi * (lg - lowcoef[4])));
+                g = lowcoef + 5;
+            } else {
+                y = lowcoef[0] + xi * xi * (lowcoef[1] + lowcoef[2] * xi * xi * (lg - lowcoef[3]));
+                g = lowcoef + 4;
+            }
+            for (int k = 1; k <= nterms; k++) y += g[k - 1] * pow(xi, 2 * k + 4);
+        }
+        out[i] = y;
+    }
+}
+
 /* V_i(phi_i), one field value per parameter row */
 CTBO_API void ctbo_potential_rows(const ctbo_config *cfg, const double *params, const double *phi, double *out,
                                   int64_t n)

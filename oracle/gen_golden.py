@@ -10,6 +10,7 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
   cosmotransitions_b200/data/finiteT_tables.npz  the 2x1000 exact-integral samples (xb,yb,xf,yf)
                                                  and scipy's splrep knots/coefficients (tb,cb,tf,cf)
   tests/golden/jspline.npz      Jb_spline / Jf_spline (finiteT.py:167-204), deriv 0..3
+  tests/golden/jseries.npz      Jb / Jf with approx='high' (deriv 0..3) and 'low' (finiteT.py:225-375)
   tests/golden/quartic.json     SingleFieldInstanton findProfile/findAction on quartic potentials
   tests/golden/profiles.npz     full R/Phi/dPhi profiles for three cases
   tests/golden/units.npz        exactSolution / rkqs unit vectors
@@ -122,8 +123,12 @@ def gen_tables():
     tb, cb, kb = fT._tckb
     tf, cf, kf = fT._tckf
     assert kb == 3 and kf == 3
+    # low-x series coefficients (finiteT.py:207-222): [a, b, c, d, logab, g_1..g_50] and [a, b, d, logaf, g_1..g_50]
+    ab, bb, cbb, db, logab, _, gb = fT.lowCoef_b
+    af, bf, df, logaf, _, gf = fT.lowCoef_f
     np.savez(os.path.join(DATA, "finiteT_tables.npz"), xb=fT._xb, yb=fT._yb, xf=fT._xf, yf=fT._yf, tb=tb, cb=cb,
-             tf=tf, cf=cf, xbmin=fT._xbmin, xbmax=fT._xbmax, xfmin=fT._xfmin, xfmax=fT._xfmax)
+             tf=tf, cf=cf, xbmin=fT._xbmin, xbmax=fT._xbmax, xfmin=fT._xfmin, xfmax=fT._xfmax,
+             low_b=np.concatenate([[ab, bb, cbb, db, logab], gb]), low_f=np.concatenate([[af, bf, df, logaf], gf]))
 
 
 def gen_jspline():
@@ -140,6 +145,26 @@ def gen_jspline():
         out["Jb%d" % n] = fT.Jb_spline(th, n)
         out["Jf%d" % n] = fT.Jf_spline(th, n)
     np.savez(os.path.join(GOLD, "jspline.npz"), **out)
+
+
+def gen_jseries():
+    """finiteT.Jb / Jf with approx='high' (deriv 0..3, n=8 and n=3) and approx='low' (n=20, n=5)  (finiteT.py:225-375)"""
+    rng = np.random.default_rng(17)
+    x = np.concatenate([[0.0, 1e-8, 1e-3, 0.05, 0.5, 1.0, 2.0, 3.5, 7.0, 15.0, 40.0, 90.0, 200.0, 800.0],
+                        10 ** rng.uniform(-4, 2, 200), rng.uniform(0, 12, 200)])
+    out = {"x": x, "xneg": -x[:40]}
+    with np.errstate(all="ignore"):
+        for nt in (8, 3):
+            for d in range(4):
+                out["Jb_high_n%d_d%d" % (nt, d)] = fT.Jb(x, approx="high", deriv=d, n=nt)
+                out["Jf_high_n%d_d%d" % (nt, d)] = fT.Jf(x, approx="high", deriv=d, n=nt)
+        for d in range(4):
+            out["Jb_high_neg_d%d" % d] = fT.Jb(-x[:40], approx="high", deriv=d, n=8)
+            out["Jf_high_neg_d%d" % d] = fT.Jf(-x[:40], approx="high", deriv=d, n=8)
+        for nt in (20, 5, 50):
+            out["Jb_low_n%d" % nt] = fT.Jb(x, approx="low", n=nt)
+            out["Jf_low_n%d" % nt] = fT.Jf(x, approx="low", n=nt)
+    np.savez(os.path.join(GOLD, "jseries.npz"), **out)
 
 
 # ---- 2. quartic bounces --------------------------------------------------------------------
@@ -376,7 +401,7 @@ def gen_model1f():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["tables", "jspline", "quartic", "profiles", "units", "model1", "model1f"]
+    which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

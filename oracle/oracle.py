@@ -165,6 +165,16 @@ def potential(cfg, params, phi):
     return out
 
 
+def jseries(which, approx, deriv, nterms, lowcoef, x):
+    """which: 0 Jb / 1 Jf; approx: 'high' | 'low' (finiteT.py:225-296)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lc = np.ascontiguousarray(lowcoef, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().ctbo_jseries(C.c_int(which), C.c_int(1 if approx == "low" else 0), C.c_int(deriv), C.c_int(nterms), _dp(lc),
+                       _dp(x), _dp(out), C.c_int64(x.size))
+    return out
+
+
 def potential_rows(cfg, params, phi):
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, cfg.nparam)
     phi = np.ascontiguousarray(phi, dtype=np.float64)

@@ -193,8 +193,39 @@ def test_jspline_golden(ctb, gold_dir):
             tol = J_ATOL if der == 0 else 1e-9 * max(1.0, np.max(np.abs(ref)))
             np.testing.assert_allclose(got, ref, rtol=0, atol=tol)
     assert np.array_equal(finiteT.Jb(th, approx="spline"), finiteT.Jb_spline(th))
+    assert np.array_equal(finiteT.Jf(th, approx="spline", deriv=2), finiteT.Jf_spline(th, 2))
     x = th[:1500].reshape(3, 500)
     assert finiteT.Jf_spline(x).shape == x.shape
+
+
+def test_jseries_golden(ctb, gold_dir):
+    """finiteT.Jb / Jf with approx='high' and 'low' (finiteT.py:225-375) against the reference's values."""
+    from cosmotransitions_b200 import finiteT
+    g = np.load(os.path.join(gold_dir, "jseries.npz"))
+    x, xneg = g["x"], g["xneg"]
+    for nm, fn in (("Jb", finiteT.Jb), ("Jf", finiteT.Jf)):
+        for nt in (8, 3):
+            for d in range(4):
+                ref = g["%s_high_n%d_d%d" % (nm, nt, d)]
+                got = fn(x, approx="high", deriv=d, n=nt)
+                np.testing.assert_allclose(got, ref, rtol=1e-11, atol=J_ATOL)
+        for d in range(4):
+            ref = g["%s_high_neg_d%d" % (nm, d)]
+            got = fn(xneg, approx="high", deriv=d, n=8)
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            ok = ~np.isnan(ref)
+            np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-11, atol=J_ATOL)
+        for nt in (20, 5, 50):
+            ref = g["%s_low_n%d" % (nm, nt)]
+            got = fn(x, approx="low", n=nt)
+            np.testing.assert_allclose(got, ref, rtol=1e-11, atol=J_ATOL)
+    assert np.array_equal(finiteT.Jb_high(x), finiteT.Jb(x))          # default approx is 'high', as in the reference
+    with pytest.raises(ValueError):
+        finiteT.Jb(x, approx="low", deriv=1)
+    with pytest.raises(ValueError):
+        finiteT.Jf(x, approx="high", deriv=4)
+    with pytest.raises(ValueError):
+        finiteT.Jb(x, approx="bogus")
 
 
 def test_jspline_large_vs_oracle(ctb, oracle, tables):

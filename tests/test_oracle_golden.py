@@ -122,6 +122,26 @@ def test_jspline(oracle, tables, gold_dir):
         np.testing.assert_allclose(jf, g["Jf%d" % der], rtol=0, atol=tol)
 
 
+def test_jseries(oracle, gold_dir):
+    import numpy as np
+    g = np.load(os.path.join(gold_dir, "jseries.npz"))
+    d = np.load(os.path.join(os.path.dirname(gold_dir), "..", "cosmotransitions_b200", "data", "finiteT_tables.npz"))
+    x, xneg = g["x"], g["xneg"]
+    for which, nm, lc in ((0, "Jb", d["low_b"]), (1, "Jf", d["low_f"])):
+        for nt in (8, 3):
+            for der in range(4):
+                np.testing.assert_allclose(oracle.jseries(which, "high", der, nt, lc, x),
+                                           g["%s_high_n%d_d%d" % (nm, nt, der)], rtol=1e-11, atol=1e-10)
+        for der in range(4):
+            ref = g["%s_high_neg_d%d" % (nm, der)]
+            got = oracle.jseries(which, "high", der, 8, lc, xneg)
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            np.testing.assert_allclose(got[~np.isnan(ref)], ref[~np.isnan(ref)], rtol=1e-11, atol=1e-10)
+        for nt in (20, 5, 50):
+            np.testing.assert_allclose(oracle.jseries(which, "low", 0, nt, lc, x), g["%s_low_n%d" % (nm, nt)],
+                                       rtol=1e-11, atol=1e-10)
+
+
 def _model1_params(g, T, x0, nhat):
     return np.array([g["p_l1"], g["p_l2"], g["p_mu2"], g["p_Y1"], g["p_Y2"], g["p_n"], g["p_renorm"], g["p_v2"], T,
                      x0[0], x0[1], nhat[0], nhat[1]], dtype=float)
