@@ -11,7 +11,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 3
+ABI_VERSION = 4
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F = 0, 1, 2
 NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6}
 (ST_CONVERGED, ST_XTOL, ST_STABLE, ST_NO_BARRIER, ST_RMAX, ST_DRMIN, ST_STEP_UNDERFLOW, ST_NONFINITE,
@@ -31,7 +32,8 @@ class JTable(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("xtol", C.c_double), ("phitol", C.c_double), ("thinCutoff", C.c_double), ("rmin", C.c_double),
                 ("rmax", C.c_double), ("phi_eps", C.c_double), ("xguess", C.c_double), ("npoints", C.c_int32),
-                ("max_interior_pts", C.c_int32), ("alpha", C.c_int32), ("block_threads", C.c_int32)]
+                ("max_interior_pts", C.c_int32), ("alpha", C.c_int32), ("block_threads", C.c_int32),
+                ("kernel", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BounceIn(C.Structure):

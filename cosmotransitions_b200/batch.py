@@ -13,7 +13,10 @@ _F64_OUT = ["S", "phi0", "r0", "rf", "x", "phi_bar", "rscale"]
 _I32_OUT = ["status", "n_shots", "n_rkck", "n_points"]
 
 
-def make_opts(alpha=2, phi_eps=1e-3, block_threads=0, **knobs):
+_KERNELS = {"auto": _lib.KERNEL_AUTO, "thread": _lib.KERNEL_THREAD, "warp": _lib.KERNEL_WARP}
+
+
+def make_opts(alpha=2, phi_eps=1e-3, block_threads=0, kernel="auto", **knobs):
     kw = dict(FINDPROFILE_DEFAULTS)
     for k, v in knobs.items():
         if k not in kw:
@@ -29,6 +32,7 @@ def make_opts(alpha=2, phi_eps=1e-3, block_threads=0, **knobs):
     o.max_interior_pts = -1 if kw["max_interior_pts"] is None else int(kw["max_interior_pts"])
     o.alpha = int(alpha)
     o.block_threads = int(block_threads)
+    o.kernel = _KERNELS[kernel]
     return o
 
 
@@ -133,7 +137,7 @@ def alloc_out(torch, n, device):
 
 def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, phi_eps=1e-3, device=None,
                       return_profiles=False, block_threads=0, schedule="auto", phi_bar=None, rscale=None,
-                      **findProfile_knobs):
+                      kernel="auto", **findProfile_knobs):
     """Solve N independent bounces.
 
     potential_kind : one of _lib.POT_* (or a DevicePotential subclass / instance, whose kind is used)
@@ -142,6 +146,8 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
     alpha, phi_eps : as SingleFieldInstanton.__init__ (tunneling1D.py:128-130)
     phi_bar, rscale : optional [N] overrides, as in __init__ (NaN entries = compute)
     schedule       : "auto" | "sorted" | "natural" (see launch_bounce); does not change results
+    kernel         : "auto" | "thread" | "warp" -- one thread or one warp per instance (include/ctbounce.h);
+                     same shooting sequence, S equal up to the summation order of the quadrature
     findProfile_knobs : xguess, xtol, phitol, thinCutoff, npoints, rmin, rmax, max_interior_pts
                         with the reference's defaults (tunneling1D.py:615-617)
 
@@ -154,7 +160,7 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
     kind = getattr(potential_kind, "kind", potential_kind)
     if kind not in _lib.NPARAM:
         raise ValueError("unknown potential kind %r" % (potential_kind,))
-    opts = make_opts(alpha=alpha, phi_eps=phi_eps, block_threads=block_threads, **findProfile_knobs)
+    opts = make_opts(alpha=alpha, phi_eps=phi_eps, block_threads=block_threads, kernel=kernel, **findProfile_knobs)
     on_host = not (isinstance(params, torch.Tensor) and params.is_cuda)
     if device is None:
         device = params.device if not on_host else torch.device("cuda", torch.cuda.current_device())

@@ -359,14 +359,21 @@ CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_op
     a.knobs.npoints = o->npoints; a.knobs.max_interior_pts = o->max_interior_pts;
     cudaStream_t st = (cudaStream_t)stream;
     int block = o->block_threads ? o->block_threads : 128;
+    const int stage_cap = o->npoints + (o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts);
+    bool warp = o->kernel == CTB_KERNEL_WARP;
+    if (o->kernel == CTB_KERNEL_AUTO) warp = a.n < 4096 && stage_cap <= 2048;
+    if (o->kernel < 0 || o->kernel > 2 || (warp && stage_cap > 2048)) return CTB_ERR_UNSUPPORTED;
+    if (pot_kind != CTB_POT_POLY4 && !jtab_ok(jb)) return CTB_ERR_BAD_ARG;
     switch (pot_kind) {
-    case CTB_POT_POLY4: return ctb::launch_bounce_poly4(a, o->alpha, block, st);
+    case CTB_POT_POLY4:
+        return warp ? ctb::launch_bounce_warp_poly4(a, o->alpha, stage_cap, st)
+                    : ctb::launch_bounce_poly4(a, o->alpha, block, st);
     case CTB_POT_MODEL1_LINE:
-        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        return ctb::launch_bounce_model1_line(a, o->alpha, block, st);
+        return warp ? ctb::launch_bounce_warp_model1_line(a, o->alpha, stage_cap, st)
+                    : ctb::launch_bounce_model1_line(a, o->alpha, block, st);
     case CTB_POT_MODEL1F:
-        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        return ctb::launch_bounce_model1f(a, o->alpha, block, st);
+        return warp ? ctb::launch_bounce_warp_model1f(a, o->alpha, stage_cap, st)
+                    : ctb::launch_bounce_model1f(a, o->alpha, block, st);
     }
     return CTB_ERR_UNSUPPORTED;
 }

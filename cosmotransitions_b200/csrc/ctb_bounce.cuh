@@ -70,6 +70,10 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(c
     if (a.out.d_n_points) a.out.d_n_points[i] = r.n_points;
 }
 
+} // namespace ctb
+#include "ctb_warp.cuh"
+namespace ctb {
+
 // __init__ only: phi_bar, rscale, status (0 / STABLE / NO_BARRIER) and the work predictor.
 template <class Pot>
 __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
@@ -117,7 +121,33 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     return (int)cudaGetLastError();
 }
 
+// warp-per-instance variant (ctb_warp.cuh): 4 warps per block, stage_cap staged points per warp
+template <class Pot>
+int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((a.n + 3) / 4);
+    const size_t sm = (Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double))
+                      + (size_t)4 * 2 * stage_cap * sizeof(double);
+    if (sm > 200 * 1024) return CTB_ERR_UNSUPPORTED;
+    const bool prof = a.out.d_prof_R != nullptr;
+#define CTB_LAUNCH_WARP(AL, PR)                                                                                  \
+    do {                                                                                                         \
+        cudaFuncSetAttribute(bounce_warp_kernel<Pot, AL, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        bounce_warp_kernel<Pot, AL, PR><<<grid, 128, sm, st>>>(a, stage_cap);                                   \
+    } while (0)
+    if (alpha == 2 && !prof) CTB_LAUNCH_WARP(2, false);
+    else if (alpha == 3 && !prof) CTB_LAUNCH_WARP(3, false);
+    else if (alpha == 2) CTB_LAUNCH_WARP(2, true);
+    else if (alpha == 3) CTB_LAUNCH_WARP(3, true);
+    else return CTB_ERR_UNSUPPORTED;
+#undef CTB_LAUNCH_WARP
+    return (int)cudaGetLastError();
+}
+
 int launch_bounce_poly4(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+int launch_bounce_warp_poly4(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);
+int launch_bounce_warp_model1_line(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);
+int launch_bounce_warp_model1f(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);
 int launch_bounce_model1_line(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_bounce_model1f(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_setup_poly4(const BounceArgs &a, cudaStream_t st);

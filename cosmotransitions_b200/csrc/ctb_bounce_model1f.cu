@@ -7,4 +7,8 @@ int launch_bounce_model1f(const BounceArgs &a, int alpha, int block, cudaStream_
     return launch_bounce_any<PotModel1F>(a, alpha, block, st);
 }
 int launch_setup_model1f(const BounceArgs &a, cudaStream_t st) { return launch_setup_any<PotModel1F>(a, st); }
+int launch_bounce_warp_model1f(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st)
+{
+    return launch_bounce_warp_any<PotModel1F>(a, alpha, stage_cap, st);
+}
 } // namespace ctb

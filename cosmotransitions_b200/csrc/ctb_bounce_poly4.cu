@@ -7,4 +7,8 @@ int launch_bounce_poly4(const BounceArgs &a, int alpha, int block, cudaStream_t 
     return launch_bounce_any<PotPoly4>(a, alpha, block, st);
 }
 int launch_setup_poly4(const BounceArgs &a, cudaStream_t st) { return launch_setup_any<PotPoly4>(a, st); }
+int launch_bounce_warp_poly4(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st)
+{
+    return launch_bounce_warp_any<PotPoly4>(a, alpha, stage_cap, st);
+}
 } // namespace ctb

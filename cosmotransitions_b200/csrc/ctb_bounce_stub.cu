@@ -6,4 +6,6 @@ int launch_bounce_model1_line(const BounceArgs &, int, int, cudaStream_t) { retu
 int launch_bounce_model1f(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
 int launch_setup_model1_line(const BounceArgs &, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
 int launch_setup_model1f(const BounceArgs &, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_bounce_warp_model1_line(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_bounce_warp_model1f(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
 } // namespace ctb

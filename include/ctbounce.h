@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 3
+#define CTB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -99,8 +99,21 @@ typedef struct ctb_opts {
     int32_t npoints;          /* 500; 2 <= npoints <= 4096 */
     int32_t max_interior_pts; /* -1 = None (npoints/2) */
     int32_t alpha;            /* 2 (O(3), finite T) or 3 (O(4), zero T) */
-    int32_t block_threads;    /* 0 = library default */
+    int32_t block_threads;    /* 0 = library default (thread-per-instance kernel only) */
+    int32_t kernel;           /* CTB_KERNEL_AUTO / _THREAD / _WARP, see below */
+    int32_t reserved;
 } ctb_opts;
+
+/* Two kernels implement the same solve (identical shooting sequence and results up to the summation
+ * order of the quadrature):
+ *   THREAD: one GPU thread per instance -- throughput; the choice for >= ~4096 instances.
+ *   WARP:   one warp per instance -- latency; the 31 nodes of the next five levels of the over/undershoot
+ *           decision tree are integrated speculatively, one per lane, and resolved by warp shuffles; the
+ *           save pass is lane-parallel with the profile staged in shared memory.
+ *   AUTO:   WARP below 4096 instances (when npoints + interior points <= 2048), THREAD otherwise. */
+#define CTB_KERNEL_AUTO 0
+#define CTB_KERNEL_THREAD 1
+#define CTB_KERNEL_WARP 2
 
 /* ---- inputs of the batched solve: one row / entry per instance ------------------------------ */
 typedef struct ctb_bounce_in {

@@ -32,7 +32,8 @@ def _np(d):
 ERR2STATUS = {"PotentialError:stable, not metastable": 2, "PotentialError:no barrier": 3}
 
 
-def test_quartic_golden(ctb, gold_dir):
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_quartic_golden(ctb, gold_dir, kernel):
     from cosmotransitions_b200 import _lib, batch
     cases = json.load(open(os.path.join(gold_dir, "quartic.json")))
     worst = 0.0
@@ -40,7 +41,7 @@ def test_quartic_golden(ctb, gold_dir):
         opts = dict(case.get("opts", {}))
         phi_eps = opts.pop("phi_eps", 1e-3)
         r = _np(batch.find_bounce_batch(_lib.POT_POLY4, np.array([case["coef"]]), [case["phi_abs"]], [case["phi_meta"]],
-                                        alpha=case["alpha"], phi_eps=phi_eps, return_profiles=True,
+                                        alpha=case["alpha"], phi_eps=phi_eps, return_profiles=True, kernel=kernel,
                                         **{k: [v] for k, v in case.get("init", {}).items()}, **opts))
         st = int(r["status"][0])
         if case["error"] is not None:
@@ -131,6 +132,36 @@ def test_quartic_sweep_vs_oracle(ctb, oracle, alpha):
         assert np.array_equal(gs[k], g[k][perm], equal_nan=True), k
     for k in ("status", "n_shots", "n_rkck", "n_points"):
         assert np.array_equal(gs[k], g[k][perm]), k
+
+
+@pytest.mark.parametrize("alpha", [2, 3])
+def test_warp_and_thread_kernels_agree(ctb, alpha):
+    """The warp-per-instance kernel resolves the same shooting sequence speculatively: identical shot and
+    step counts, identical phi0 / rf / x, S equal up to the summation order of the quadrature."""
+    from cosmotransitions_b200 import _lib, batch, potentials
+    N = 3000
+    c = 0.02 + 0.479 * np.random.default_rng(9).random(N)     # reaches into the brentq-failure zone
+    p = potentials.quartic_family_params(c)
+    p[5] = [0, 0, -0.1, -0.8 / 3, 0.25]
+    a = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, alpha=alpha, kernel="thread", return_profiles=True))
+    b = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, alpha=alpha, kernel="warp", return_profiles=True))
+    assert np.array_equal(a["status"], b["status"])
+    ok = a["status"] <= 1
+    assert ok.mean() > 0.9 and (~ok).sum() > 1
+    for k in ("n_shots", "n_rkck", "n_points"):
+        assert np.array_equal(a[k][ok], b[k][ok]), k
+    for k in ("phi0", "x", "phi_bar", "rscale"):
+        assert np.array_equal(a[k][ok], b[k][ok]), k
+    # the two kernels are separate compilations of the same source: FMA contraction may differ in the
+    # last ulp (e.g. rf = r + dr * t), nothing more
+    # (rf sits where phi' or phi - phi_meta crosses zero in the flat tail: ill-conditioned, see the golden test)
+    np.testing.assert_allclose(b["r0"][ok], a["r0"][ok], rtol=1e-12)
+    np.testing.assert_allclose(b["rf"][ok], a["rf"][ok], rtol=1e-7)
+    np.testing.assert_allclose(b["S"][ok], a["S"][ok], rtol=1e-10)
+    for k, tol in (("R", 1e-7), ("Phi", 1e-8), ("dPhi", 1e-8)):
+        m = np.isfinite(a[k][ok])
+        assert np.array_equal(m, np.isfinite(b[k][ok])), k
+        np.testing.assert_allclose(b[k][ok][m], a[k][ok][m], rtol=tol, atol=tol, err_msg=k)
 
 
 def test_schedules_agree(ctb):
@@ -271,12 +302,13 @@ def test_model1_line_bounces_golden(ctb, gold_dir):
         assert len(prof.R) == ref["npts"]
 
 
-def test_model1f_golden_and_oracle(ctb, oracle, tables, gold_dir):
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_model1f_golden_and_oracle(ctb, oracle, tables, gold_dir, kernel):
     from cosmotransitions_b200 import _lib, batch
     cases = json.load(open(os.path.join(gold_dir, "model1f.json")))
     params = np.array([[c["lam"], c["v2"], c["Y"], c["n"], c["v2"], c["T"]] for c in cases])
     pa = np.array([c["phi_abs"] for c in cases])
-    r = _np(batch.find_bounce_batch(_lib.POT_MODEL1F, params, pa, 0.0))
+    r = _np(batch.find_bounce_batch(_lib.POT_MODEL1F, params, pa, 0.0, kernel=kernel))
     S_ref = np.array([c["S"] for c in cases])
     assert (r["status"] <= 1).all()
     rel = np.abs(r["S"] - S_ref) / S_ref

@@ -27,7 +27,7 @@ def test_struct_layout_matches_header():
     import ctypes as C
     from cosmotransitions_b200 import _lib
     assert C.sizeof(_lib.JTable) == 64
-    assert C.sizeof(_lib.Opts) == 7 * 8 + 4 * 4
+    assert C.sizeof(_lib.Opts) == 7 * 8 + 6 * 4
     assert C.sizeof(_lib.BounceOut) == 15 * 8
     assert C.sizeof(_lib.BounceIn) == 7 * 8
 
