@@ -28,7 +28,7 @@ struct BounceArgs {
 // lanes follow similar trajectories; blocks are small so that the hardware block scheduler balances
 // the 4x spread in work per instance across the 148 SMs.
 template <class Pot, int ALPHA, bool PROFILE>
-__global__ void __launch_bounds__(CTB_MAX_BLOCK, CTB_MIN_BLOCKS) bounce_kernel(const BounceArgs a)
+__global__ void __launch_bounds__(CTB_MAX_BLOCK, Pot::min_blocks) bounce_kernel(const BounceArgs a)
 {
     // every lane of every warp runs the solver (it votes warp-wide); lanes past the end of the batch
     // carry a dummy instance that is never integrated

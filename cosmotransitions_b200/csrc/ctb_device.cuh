@@ -12,6 +12,9 @@
 namespace ctb {
 
 #define CTB_DEV __device__ __forceinline__
+#ifndef CTB_THERMAL_MIN_BLOCKS
+#define CTB_THERMAL_MIN_BLOCKS 4
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Jb / Jf spline tables (piecewise cubic, see ctbounce.h)                      FT:167-174,197-204
@@ -84,6 +87,7 @@ CTB_DEV double jtab_eval(const JTab &t, double theta)
 
 struct PotPoly4 {
     static constexpr bool analytic = true;
+    static constexpr int min_blocks = 3; // 128-thread blocks per SM the bounce kernel is compiled for (<= 168 regs)
     static constexpr int nparam = CTB_NPARAM_POLY4;
     double c0, c1, c2, c3, c4;
     CTB_DEV void load(const double *p, const JTab *, const JTab *)
@@ -119,48 +123,28 @@ CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, do
     f.m0 = A + B; f.m1 = A - B;
     double r = .25 * l1 * (phi1 * phi1 - v2) * (phi1 * phi1 - v2) + .25 * l2 * (phi2 * phi2 - v2) * (phi2 * phi2 - v2);
     r -= mu2 * phi1 * phi2;
+    const double inv_rs = 1.0 / rs;
     double y1 = 0.0;
-    y1 += 1.0 * f.m0 * f.m0 * (log(fabs(f.m0 / rs) + 1e-100) - 1.5);
-    y1 += 1.0 * f.m1 * f.m1 * (log(fabs(f.m1 / rs) + 1e-100) - 1.5);
-    y1 += nb * f.mb * f.mb * (log(fabs(f.mb / rs) + 1e-100) - 1.5);
-    f.V01 = r + y1 / (64 * CTB_PI * CTB_PI);
+    y1 += 1.0 * f.m0 * f.m0 * (log(fabs(f.m0 * inv_rs) + 1e-100) - 1.5);
+    y1 += 1.0 * f.m1 * f.m1 * (log(fabs(f.m1 * inv_rs) + 1e-100) - 1.5);
+    y1 += nb * f.mb * f.mb * (log(fabs(f.mb * inv_rs) + 1e-100) - 1.5);
+    f.V01 = r + y1 * (1.0 / (64 * CTB_PI * CTB_PI));
     return f;
 }
 
 // examples/testModel1.py:62-116 through GP:312-337, on the line X = x0 + phi*nhat
-CTB_DEV double vtot_model1(double l1, double l2, double mu2, double Y1, double Y2, double nb, double rs, double v2,
-                           const JTab &jb, double phi1, double phi2, double T)
-{
-    double a = l1 * (3 * phi1 * phi1 - v2);
-    double b = l2 * (3 * phi2 * phi2 - v2);
-    double A = .5 * (a + b);
-    double B = sqrt(.25 * (a - b) * (a - b) + mu2 * mu2);
-    double mb = Y1 * (phi1 * phi1 + phi2 * phi2) + Y2 * phi1 * phi2;
-    double m0 = A + B, m1 = A - B;
-    double r = .25 * l1 * (phi1 * phi1 - v2) * (phi1 * phi1 - v2) + .25 * l2 * (phi2 * phi2 - v2) * (phi2 * phi2 - v2);
-    r -= mu2 * phi1 * phi2;
-    double y1 = 0.0;
-    y1 += 1.0 * m0 * m0 * (log(fabs(m0 / rs) + 1e-100) - 1.5);
-    y1 += 1.0 * m1 * m1 * (log(fabs(m1 / rs) + 1e-100) - 1.5);
-    y1 += nb * mb * mb * (log(fabs(mb / rs) + 1e-100) - 1.5);
-    r += y1 / (64 * CTB_PI * CTB_PI);
-    double T2 = T * T + 1e-100, T4 = T * T * T * T;
-    double yt = 0.0;
-    yt += 1.0 * jtab_eval<0>(jb, m0 / T2);
-    yt += 1.0 * jtab_eval<0>(jb, m1 / T2);
-    yt += nb * jtab_eval<0>(jb, mb / T2);
-    r += yt * T4 / (2 * CTB_PI * CTB_PI);
-    return r;
-}
-
 struct PotModel1Line {
     static constexpr bool analytic = false;
+    static constexpr int min_blocks = CTB_THERMAL_MIN_BLOCKS;
     static constexpr int nparam = CTB_NPARAM_MODEL1_LINE;
-    double l1, l2, mu2, Y1, Y2, nb, rs, v2, T, x0, x1, n0, n1;
+    double l1, l2, mu2, Y1, Y2, nb, rs, v2, inv_T2, T4c, x0, x1, n0, n1;
     JTab jb;
     CTB_DEV void load(const double *p, const JTab *jb_, const JTab *)
     {
-        l1 = p[0]; l2 = p[1]; mu2 = p[2]; Y1 = p[3]; Y2 = p[4]; nb = p[5]; rs = p[6]; v2 = p[7]; T = p[8];
+        l1 = p[0]; l2 = p[1]; mu2 = p[2]; Y1 = p[3]; Y2 = p[4]; nb = p[5]; rs = p[6]; v2 = p[7];
+        const double T = p[8];
+        inv_T2 = 1.0 / (T * T + 1e-100);
+        T4c = (T * T * T * T) / (2 * CTB_PI * CTB_PI);
         x0 = p[9]; x1 = p[10]; n0 = p[11]; n1 = p[12];
         jb = *jb_;
     }
@@ -168,35 +152,41 @@ struct PotModel1Line {
     // one copy keeps the kernel inside the instruction cache
     __device__ __noinline__ double V(double phi) const
     {
-        return vtot_model1(l1, l2, mu2, Y1, Y2, nb, rs, v2, jb, x0 + phi * n0, x1 + phi * n1, T);
+        const Model1Field f = model1_field(l1, l2, mu2, Y1, Y2, nb, rs, v2, x0 + phi * n0, x1 + phi * n1);
+        const double yt = jtab_eval<0>(jb, f.m0 * inv_T2) + jtab_eval<0>(jb, f.m1 * inv_T2)
+                          + nb * jtab_eval<0>(jb, f.mb * inv_T2);
+        return f.V01 + yt * T4c;
     }
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
 
 struct PotModel1F {
     static constexpr bool analytic = false;
+    static constexpr int min_blocks = CTB_THERMAL_MIN_BLOCKS;
     static constexpr int nparam = CTB_NPARAM_MODEL1F;
-    double lam, v2, Y, nb, rs, T;
+    double lam, v2, Y, nb, inv_rs, inv_T2, T4c;
     JTab jb;
     CTB_DEV void load(const double *p, const JTab *jb_, const JTab *)
     {
-        lam = p[0]; v2 = p[1]; Y = p[2]; nb = p[3]; rs = p[4]; T = p[5];
+        lam = p[0]; v2 = p[1]; Y = p[2]; nb = p[3];
+        const double T = p[5];
+        // the reference divides by renormScaleSq, T^2 + 1e-100 and 2 pi^2 at every evaluation
+        // (GP:250,282,296); the reciprocals are formed once here (<= 1 ulp per factor)
+        inv_rs = 1.0 / p[4];
+        inv_T2 = 1.0 / (T * T + 1e-100);
+        T4c = (T * T * T * T) / (2 * CTB_PI * CTB_PI);
         jb = *jb_;
     }
     __device__ __noinline__ double V(double phi) const // out of line, see PotModel1Line::V
     {
-        double m0 = lam * (3 * phi * phi - v2), m1 = Y * phi * phi;
-        double r = .25 * lam * (phi * phi - v2) * (phi * phi - v2);
-        double y1 = 0.0;
-        y1 += 1.0 * m0 * m0 * (log(fabs(m0 / rs) + 1e-100) - 1.5);
-        y1 += nb * m1 * m1 * (log(fabs(m1 / rs) + 1e-100) - 1.5);
-        r += y1 / (64 * CTB_PI * CTB_PI);
-        double T2 = T * T + 1e-100, T4 = T * T * T * T;
-        double yt = 0.0;
-        yt += 1.0 * jtab_eval<0>(jb, m0 / T2);
-        yt += nb * jtab_eval<0>(jb, m1 / T2);
-        r += yt * T4 / (2 * CTB_PI * CTB_PI);
-        return r;
+        const double p2 = phi * phi;
+        const double m0 = lam * (3 * p2 - v2), m1 = Y * p2;
+        double r = .25 * lam * (p2 - v2) * (p2 - v2);
+        double y1 = m0 * m0 * (log(fabs(m0 * inv_rs) + 1e-100) - 1.5);
+        y1 += nb * m1 * m1 * (log(fabs(m1 * inv_rs) + 1e-100) - 1.5);
+        r += y1 * (1.0 / (64 * CTB_PI * CTB_PI));
+        const double yt = jtab_eval<0>(jb, m0 * inv_T2) + nb * jtab_eval<0>(jb, m1 * inv_T2);
+        return r + yt * T4c;
     }
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
@@ -513,8 +503,9 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
 template <class Pot, int ALPHA>
 struct Sfi {
     Pot pot;
-    double phi_abs, phi_meta, phi_eps;
+    double phi_abs, phi_meta, phi_eps, inv_12eps;
     int n_rkck;
+    CTB_DEV void set_phi_eps(double e) { phi_eps = e; inv_12eps = 1.0 / (12. * e); }
 
     // T1D:151-161, 191-201 (5-point stencils) or the functor's analytic forms
     CTB_DEV double dV(double phi) const
@@ -524,7 +515,7 @@ struct Sfi {
         } else {
             double eps = phi_eps;
             return (pot.V(phi - 2 * eps) - 8 * pot.V(phi - eps) + 8 * pot.V(phi + eps) - pot.V(phi + 2 * eps))
-                   / (12. * eps);
+                   * inv_12eps;
         }
     }
     CTB_DEV double d2V(double phi) const
@@ -725,7 +716,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     res.n_shots = res.n_rkck = res.n_points = 0;
     res.status = CTB_ST_NOT_RUN;
     s.n_rkck = 0;
-    s.phi_eps = 0.0;
+    s.phi_eps = 0.0; s.inv_12eps = 0.0;
     const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
     const Pot &pot = s.pot;
     int phase = valid ? PH_SHOOT : PH_DONE;
@@ -739,7 +730,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
         res.rscale = rscale;
         if (st) { res.status = st; phase = PH_DONE; rscale = 1.0; phi_bar = 0.5 * (phi_abs + phi_meta); }
     }
-    s.phi_eps = k.phi_eps * fabs(phi_abs - phi_meta);
+    s.set_phi_eps(k.phi_eps * fabs(phi_abs - phi_meta));
 
     // ---- findProfile : T1D:676-700 ----
     const double xtol = k.xtol, phitol = k.phitol;

@@ -108,7 +108,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
     res.n_shots = res.n_rkck = res.n_points = 0;
     res.status = CTB_ST_NOT_RUN;
     s.n_rkck = 0;
-    s.phi_eps = 0.0;
+    s.phi_eps = 0.0; s.inv_12eps = 0.0;
     const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
     const Pot &pot = s.pot;
 
@@ -121,7 +121,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
         res.rscale = rscale;
         if (st) { res.status = st; return; }
     }
-    s.phi_eps = k.phi_eps * fabs(phi_abs - phi_meta);
+    s.set_phi_eps(k.phi_eps * fabs(phi_abs - phi_meta));
 
     const double xtol = k.xtol, phitol = k.phitol;
     double xmin = xtol * 10, xmax = INFINITY, x;
