@@ -32,6 +32,10 @@ WORKLOADS = {
                flop_per_bounce=9.0e4),
 }
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (bounce_kernel),
+# from the `ncu --set full` capture committed as profiles/r1_final_c2_final_metrics.csv
+# (8.07 MB read: 5.6 MB parameters/minima + 2.4 MB phi_bar/rscale/order; the 5.6 MB of results stay in L2)
+NCU_TRAFFIC_BYTES = {"c2": 8.072704e6 + 512.0}
 
 
 def sweep_c(n, rank=0, world=1):
@@ -321,7 +325,10 @@ def main():
                              "between timed iterations", "wall_s_timed_region": t_wall},
         "solved_fraction": float((status <= 1).mean()),
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                     "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                     "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
+                     "traffic_note": "bytes per launch of bounce_kernel, ncu dram__bytes_read+write "
+                                     "(profiles/r1_final_c2_final_metrics.csv); algorithmic: 64 B x instances",
                      "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
