@@ -144,6 +144,9 @@ int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaSt
     return (int)cudaGetLastError();
 }
 
+int launch_bounce_spline(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+int launch_setup_spline(const BounceArgs &a, cudaStream_t st);
+int launch_bounce_warp_spline(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);
 int launch_bounce_poly4(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_bounce_warp_poly4(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);
 int launch_bounce_warp_model1_line(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);

@@ -108,6 +108,56 @@ struct PotPoly4 {
     CTB_DEV double d2V(double x) const { return 2 * c2 + x * (6 * c3 + x * 12 * c4); }
 };
 
+// Tabulated potential (CTB_POT_SPLINE): one cubic per knot interval, per-instance table in global memory
+// (L1/L2-resident), located by bisection.  V, dV, d2V are the polynomial and its derivatives, i.e. what
+// splev(x, tck, der=0|1|2) returns for the reference's SplinePath.
+struct PotSpline {
+    static constexpr bool analytic = true;
+    static constexpr int min_blocks = 3;
+    static constexpr int nparam = CTB_NPARAM_SPLINE;
+    const double *brk, *coef;
+    int nint;
+    CTB_DEV void load(const double *p, const JTab *, const JTab *)
+    {
+        nint = (int)p[0];
+        if (nint < 1) nint = 1;
+        if (nint > CTB_SPLINE_MAX_PIECES) nint = CTB_SPLINE_MAX_PIECES;
+        brk = p + 1;
+        coef = p + 1 + (CTB_SPLINE_MAX_PIECES + 1);
+    }
+    CTB_DEV int locate(double x) const
+    {
+        int lo = 0, hi = nint - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (x >= __ldg(brk + mid)) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    }
+    CTB_DEV double V(double x) const
+    {
+        const int j = locate(x);
+        const double dx = x - __ldg(brk + j);
+        const double *c = coef + 4 * j;
+        return __ldg(c) + dx * (__ldg(c + 1) + dx * (__ldg(c + 2) + dx * __ldg(c + 3)));
+    }
+    CTB_DEV double V_quad(double x) const { return V(x); }
+    CTB_DEV double dV(double x) const
+    {
+        const int j = locate(x);
+        const double dx = x - __ldg(brk + j);
+        const double *c = coef + 4 * j;
+        return __ldg(c + 1) + dx * (2.0 * __ldg(c + 2) + dx * (3.0 * __ldg(c + 3)));
+    }
+    CTB_DEV double d2V(double x) const
+    {
+        const int j = locate(x);
+        const double dx = x - __ldg(brk + j);
+        const double *c = coef + 4 * j;
+        return 2.0 * __ldg(c + 2) + dx * (6.0 * __ldg(c + 3));
+    }
+};
+
 // Field-dependent part of model1's Vtot: the three boson masses (examples/testModel1.py:89-93) and
 // V0 + V1 (examples/testModel1.py:78-80, GP:240-256).  Independent of T.
 struct Model1Field { double m0, m1, mb, V01; };

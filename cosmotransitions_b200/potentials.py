@@ -57,6 +57,39 @@ class QuarticPotential(Poly4Potential):
         DevicePotential.__init__(self, quartic_family_params(c)[0])
 
 
+class SplinePotential(DevicePotential):
+    """Tabulated potential: the cubic B-spline (t, c, k) that scipy.interpolate.splrep returns -- what
+    pathDeformation.SplinePath builds from V_spline_samples samples and hands to the tunneling class as
+    V, dV, d2V = splev(x, tck, der=0|1|2) (pathDeformation.py:801-834).  Converted once, on the host, to
+    one cubic per knot interval."""
+    kind = _lib.POT_SPLINE
+
+    def __init__(self, tck):
+        t, c, k = tck
+        if k > 3:
+            raise ValueError("spline degree must be <= 3")
+        brk, coef = _tables.bspline_to_pp(np.asarray(t, float), np.asarray(c, float), int(k))
+        nint = coef.shape[0]
+        if nint > _lib.SPLINE_MAX_PIECES:
+            raise ValueError("spline has %d pieces; at most %d are supported" % (nint, _lib.SPLINE_MAX_PIECES))
+        row = np.zeros(_lib.NPARAM[self.kind])
+        row[0] = nint
+        row[1:1 + nint + 1] = brk
+        c4 = np.zeros((nint, 4))
+        c4[:, :coef.shape[1]] = coef
+        off = 1 + _lib.SPLINE_MAX_PIECES + 1
+        row[off:off + 4 * nint] = c4.reshape(-1)
+        self.tck = tck
+        super().__init__(row)
+
+    @classmethod
+    def from_callable(cls, V):
+        """If V is a bound method of an object that carries a `_V_tck` spline (the reference's
+        SplinePath.V / .dV / .d2V), wrap that spline; otherwise None."""
+        tck = getattr(getattr(V, "__self__", None), "_V_tck", None)
+        return cls(tck) if tck is not None else None
+
+
 def model1_model8(m1=120., m2=50., mu=25., Y1=.1, Y2=.15, n=30, v2=246. ** 2):
     """(l1, l2, mu2, Y1, Y2, n, renormScaleSq, v2) of examples/testModel1.py:19-47."""
     return np.array([.5 * m1 ** 2 / v2, .5 * m2 ** 2 / v2, mu ** 2, Y1, Y2, float(n), v2, v2])

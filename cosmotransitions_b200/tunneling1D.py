@@ -17,7 +17,7 @@ from collections import namedtuple
 import numpy as np
 
 from . import _lib, batch
-from .helper_functions import IntegrationError
+from .helper_functions import IntegrationError, monotonicIndices
 from .potentials import DevicePotential
 
 
@@ -63,6 +63,11 @@ class SingleFieldInstanton:
     def __init__(self, phi_absMin, phi_metaMin, V, dV=None, d2V=None, phi_eps=1e-3, alpha=2, phi_bar=None,
                  rscale=None):
         if not isinstance(V, DevicePotential):
+            # pathDeformation.fullTunneling passes path.V, path.dV, path.d2V of a SplinePath
+            # (pathDeformation.py:959-964): all three are splev() of one cubic spline -> tabulated functor
+            from .potentials import SplinePotential
+            V = SplinePotential.from_callable(V) or V
+        if not isinstance(V, DevicePotential):
             raise TypeError("V must be a cosmotransitions_b200.potentials.DevicePotential (device functor); "
                             "arbitrary Python callables cannot run on the GPU and there is no CPU fallback")
         self.phi_absMin, self.phi_metaMin = float(phi_absMin), float(phi_metaMin)
@@ -104,4 +109,26 @@ class SingleFieldInstanton:
                                   "returned by the most recent findProfile() call")
 
     def evenlySpacedPhi(self, phi, dphi, npoints=100, k=1, fixAbs=True):
-        raise NotImplementedError("evenlySpacedPhi belongs to the multi-field caller (SURVEY.md s.8f, next row)")
+        """
+        Re-grids `dphi` onto linearly spaced `phi` (tunneling1D.py:793-826; host-side post-processing of
+        one ~750-point profile for the multi-field caller, pathDeformation.py:967-968).  k=1 (the only
+        value the reference passes) is plain linear interpolation.
+        """
+        phi, dphi = np.asarray(phi, dtype=float), np.asarray(dphi, dtype=float)
+        if fixAbs is True:
+            phi = np.append(self.phi_absMin, np.append(phi, self.phi_metaMin))
+            dphi = np.append(0.0, np.append(dphi, 0.0))
+        else:
+            phi = np.append(phi, self.phi_metaMin)
+            dphi = np.append(dphi, 0.0)
+        i = monotonicIndices(phi)
+        if fixAbs:
+            p = np.linspace(self.phi_absMin, self.phi_metaMin, npoints)
+        else:
+            p = np.linspace(phi[i][0], self.phi_metaMin, npoints)
+        if k == 1:
+            dp = np.interp(p, phi[i], dphi[i])
+        else:
+            from scipy import interpolate
+            dp = interpolate.splev(p, interpolate.splrep(phi[i], dphi[i], k=k))
+        return p, dp

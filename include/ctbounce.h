@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 4
+#define CTB_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -65,7 +65,16 @@ extern "C" {
  * {lam(3phi^2-v2), Y phi^2}, dof (1, n), c = 3/2.  params[6] = lam, v2, Y, n, renormScaleSq, T      */
 #define CTB_POT_MODEL1F 2
 
+/* Tabulated potential: an interpolating cubic spline in piecewise-polynomial form -- what
+ * pathDeformation.SplinePath hands to the tunneling class (V, dV, d2V = splev of one cubic B-spline with
+ * der = 0, 1, 2; pathDeformation.py:801-834, 959-964).  Outside the table the end pieces extrapolate, as
+ * splev does.  params[1280] = nint (<= 255, as a double), brk[0..255], coef[255 * 4] (c0..c3 per piece:
+ * V = c0 + dx (c1 + dx (c2 + dx c3)), dx = phi - brk[j]), zero padded.                              */
+#define CTB_POT_SPLINE 3
+#define CTB_SPLINE_MAX_PIECES 255
+
 #define CTB_NPARAM_POLY4 5
+#define CTB_NPARAM_SPLINE 1280
 #define CTB_NPARAM_MODEL1_LINE 13
 #define CTB_NPARAM_MODEL1F 6
 

@@ -64,7 +64,7 @@ enum {
 enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
 
 /* potential kinds */
-enum { POT_POLY4 = 0, POT_MODEL1_LINE = 1, POT_MODEL1F = 2 };
+enum { POT_POLY4 = 0, POT_MODEL1_LINE = 1, POT_MODEL1F = 2, POT_SPLINE = 3 };
 
 typedef struct {
     int n;           /* number of knots  */
@@ -236,20 +236,32 @@ static double pot_V(const pot_t *P, double phi)
         return vtot_model1(p, P->jb, p[9] + phi * p[11], p[10] + phi * p[12], p[8]);
     case POT_MODEL1F:
         return vtot_model1f(p, P->jb, phi, p[5]);
+    case POT_SPLINE: { /* pathDeformation.SplinePath.V: splev(x, tck); p = [n, t[n], c[n]] */
+        spline_t s = {(int)p[0], 3, p + 1, p + 1 + (int)p[0], 0, 0};
+        return splev(&s, phi, 0);
+    }
     }
     return NAN;
 }
 
-static int pot_has_analytic_derivs(const pot_t *P) { return P->kind == POT_POLY4; }
+static int pot_has_analytic_derivs(const pot_t *P) { return P->kind == POT_POLY4 || P->kind == POT_SPLINE; }
 
 static double pot_dV_analytic(const pot_t *P, double phi)
 {
     const double *p = P->p;
+    if (P->kind == POT_SPLINE) { /* SplinePath.dV: splev(x, tck, der=1) */
+        spline_t s = {(int)p[0], 3, p + 1, p + 1 + (int)p[0], 0, 0};
+        return splev(&s, phi, 1);
+    }
     return p[1] + phi * (2 * p[2] + phi * (3 * p[3] + phi * 4 * p[4]));
 }
 static double pot_d2V_analytic(const pot_t *P, double phi)
 {
     const double *p = P->p;
+    if (P->kind == POT_SPLINE) { /* SplinePath.d2V: splev(x, tck, der=2) */
+        spline_t s = {(int)p[0], 3, p + 1, p + 1 + (int)p[0], 0, 0};
+        return splev(&s, phi, 2);
+    }
     return 2 * p[2] + phi * (6 * p[3] + phi * 12 * p[4]);
 }
 

@@ -16,6 +16,8 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
   tests/golden/units.npz        exactSolution / rkqs unit vectors
   tests/golden/model1.npz       generic_potential.Vtot for examples/testModel1.py + finite-T bounces
   tests/golden/model1f.json     one-field thermal model sweep
+  tests/golden/splinepath.npz   every 1-D solve inside pathDeformation.fullTunneling (examples/fullTunneling.py,
+                                model1.findAllTransitions): the SplinePath potential spline, profile, action
   tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
 """
 import json
@@ -345,6 +347,61 @@ def gen_model1():
     np.savez(os.path.join(GOLD, "model1.npz"), **out)
 
 
+def gen_splinepath():
+    """The reference's OWN multi-field flow: pathDeformation.fullTunneling on examples/fullTunneling.py
+    (BASELINE.json configs[0]) and model1.findAllTransitions().  Every time fullTunneling instantiates the
+    tunneling class it passes SplinePath.V / dV / d2V (pathDeformation.py:959-964); the spline (t, c, k),
+    the profile, evenlySpacedPhi's output and the action are recorded."""
+    import cosmoTransitions.pathDeformation as pd
+    import fullTunneling as ex
+    import testModel1
+    rec = []
+
+    class Recorder(t1.SingleFieldInstanton):
+        def __init__(self, phi_absMin, phi_metaMin, V, dV, d2V, **kw):
+            super().__init__(phi_absMin, phi_metaMin, V, dV, d2V, **kw)
+            self._rec = dict(tck=V.__self__._V_tck, phi_abs=phi_absMin, phi_meta=phi_metaMin,
+                             phi_bar=self.phi_bar, rscale=self.rscale)
+            rec.append(self._rec)
+
+        def findProfile(self, **kw):
+            p = super().findProfile(**kw)
+            self._rec.update(R=p.R, Phi=p.Phi, dPhi=p.dPhi, S=self.findAction(p))
+            return p
+
+        def evenlySpacedPhi(self, phi, dphi, **kw):
+            out = super().evenlySpacedPhi(phi, dphi, **kw)
+            self._rec.update(esp_kw=kw, esp_p=out[0], esp_dp=out[1])
+            return out
+
+    tags = []
+    for fy in (2.0, 80.0):
+        n0 = len(rec)
+        m = ex.Potential(c=5., fx=0., fy=fy)
+        Y = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV, tunneling_class=Recorder)
+        tags += ["fullTunneling_fy%g" % fy] * (len(rec) - n0)
+        print("fullTunneling fy=%g: %d 1-D solves, action %.9f" % (fy, len(rec) - n0, Y.action))
+    n0 = len(rec)
+    m1 = testModel1.model1()
+    m1.findAllTransitions(tunnelFromPhase_args=dict(fullTunneling_params=dict(tunneling_class=Recorder)))
+    tags += ["model1_findAllTransitions"] * (len(rec) - n0)
+    print("model1.findAllTransitions: %d 1-D solves; Tnuc %.6f action %.6f" % (
+        len(rec) - n0, m1.TnTrans[0]["Tnuc"], m1.TnTrans[0]["action"]))
+    out = {"n": len(rec), "tags": np.array(tags)}
+    for i, r in enumerate(rec):
+        t, c, k = r["tck"]
+        assert k == 3
+        out["t%d" % i], out["c%d" % i] = t, c
+        out["scal%d" % i] = np.array([r["phi_abs"], r["phi_meta"], r["phi_bar"], r["rscale"], r.get("S", np.nan)])
+        for key in ("R", "Phi", "dPhi", "esp_p", "esp_dp"):
+            if key in r:
+                out["%s%d" % (key, i)] = r[key]
+        if "esp_kw" in r:
+            out["espkw%d" % i] = np.array([r["esp_kw"].get("npoints", 100), r["esp_kw"].get("k", 1),
+                                           1 if r["esp_kw"].get("fixAbs", True) else 0])
+    np.savez_compressed(os.path.join(GOLD, "splinepath.npz"), **out)
+
+
 class Model1F(gp.generic_potential):
     """One-field model1-style thermal potential, written against the real
     generic_potential so that Vtot / V1 / V1T / Jb_spline are the reference's own code."""
@@ -401,7 +458,8 @@ def gen_model1f():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f"]
+    which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
+                               "splinepath"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

@@ -12,8 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libctb_oracle.so")
 
-POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F = 0, 1, 2
-NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6}
+POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE = 0, 1, 2, 3
+NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: None}  # spline: 1 + 2 n_knots
 
 STATUS_NAMES = {
     0: "converged", 1: "xtol", 2: "stable, not metastable", 3: "no barrier", 4: "r > rmax",
@@ -79,10 +79,17 @@ class Tables:
         return cls(d["tb"], d["cb"], d["tf"], d["cf"])
 
 
+def spline_params(tck):
+    """Parameter row of POT_SPLINE for the oracle: [n, t[n], c[n]] (cubic tck as returned by splrep)."""
+    t, c, k = tck
+    assert k == 3
+    return np.concatenate([[len(t)], np.asarray(t, float), np.asarray(c, float)])
+
+
 def make_config(kind=POT_POLY4, alpha=2, tables=None, xtol=1e-4, phitol=1e-4, thinCutoff=.01, npoints=500,
-                rmin=1e-4, rmax=1e4, max_interior_pts=None, phi_eps=1e-3, xguess=None):
+                rmin=1e-4, rmax=1e4, max_interior_pts=None, phi_eps=1e-3, xguess=None, nparam=None):
     cfg = _Config()
-    cfg.kind, cfg.nparam, cfg.alpha, cfg.npoints = kind, NPARAM[kind], int(alpha), int(npoints)
+    cfg.kind, cfg.nparam, cfg.alpha, cfg.npoints = kind, nparam or NPARAM[kind], int(alpha), int(npoints)
     cfg.max_interior_pts = -1 if max_interior_pts is None else int(max_interior_pts)
     cfg.xtol, cfg.phitol, cfg.thinCutoff, cfg.rmin, cfg.rmax = xtol, phitol, thinCutoff, rmin, rmax
     cfg.phi_eps = phi_eps

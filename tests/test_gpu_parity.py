@@ -90,6 +90,55 @@ def test_profiles_golden(ctb, gold_dir):
         assert abs(S - float(g[name + "_S"])) < S_RTOL * abs(float(g[name + "_S"]))
 
 
+def test_splinepath_drop_in(ctb, gold_dir):
+    """The class as pathDeformation.fullTunneling uses it (pathDeformation.py:959-968, 1000):
+    tunneling_class(0.0, path.L, path.V, path.dV, path.d2V).findProfile() -> evenlySpacedPhi -> findAction,
+    on every spline potential the reference built for examples/fullTunneling.py (BASELINE.json
+    configs[0]) and for model1.findAllTransitions()."""
+    from scipy import interpolate
+    from cosmotransitions_b200 import tunneling1D as t1
+
+    class FakeSplinePath:     # stands in for pathDeformation.SplinePath (the reference is not on the GPU box)
+        def __init__(self, tck):
+            self._V_tck = tck
+
+        def V(self, x):
+            return interpolate.splev(x, self._V_tck, der=0)
+
+        def dV(self, x):
+            return interpolate.splev(x, self._V_tck, der=1)
+
+        def d2V(self, x):
+            return interpolate.splev(x, self._V_tck, der=2)
+
+    g = np.load(os.path.join(gold_dir, "splinepath.npz"))
+    worst = 0.0
+    for i in range(int(g["n"])):
+        path = FakeSplinePath((g["t%d" % i], g["c%d" % i], 3))
+        pa, pm, bar, rs, S_ref = g["scal%d" % i]
+        tobj = t1.SingleFieldInstanton(pa, pm, path.V, path.dV, path.d2V)
+        assert abs(tobj.phi_bar - bar) <= 1e-11 * max(1.0, abs(bar))
+        # findRScale stops fminbound at xtol = 1e-6 |phi_bar - phi_meta| (tunneling1D.py:261-265): the barrier
+        # top, hence rscale, is only defined to ~1e-6 relative; the piecewise-cubic form of the spline rounds
+        # differently from FITPACK's de Boor recursion, so the last parabolic steps may differ
+        assert abs(tobj.rscale - rs) <= 5e-5 * rs
+        prof = tobj.findProfile()
+        S = tobj.findAction(prof)
+        rel = abs(S - S_ref) / abs(S_ref)
+        print(i, str(g["tags"][i]), "rscale rel %.2e  S rel %.2e" % (abs(tobj.rscale - rs) / rs, rel))
+        worst = max(worst, rel)
+        assert rel < S_RTOL, (i, str(g["tags"][i]), rel)
+        assert len(prof.R) == len(g["R%d" % i])
+        np.testing.assert_allclose(prof.R, g["R%d" % i], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(prof.Phi, g["Phi%d" % i], rtol=0, atol=1e-7 * abs(pm - pa))
+        if "esp_p%d" % i in g:
+            npts, k, fixAbs = (int(v) for v in g["espkw%d" % i])
+            p, dp = tobj.evenlySpacedPhi(g["Phi%d" % i], g["dPhi%d" % i], npoints=npts, k=k, fixAbs=bool(fixAbs))
+            np.testing.assert_allclose(p, g["esp_p%d" % i], rtol=1e-14, atol=1e-14)
+            np.testing.assert_allclose(dp, g["esp_dp%d" % i], rtol=1e-11, atol=1e-13)
+    print("splinepath drop-in: worst rel err in S", worst)
+
+
 def test_scalar_api_errors(ctb):
     from cosmotransitions_b200 import tunneling1D as t1, potentials
     with pytest.raises(t1.PotentialError) as e:

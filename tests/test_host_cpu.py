@@ -110,3 +110,41 @@ def test_status_to_exception_mapping():
         t1.raise_for_status(_lib.ST_NONFINITE)
     t1.raise_for_status(0)
     t1.raise_for_status(1)
+
+
+def test_evenly_spaced_phi_matches_reference_golden(gold_dir):
+    """evenlySpacedPhi is host-side numpy (tunneling1D.py:793-826): checked on CPU against the reference's
+    recorded calls (no GPU needed: the method does not touch the solver)."""
+    from cosmotransitions_b200 import tunneling1D as t1
+    g = np.load(os.path.join(gold_dir, "splinepath.npz"))
+    done = 0
+    for i in range(int(g["n"])):
+        if "esp_p%d" % i not in g:
+            continue
+        pa, pm = g["scal%d" % i][:2]
+        obj = t1.SingleFieldInstanton.__new__(t1.SingleFieldInstanton)
+        obj.phi_absMin, obj.phi_metaMin = float(pa), float(pm)
+        npts, k, fixAbs = (int(v) for v in g["espkw%d" % i])
+        p, dp = obj.evenlySpacedPhi(g["Phi%d" % i], g["dPhi%d" % i], npoints=npts, k=k, fixAbs=bool(fixAbs))
+        np.testing.assert_allclose(p, g["esp_p%d" % i], rtol=1e-14, atol=1e-14)
+        np.testing.assert_allclose(dp, g["esp_dp%d" % i], rtol=1e-11, atol=1e-13)
+        done += 1
+    assert done >= 10
+
+
+def test_spline_potential_row_layout():
+    from scipy import interpolate
+    from cosmotransitions_b200 import _lib, potentials
+    x = np.linspace(-1, 3, 60)
+    tck = interpolate.splrep(x, np.sin(x) * x, s=0)
+    pot = potentials.SplinePotential(tck)
+    row = pot.params
+    nint = int(row[0])
+    assert nint == 57 and len(row) == _lib.NPARAM[_lib.POT_SPLINE]
+    brk = row[1:2 + nint]
+    coef = row[1 + 256:1 + 256 + 4 * nint].reshape(nint, 4)
+    xs = np.random.default_rng(0).uniform(-1, 3, 500)
+    j = np.clip(np.searchsorted(brk, xs, side="right") - 1, 0, nint - 1)
+    dx = xs - brk[j]
+    v = coef[j, 0] + dx * (coef[j, 1] + dx * (coef[j, 2] + dx * coef[j, 3]))
+    np.testing.assert_allclose(v, interpolate.splev(xs, tck), rtol=1e-12, atol=1e-13)

@@ -189,3 +189,27 @@ def test_model1f_bounces(oracle, tables, gold_dir):
         assert abs(r["S"] - c["S"]) < 1e-6 * abs(c["S"]), (c["T"], r["S"], c["S"])
         assert r["n_points"] == c["npts"]
         assert r["n_shots"] == c["n_shots"]
+
+
+def test_splinepath_solves(oracle, gold_dir):
+    """Every 1-D solve the reference performs inside pathDeformation.fullTunneling
+    (examples/fullTunneling.py thin + thick, model1.findAllTransitions): potential = SplinePath's spline."""
+    g = np.load(os.path.join(gold_dir, "splinepath.npz"))
+    n = int(g["n"])
+    assert n >= 20
+    worst = 0.0
+    for i in range(n):
+        tck = (g["t%d" % i], g["c%d" % i], 3)
+        pa, pm, bar, rs, S = g["scal%d" % i]
+        params = oracle.spline_params(tck)
+        cfg = oracle.make_config(kind=oracle.POT_SPLINE, alpha=2, nparam=len(params))
+        r = oracle.bounce_one(cfg, params, pa, pm)
+        assert r["status"] in (0, 1)
+        assert abs(r["phi_bar"] - bar) <= 1e-12 * max(1.0, abs(bar))
+        assert abs(r["rscale"] - rs) <= 1e-9 * rs
+        rel = abs(r["S"] - S) / abs(S)
+        worst = max(worst, rel)
+        assert rel < S_RTOL, (i, str(g["tags"][i]), rel)
+        assert len(r["R"]) == len(g["R%d" % i])
+        np.testing.assert_allclose(r["Phi"], g["Phi%d" % i], rtol=0, atol=1e-9 * abs(pm - pa))
+    print("splinepath worst rel err", worst)
