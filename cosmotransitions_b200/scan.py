@@ -126,6 +126,53 @@ def model1f_bounce_scan(lam, Y, n, nT=256, v2=246. ** 2, window=None, phi_box=(5
                 n_rkck=res["n_rkck"].reshape(P, nT))
 
 
+def model1f_tnuc(lam, Y, n, v2=246. ** 2, target=140.0, nT_coarse=24, rounds=10, T_tol=1e-7, phi_box=(50.0, 500.0),
+                 window=None, **knobs):
+    """Nucleation temperature per parameter point: the root of S3(T)/T - 140 (the reference's default
+    nuclCriterion, transitionFinder.py:773, found there by a sequential brentq over T, :836-837).
+    Batched form: a coarse sweep brackets the crossing, then every round solves ONE bounce per point at
+    an Illinois (regula-falsi) abscissa, all points in one launch.  Returns device tensors
+    dict(Tnuc, S, T0, Tc, bracket_lo, bracket_hi, rounds)."""
+    torch = _lib.require_cuda()
+    lam, Y, n = (torch.as_tensor(x, dtype=torch.float64).cuda().reshape(-1) for x in (lam, Y, n))
+    P = lam.numel()
+    sweep = model1f_bounce_scan(lam, Y, n, nT=nT_coarse, v2=v2, window=window, phi_box=phi_box, **knobs)
+    T, soT = sweep["T"], sweep["S_over_T"]
+    f = soT - target
+    cross = (f[:, :-1] <= 0) & (f[:, 1:] > 0)
+    has = cross.any(dim=1)
+    idx = (cross.to(torch.int64) * torch.arange(1, nT_coarse, device=T.device)).amax(dim=1)
+    i0 = (idx - 1).clamp(min=0)
+    a, b = T.gather(1, i0[:, None])[:, 0], T.gather(1, idx[:, None])[:, 0]
+    fa, fb = f.gather(1, i0[:, None])[:, 0], f.gather(1, idx[:, None])[:, 0]
+    lo = torch.full((P,), phi_box[0], dtype=torch.float64, device=T.device)
+    hi = torch.full((P,), phi_box[1], dtype=torch.float64, device=T.device)
+    side = torch.zeros(P, dtype=torch.int64, device=T.device)
+    S_last = torch.full((P,), float("nan"), dtype=torch.float64, device=T.device)
+    done_rounds = 0
+    for _ in range(rounds):
+        if not bool(((b - a) > T_tol).any()):
+            break
+        done_rounds += 1
+        Tm = (a * fb - b * fa) / (fb - fa)
+        bad = ~torch.isfinite(Tm) | (Tm <= a) | (Tm >= b)
+        Tm = torch.where(bad, 0.5 * (a + b), Tm)
+        params = model1f_params(lam, Y, n, Tm, v2)
+        phi_abs, _ = minimize_1d(_lib.POT_MODEL1F, params, lo, hi)
+        r = batch.find_bounce_batch(_lib.POT_MODEL1F, params, phi_abs, torch.zeros_like(phi_abs), **knobs)
+        fm = torch.where(r["status"] <= 1, r["S"] / Tm - target, torch.full_like(Tm, float("inf")))
+        S_last = r["S"]
+        left = fm <= 0          # root is to the right of Tm
+        # Illinois: halve the retained end's function value when the same side is kept twice in a row
+        fb = torch.where(left & (side == 1), 0.5 * fb, fb)
+        fa = torch.where(~left & (side == 2), 0.5 * fa, fa)
+        side = torch.where(left, torch.ones_like(side), torch.full_like(side, 2))
+        a, fa = torch.where(left, Tm, a), torch.where(left, fm, fa)
+        b, fb = torch.where(left, b, Tm), torch.where(left, fb, fm)
+    Tn = torch.where(has, torch.where(fa.abs() < fb.abs(), a, b), torch.full_like(a, float("nan")))
+    return dict(Tnuc=Tn, S=S_last, T0=sweep["T0"], Tc=sweep["Tc"], bracket_lo=a, bracket_hi=b, rounds=done_rounds)
+
+
 # ---- model1 along a fixed straight line (BASELINE.json configs[3]; SURVEY.md s.8d C4) -------------------
 
 def model1_line_bounce_scan(model8, x_low, x_high, T, alpha=2, **knobs):

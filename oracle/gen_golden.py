@@ -452,6 +452,17 @@ def gen_model1f():
                      Vsamples=[float(V(x, T)) for x in (0.0, 0.3 * pa, 0.7 * pa, pa, 1.1 * pa)])
             cases.append(r)
             print("model1f", k, "T=%.3f" % T, {q: r.get(q) for q in ("S", "npts", "n_shots", "n_rkck", "error")})
+        # nucleation temperature the reference's way: brentq over T of S3(T)/T - 140
+        # (transitionFinder.py:773, 836-837), phi_absMin(T) re-minimised at every T
+        def nucl(T):
+            pa_ = float(optimize.minimize_scalar(lambda p: float(V(p, T)), bounds=(50, 500), method="bounded",
+                                                 options=dict(xatol=1e-10)).x)
+            o = t1.SingleFieldInstanton(pa_, 0.0, lambda phi: V(phi, T))
+            return o.findAction(o.findProfile()) / T - 140.0
+        Tn = optimize.brentq(nucl, T0 + 0.05 * (Tc - T0), T0 + 0.98 * (Tc - T0), xtol=1e-6)
+        for c_ in cases[-5:]:
+            c_["Tnuc"] = float(Tn)
+        print("model1f", k, "Tnuc = %.6f" % Tn)
     with open(os.path.join(GOLD, "model1f.json"), "w") as f:
         json.dump(cases, f, indent=0)
 
