@@ -11,19 +11,21 @@
  * and committed under tests/golden/.  tests/test_oracle_golden.py checks this file against them.
  *
  * What it follows (file:line into the reference checkout):
- *   cosmoTransitions/tunneling1D.py:128-149   SingleFieldInstanton.__init__        -> ctbo_setup
- *   cosmoTransitions/tunneling1D.py:151-201   dV / d2V finite differences, dV_from_absMin
- *   cosmoTransitions/tunneling1D.py:203-226   findBarrierLocation                  -> find_barrier
- *   cosmoTransitions/tunneling1D.py:228-285   findRScale                           -> find_rscale
+ *   cosmoTransitions/tunneling1D.py:128-149   SingleFieldInstanton.__init__        -> sfi_setup
+ *   cosmoTransitions/tunneling1D.py:151-201   dV / d2V finite differences, dV_from_absMin -> sfi_dV, sfi_d2V, sfi_dV_from_absMin
+ *   cosmoTransitions/tunneling1D.py:203-226   findBarrierLocation                  -> sfi_setup (bisection block)
+ *   cosmoTransitions/tunneling1D.py:228-285   findRScale                           -> sfi_setup (fminbound block)
  *   cosmoTransitions/tunneling1D.py:294-373   exactSolution                        -> exact_solution
  *   cosmoTransitions/tunneling1D.py:377-434   initialConditions                    -> initial_conditions
  *   cosmoTransitions/tunneling1D.py:436-440   equationOfMotion                     -> eom
  *   cosmoTransitions/tunneling1D.py:444-536   integrateProfile                     -> integrate_profile
  *   cosmoTransitions/tunneling1D.py:539-613   integrateAndSaveProfile              -> integrate_and_save
- *   cosmoTransitions/tunneling1D.py:615-761   findProfile                          -> find_profile
- *   cosmoTransitions/tunneling1D.py:763-791   findAction                           -> find_action
+ *   cosmoTransitions/tunneling1D.py:615-761   findProfile                          -> solve_one
+ *   cosmoTransitions/tunneling1D.py:763-791   findAction                           -> solve_one (tail)
  *   cosmoTransitions/helper_functions.py:113-179  rkqs ; :204-236 _rkck ; :583-599 cubicInterpFunction
- *   cosmoTransitions/finiteT.py:167-174,197-204   Jf_spline / Jb_spline (evaluation + clamps)
+ *   cosmoTransitions/finiteT.py:167-174,197-204   Jf_spline / Jb_spline (evaluation + clamps)   -> J_spline
+ *   cosmoTransitions/finiteT.py:207-296           Jb/Jf low- and high-x series                  -> ctbo_jseries
+ *   cosmoTransitions/pathDeformation.py:811-834   SplinePath.V / dV / d2V (splev of one tck)    -> POT_SPLINE
  *   cosmoTransitions/generic_potential.py:240-337 V1, V1T, Vtot
  *   examples/testModel1.py:62-116                 model1.V0 / boson_massSq
  *

@@ -235,6 +235,22 @@ def test_scalar_api_overrides(ctb):
     assert inst.phi_bar == 0.8
 
 
+def test_multigpu_driver(ctb):
+    """Single-process multi-device driver: strided shards, gather in the original order.  With one
+    visible device it degenerates to one shard; with several the result must not change."""
+    import torch
+    from cosmotransitions_b200 import _lib, batch, multigpu, potentials
+    n = 777
+    c = 0.02 + 0.475 * np.random.default_rng(2).random(n)
+    p = potentials.quartic_family_params(c)
+    ref = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, kernel="thread"))
+    devs = list(range(torch.cuda.device_count()))
+    for dl in ([0], devs, [0, 0, 0]):       # the same device three times exercises G > 1 on a 1-GPU box
+        got = _np(multigpu.find_bounce_batch_multi(_lib.POT_POLY4, p, 1.0, 0.0, devices=dl, kernel="thread"))
+        for k in ("S", "phi0", "rf", "status", "n_rkck"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (dl, k)
+
+
 def test_edge_batches(ctb):
     from cosmotransitions_b200 import _lib, batch, potentials
     r = batch.find_bounce_batch(_lib.POT_POLY4, np.zeros((0, 5)), np.zeros(0), np.zeros(0))

@@ -148,3 +148,18 @@ def test_spline_potential_row_layout():
     dx = xs - brk[j]
     v = coef[j, 0] + dx * (coef[j, 1] + dx * (coef[j, 2] + dx * coef[j, 3]))
     np.testing.assert_allclose(v, interpolate.splev(xs, tck), rtol=1e-12, atol=1e-13)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the keys the
+    driver reads.  Runs on CPU in a few seconds."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], stdout=subprocess.PIPE, text=True, timeout=600).stdout
+    j = json.loads(out.strip().splitlines()[-1])
+    assert j["impl"] == "reference" and j["unit"] == "bounces/s" and j["higher_is_better"] is True
+    assert j["value"] > 1e3 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    assert j["config"]["workload"].startswith("C2") and j["solved_fraction"] == 1.0
