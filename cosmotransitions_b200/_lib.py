@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 5
+ABI_VERSION = 6
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE = 0, 1, 2, 3
 SPLINE_MAX_PIECES = 255
@@ -39,7 +39,8 @@ class Opts(C.Structure):
 
 class BounceIn(C.Structure):
     _fields_ = [("d_params", C.c_void_p), ("d_phi_abs", C.c_void_p), ("d_phi_meta", C.c_void_p),
-                ("d_phi_bar", C.c_void_p), ("d_rscale", C.c_void_p), ("d_order", C.c_void_p), ("n", C.c_int64)]
+                ("d_phi_bar", C.c_void_p), ("d_rscale", C.c_void_p), ("d_order", C.c_void_p), ("d_scratch", C.c_void_p),
+                ("n", C.c_int64)]
 
 
 class BounceOut(C.Structure):

@@ -51,8 +51,9 @@ def _as_device(torch, x, device, shape=None):
     return t.contiguous()
 
 
-def _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar=None, rscale=None, order=None):
+def _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar=None, rscale=None, order=None, scratch=None):
     bi = _lib.BounceIn()
+    bi.d_scratch = scratch.data_ptr() if scratch is not None else None
     bi.d_params, bi.d_phi_abs, bi.d_phi_meta = d_params.data_ptr(), d_phi_abs.data_ptr(), d_phi_meta.data_ptr()
     bi.d_phi_bar = phi_bar.data_ptr() if phi_bar is not None else None
     bi.d_rscale = rscale.data_ptr() if rscale is not None else None
@@ -76,7 +77,7 @@ SORT_THRESHOLD = 4096
 
 
 def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=None, stream=None, schedule="auto",
-                  phi_bar=None, rscale=None):
+                  phi_bar=None, rscale=None, split="auto"):
     """Lowest-level call: device tensors in, device tensors (pre-allocated dict `out`) filled.
     Asynchronous on `stream` (default: torch's current stream).
 
@@ -84,7 +85,9 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
     rscale and a work predictor per instance, the instances are sorted heavy-first (so that lanes of a
     warp follow similar trajectories and the longest-running warps start first), and the solve kernel
     walks that permutation.  Results do not depend on the schedule (instances are independent).
-    "auto" = sorted for batches of SORT_THRESHOLD or more."""
+    "auto" = sorted for batches of SORT_THRESHOLD or more.
+    split: run the thread-per-instance solve as two kernels (shooting, then dense output + action) handing
+    over through a 3 n-double scratch buffer; "auto" = for batches of SORT_THRESHOLD or more.  Same results."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     n = d_phi_abs.numel()
@@ -107,7 +110,12 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
             phi_bar, rscale = out["phi_bar"], out["rscale"]
         elif schedule != "natural":
             raise ValueError("schedule must be 'auto', 'sorted' or 'natural'")
-        bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale, order)
+        scratch = None
+        if split == "auto":
+            split = n >= SORT_THRESHOLD
+        if split and profiles is None and opts.kernel != _lib.KERNEL_WARP:
+            scratch = torch.empty(3 * n, dtype=torch.float64, device=dev)
+        bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale, order, scratch)
         _lib.check(lib.ctb_bounce_batch(kind, bi, opts, jb, jf, bo, st), "ctb_bounce_batch")
 
 
@@ -137,7 +145,7 @@ def alloc_out(torch, n, device):
 
 def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, phi_eps=1e-3, device=None,
                       return_profiles=False, block_threads=0, schedule="auto", phi_bar=None, rscale=None,
-                      kernel="auto", **findProfile_knobs):
+                      kernel="auto", split="auto", **findProfile_knobs):
     """Solve N independent bounces.
 
     potential_kind : one of _lib.POT_* (or a DevicePotential subclass / instance, whose kind is used)
@@ -177,7 +185,8 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
     d_bar = _as_device(torch, phi_bar, device, (n,)) if phi_bar is not None else None
     d_rs = _as_device(torch, rscale, device, (n,)) if rscale is not None else None
     if n:
-        launch_bounce(kind, d_params, d_abs, d_meta, opts, out, prof, schedule=schedule, phi_bar=d_bar, rscale=d_rs)
+        launch_bounce(kind, d_params, d_abs, d_meta, opts, out, prof, schedule=schedule, phi_bar=d_bar, rscale=d_rs,
+                      split=split)
     if prof is not None:
         out.update(prof)
     if on_host:

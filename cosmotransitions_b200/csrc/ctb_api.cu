@@ -338,6 +338,7 @@ static int fill_args(BounceArgs &a, const ctb_bounce_in *in, const ctb_jtable *j
     if (in->n > 0 && (!in->d_params || !in->d_phi_abs || !in->d_phi_meta)) return CTB_ERR_BAD_ARG;
     a.params = in->d_params; a.phi_abs = in->d_phi_abs; a.phi_meta = in->d_phi_meta; a.n = in->n;
     a.phi_bar_in = in->d_phi_bar; a.rscale_in = in->d_rscale; a.order = in->d_order; a.work_key = nullptr;
+    a.scratch = in->d_scratch;
     a.jb = to_jtab(jb); a.jf = to_jtab(jf);
     a.out = *out;
     return CTB_OK;

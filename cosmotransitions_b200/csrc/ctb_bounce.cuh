@@ -17,7 +17,8 @@ struct BounceArgs {
     const double *params, *phi_abs, *phi_meta;
     const double *phi_bar_in, *rscale_in; // optional overrides (NaN entry = compute)
     const int64_t *order;                 // optional permutation: thread t solves instance order[t]
-    float *work_key;                      // setup kernel only
+    float *work_key;
+    double *scratch;                      // split solve: 3 n doubles (y(r0), y'(r0), delta_phi0 of the accepted shot)                     // setup kernel only
     int64_t n;
     Knobs knobs;
     JTab jb, jf;
@@ -27,8 +28,22 @@ struct BounceArgs {
 // One thread = one instance.  Adjacent instances (adjacent model parameters) share a warp, so that
 // lanes follow similar trajectories; blocks are small so that the hardware block scheduler balances
 // the 4x spread in work per instance across the 148 SMs.
-template <class Pot, int ALPHA, bool PROFILE>
-__global__ void __launch_bounds__(CTB_MAX_BLOCK, Pot::min_blocks) bounce_kernel(const BounceArgs a)
+// occupancy target (128-thread blocks per SM) per kernel flavour; tuned on B200
+#ifndef CTB_SHOOT_MIN_BLOCKS
+#define CTB_SHOOT_MIN_BLOCKS 3
+#endif
+#ifndef CTB_SAVE_MIN_BLOCKS
+#define CTB_SAVE_MIN_BLOCKS 3
+#endif
+template <class Pot, int MODE>
+constexpr int bounce_min_blocks()
+{
+    if (!Pot::analytic) return Pot::min_blocks;
+    return MODE == MODE_SHOOT ? CTB_SHOOT_MIN_BLOCKS : MODE == MODE_SAVE ? CTB_SAVE_MIN_BLOCKS : Pot::min_blocks;
+}
+
+template <class Pot, int ALPHA, bool PROFILE, int MODE>
+__global__ void __launch_bounds__(CTB_MAX_BLOCK, bounce_min_blocks<Pot, MODE>()) bounce_kernel(const BounceArgs a)
 {
     // every lane of every warp runs the solver (it votes warp-wide); lanes past the end of the batch
     // carry a dummy instance that is never integrated
@@ -53,10 +68,25 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, Pot::min_blocks) bounce_kernel(
         sink.Phi = a.out.d_prof_Phi + i * a.out.prof_stride;
         sink.dPhi = a.out.d_prof_dPhi + i * a.out.prof_stride;
     }
+    HandOff h{nullptr, nullptr, nullptr};
+    if (MODE != MODE_FUSED) { h.y00 = a.scratch + i; h.y01 = a.scratch + a.n + i; h.dphi0 = a.scratch + 2 * a.n + i; }
     const double qn = nan("");
-    solve_instance<Pot, ALPHA, PROFILE>(s, a.knobs, valid, a.phi_bar_in ? a.phi_bar_in[i] : qn,
-                                        a.rscale_in ? a.rscale_in[i] : qn, r, sink);
+    double phi_bar_in = a.phi_bar_in ? a.phi_bar_in[i] : qn, rscale_in = a.rscale_in ? a.rscale_in[i] : qn;
+    if (MODE == MODE_SAVE) { // what the shoot kernel left behind (these outputs are mandatory in split mode)
+        r.status = a.out.d_status[i]; r.r0 = a.out.d_r0[i]; r.rf = a.out.d_rf[i];
+        r.n_shots = a.out.d_n_shots[i]; r.n_rkck = a.out.d_n_rkck[i];
+        r.S = qn; r.n_points = 0;
+        phi_bar_in = a.out.d_phi_bar[i]; rscale_in = a.out.d_rscale[i];
+    }
+    solve_instance<Pot, ALPHA, PROFILE, MODE>(s, a.knobs, valid, phi_bar_in, rscale_in, r, sink, h);
     if (!valid) return;
+    if (MODE == MODE_SAVE) {
+        if (a.out.d_S) a.out.d_S[i] = r.S;
+        a.out.d_status[i] = r.status;
+        a.out.d_n_rkck[i] = r.n_rkck;
+        if (a.out.d_n_points) a.out.d_n_points[i] = r.n_points;
+        return;
+    }
     if (a.out.d_S) a.out.d_S[i] = r.S;
     if (a.out.d_phi0) a.out.d_phi0[i] = r.phi0;
     if (a.out.d_r0) a.out.d_r0[i] = r.r0;
@@ -113,11 +143,22 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     unsigned grid = (unsigned)((a.n + block - 1) / block);
     const bool prof = a.out.d_prof_R != nullptr;
     const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double);
-    if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false><<<grid, block, sm, st>>>(a);
-    else if (alpha == 3 && !prof) bounce_kernel<Pot, 3, false><<<grid, block, sm, st>>>(a);
-    else if (alpha == 2) bounce_kernel<Pot, 2, true><<<grid, block, sm, st>>>(a);
-    else if (alpha == 3) bounce_kernel<Pot, 3, true><<<grid, block, sm, st>>>(a);
-    else return CTB_ERR_UNSUPPORTED;
+    // split solve (shoot kernel, then save kernel) when the caller provides scratch and all hand-over arrays
+    const bool split = a.scratch && !prof && a.out.d_status && a.out.d_r0 && a.out.d_rf && a.out.d_n_shots &&
+                       a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
+    if (alpha != 2 && alpha != 3) return CTB_ERR_UNSUPPORTED;
+    if (split) {
+        if (alpha == 2) {
+            bounce_kernel<Pot, 2, false, MODE_SHOOT><<<grid, block, sm, st>>>(a);
+            bounce_kernel<Pot, 2, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
+        } else {
+            bounce_kernel<Pot, 3, false, MODE_SHOOT><<<grid, block, sm, st>>>(a);
+            bounce_kernel<Pot, 3, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
+        }
+    } else if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false, MODE_FUSED><<<grid, block, sm, st>>>(a);
+    else if (alpha == 3 && !prof) bounce_kernel<Pot, 3, false, MODE_FUSED><<<grid, block, sm, st>>>(a);
+    else if (alpha == 2) bounce_kernel<Pot, 2, true, MODE_FUSED><<<grid, block, sm, st>>>(a);
+    else bounce_kernel<Pot, 3, true, MODE_FUSED><<<grid, block, sm, st>>>(a);
     return (int)cudaGetLastError();
 }
 

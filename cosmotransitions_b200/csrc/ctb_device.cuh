@@ -85,9 +85,12 @@ CTB_DEV double jtab_eval(const JTab &t, double theta)
 // potentials
 #define CTB_PI 3.14159265358979323846
 
+#ifndef CTB_POLY4_MIN_BLOCKS
+#define CTB_POLY4_MIN_BLOCKS 3
+#endif
 struct PotPoly4 {
     static constexpr bool analytic = true;
-    static constexpr int min_blocks = 3; // 128-thread blocks per SM the bounce kernel is compiled for (<= 168 regs)
+    static constexpr int min_blocks = CTB_POLY4_MIN_BLOCKS; // 128-thread blocks per SM the bounce kernel is compiled for (<= 168 regs)
     static constexpr int nparam = CTB_NPARAM_POLY4;
     double c0, c1, c2, c3, c4;
     CTB_DEV void load(const double *p, const JTab *, const JTab *)
@@ -756,29 +759,47 @@ CTB_DEV double work_key(double phi_abs, double phi_meta, double phi_bar)
 // code runs once per warp instead of once per group of lanes that happen to finish together.
 enum { PH_SHOOT = 0, PH_WAIT = 1, PH_SAVE = 2, PH_DONE = 3 };
 
-template <class Pot, int ALPHA, bool PROFILE>
+// The solve can also be split over two kernels (MODE_SHOOT then MODE_SAVE) that hand the accepted shot
+// over through global memory: all warps of an SM are then in the same phase, which halves the hot
+// instruction footprint each kernel needs in the instruction cache.  MODE_FUSED is the single-kernel form.
+enum { MODE_FUSED = 0, MODE_SHOOT = 1, MODE_SAVE = 2 };
+struct HandOff { // state of the last integrated shot (pointers already offset to this instance)
+    double *y00, *y01, *dphi0;
+};
+
+template <class Pot, int ALPHA, bool PROFILE, int MODE>
 __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, double phi_bar_in, double rscale_in,
-                               InstanceResult &res, const ProfileSink &sink)
+                               InstanceResult &res, const ProfileSink &sink, const HandOff &h)
 {
     const unsigned FULL = 0xffffffffu;
     const double qnan = nan("");
-    res.S = res.phi0 = res.r0 = res.rf = res.x = res.phi_bar = res.rscale = qnan;
-    res.n_shots = res.n_rkck = res.n_points = 0;
-    res.status = CTB_ST_NOT_RUN;
-    s.n_rkck = 0;
+    // MODE_SAVE: res arrives filled with what the shoot kernel wrote (status, r0, rf, x, n_shots, n_rkck)
+    const int status_in = res.status;
+    const double r0_in = res.r0, rf_in = res.rf;
+    if (MODE != MODE_SAVE) {
+        res.S = res.phi0 = res.r0 = res.rf = res.x = res.phi_bar = res.rscale = qnan;
+        res.n_shots = res.n_rkck = res.n_points = 0;
+        res.status = CTB_ST_NOT_RUN;
+        s.n_rkck = 0;
+    } else {
+        s.n_rkck = res.n_rkck;
+        valid = valid && (status_in == CTB_ST_CONVERGED || status_in == CTB_ST_XTOL);
+    }
     s.phi_eps = 0.0; s.inv_12eps = 0.0;
     const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
     const Pot &pot = s.pot;
-    int phase = valid ? PH_SHOOT : PH_DONE;
+    int phase = valid ? (MODE == MODE_SAVE ? PH_WAIT : PH_SHOOT) : PH_DONE;
 
     // ---- __init__ : T1D:128-149 ----
     double V_meta = 0.0, phi_bar = phi_bar_in, rscale = rscale_in;
     if (valid) {
         V_meta = pot.V(phi_meta);
-        int st = sfi_init(pot, phi_abs, phi_meta, V_meta, phi_bar, rscale);
-        res.phi_bar = phi_bar;
-        res.rscale = rscale;
-        if (st) { res.status = st; phase = PH_DONE; rscale = 1.0; phi_bar = 0.5 * (phi_abs + phi_meta); }
+        if (MODE != MODE_SAVE) { // (the save kernel receives the phi_bar / rscale the shoot kernel used)
+            int st = sfi_init(pot, phi_abs, phi_meta, V_meta, phi_bar, rscale);
+            res.phi_bar = phi_bar;
+            res.rscale = rscale;
+            if (st) { res.status = st; phase = PH_DONE; rscale = 1.0; phi_bar = 0.5 * (phi_abs + phi_meta); }
+        }
     }
     s.set_phi_eps(k.phi_eps * fabs(phi_abs - phi_meta));
 
@@ -801,6 +822,12 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     bool have_rf = false;
     double rf = qnan, r0 = qnan, y00 = qnan, y01 = qnan, delta_phi0 = qnan, dv0 = qnan, d2v0 = qnan;
     int status = CTB_ST_XTOL, nshots = 0;
+    if (MODE == MODE_SAVE && valid) { // take over the last integrated shot
+        r0 = r0_in; rf = rf_in; y00 = *h.y00; y01 = *h.y01; delta_phi0 = *h.dphi0;
+        status = status_in; nshots = res.n_shots;
+        dv0 = s.dV_from_absMin(delta_phi0);
+        d2v0 = s.d2V(phi_abs + delta_phi0);
+    }
     // dense-output state (save pass only)
     SimpsonStream simp;
     int N = 0, i_pt = 1, pidx = 0;
@@ -817,10 +844,11 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
 
     for (;;) { // one trip = one shot (T1D:702-727) or, once for the whole warp, the save pass (T1D:729-761)
         if (__all_sync(FULL, phase != PH_SHOOT)) {
+            if (MODE == MODE_SHOOT) break; // every lane has its accepted shot (or failed): hand over
             if (__all_sync(FULL, phase == PH_DONE)) break;
             if (phase == PH_WAIT) phase = PH_SAVE;
         }
-        if (phase == PH_SHOOT) {
+        if (MODE != MODE_SAVE && phase == PH_SHOOT) {
             delta_phi0 = exp(-x) * delta_phi;
             dv0 = s.dV_from_absMin(delta_phi0);
             d2v0 = s.d2V(phi_abs + delta_phi0);
@@ -835,7 +863,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 r0 = r0_; y00 = p0; y01 = dp0;
             }
         }
-        if (phase == PH_SAVE) { // grid, interior points (T1D:734-760) and the first dense-output point
+        if (MODE != MODE_SHOOT && phase == PH_SAVE) { // grid, interior points (T1D:734-760), first dense point
             res.r0 = r0; res.rf = rf;
             res.phi0 = phi_abs + delta_phi0;
             step = (rf - r0) / (npoints - 1);
@@ -882,7 +910,8 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
 
         // ---- integrate from (r0, y00, y01): T1D:489-536 (shooting) / T1D:578-613 (saving) ----
         if (phase == PH_SHOOT || phase == PH_SAVE) {
-            const bool saving = phase == PH_SAVE;
+            // compile-time constant in the split kernels: the other mode's code is not generated
+            const bool saving = (MODE == MODE_SAVE) ? true : (MODE == MODE_SHOOT) ? false : (phase == PH_SAVE);
             int ctype = -1;
             double r_ = r0, ya = y00, yb = y01, dr = dr0, da, db;
             s.eom(ya, yb, r_, da, db);
@@ -969,6 +998,12 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     }
     res.n_shots = nshots;
     res.n_rkck = s.n_rkck;
+    if (MODE == MODE_SHOOT && phase == PH_WAIT) { // accepted shot -> global memory for the save kernel
+        res.status = status;
+        res.r0 = r0; res.rf = rf;
+        res.phi0 = phi_abs + delta_phi0;
+        *h.y00 = y00; *h.y01 = y01; *h.dphi0 = delta_phi0;
+    }
 }
 
 } // namespace ctb

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 5
+#define CTB_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -134,6 +134,9 @@ typedef struct ctb_bounce_in {
     const double *d_rscale;   /* optional [n]: the rscale= override (tunneling1D.py:144-147)         */
     const int64_t *d_order;   /* optional [n] permutation: GPU thread t solves instance d_order[t]
                                  (results are always written at the instance's own index)           */
+    double *d_scratch;        /* optional [3 n] workspace.  When given (thread-per-instance kernel, no profile
+                                 dump, all scalar outputs requested) the solve runs as two kernels -- shooting,
+                                 then dense output + action -- handing the accepted shot over through it  */
     int64_t n;
 } ctb_bounce_in;
 

@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.JTable) == 64
     assert C.sizeof(_lib.Opts) == 7 * 8 + 6 * 4
     assert C.sizeof(_lib.BounceOut) == 15 * 8
-    assert C.sizeof(_lib.BounceIn) == 7 * 8
+    assert C.sizeof(_lib.BounceIn) == 8 * 8
 
 
 def test_bspline_to_pp_matches_scipy():
