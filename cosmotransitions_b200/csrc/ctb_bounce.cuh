@@ -28,22 +28,19 @@ struct BounceArgs {
 // One thread = one instance.  Adjacent instances (adjacent model parameters) share a warp, so that
 // lanes follow similar trajectories; blocks are small so that the hardware block scheduler balances
 // the 4x spread in work per instance across the 148 SMs.
-// occupancy target (128-thread blocks per SM) per kernel flavour; tuned on B200
-#ifndef CTB_SHOOT_MIN_BLOCKS
-#define CTB_SHOOT_MIN_BLOCKS 3
-#endif
-#ifndef CTB_SAVE_MIN_BLOCKS
-#define CTB_SAVE_MIN_BLOCKS 3
-#endif
-template <class Pot, int MODE>
+// Occupancy target (128-thread blocks per SM), measured on B200: the shoot kernel of an
+// analytic potential wants 3 blocks (168 registers, no spills) while the batch is small enough for the
+// longest warps to set the run time (C2, 1e5 instances: 1.107 vs 1.156 ms) and 4 blocks (128 registers)
+// once throughput dominates (C3, 1e6 instances: 10.59 vs 11.05 ms); the save kernel wants 4 in both.
+template <class Pot, int MODE, int OCC>
 constexpr int bounce_min_blocks()
 {
     if (!Pot::analytic) return Pot::min_blocks;
-    return MODE == MODE_SHOOT ? CTB_SHOOT_MIN_BLOCKS : MODE == MODE_SAVE ? CTB_SAVE_MIN_BLOCKS : Pot::min_blocks;
+    return MODE == MODE_SHOOT ? OCC : MODE == MODE_SAVE ? 4 : Pot::min_blocks;
 }
 
-template <class Pot, int ALPHA, bool PROFILE, int MODE>
-__global__ void __launch_bounds__(CTB_MAX_BLOCK, bounce_min_blocks<Pot, MODE>()) bounce_kernel(const BounceArgs a)
+template <class Pot, int ALPHA, bool PROFILE, int MODE, int OCC = 3>
+__global__ void __launch_bounds__(CTB_MAX_BLOCK, bounce_min_blocks<Pot, MODE, OCC>()) bounce_kernel(const BounceArgs a)
 {
     // every lane of every warp runs the solver (it votes warp-wide); lanes past the end of the batch
     // carry a dummy instance that is never integrated
@@ -148,11 +145,14 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
                        a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
     if (alpha != 2 && alpha != 3) return CTB_ERR_UNSUPPORTED;
     if (split) {
+        const bool big = Pot::analytic && a.n >= 300000; // throughput regime: trade registers for warps
         if (alpha == 2) {
-            bounce_kernel<Pot, 2, false, MODE_SHOOT><<<grid, block, sm, st>>>(a);
+            if (big) bounce_kernel<Pot, 2, false, MODE_SHOOT, 4><<<grid, block, sm, st>>>(a);
+            else bounce_kernel<Pot, 2, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
             bounce_kernel<Pot, 2, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
         } else {
-            bounce_kernel<Pot, 3, false, MODE_SHOOT><<<grid, block, sm, st>>>(a);
+            if (big) bounce_kernel<Pot, 3, false, MODE_SHOOT, 4><<<grid, block, sm, st>>>(a);
+            else bounce_kernel<Pot, 3, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
             bounce_kernel<Pot, 3, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
         }
     } else if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false, MODE_FUSED><<<grid, block, sm, st>>>(a);

@@ -12,6 +12,15 @@
 namespace ctb {
 
 #define CTB_DEV __device__ __forceinline__
+// PINNED ARITHMETIC.  Everything that steers control flow of the integration (Cash-Karp stages, error
+// norm, step controller, dense-output cubic, root finds, potential derivatives) is written with explicit
+// fma() / __dmul_rn / __dadd_rn so that the rounding of every operation is fixed in the source instead of
+// being left to the compiler's FMA-contraction choices.  The shoot kernel, the save kernel, the fused
+// kernel and the warp kernel are separate compilations of this code and must produce the SAME trajectory
+// bit for bit (e.g. the save pass has to find the end point rf inside the very step in which the shot found it).
+#define CTB_MUL(a, b) __dmul_rn((a), (b))
+#define CTB_ADD(a, b) __dadd_rn((a), (b))
+#define CTB_SUB(a, b) __dsub_rn((a), (b))
 #ifndef CTB_THERMAL_MIN_BLOCKS
 #define CTB_THERMAL_MIN_BLOCKS 4
 #endif
@@ -107,8 +116,11 @@ struct PotPoly4 {
         return __dadd_rn(c0, __dmul_rn(x, v));
     }
     CTB_DEV double V_quad(double x) const { return c0 + x * (c1 + x * (c2 + x * (c3 + x * c4))); } // integrand only
-    CTB_DEV double dV(double x) const { return c1 + x * (2 * c2 + x * (3 * c3 + x * 4 * c4)); }
-    CTB_DEV double d2V(double x) const { return 2 * c2 + x * (6 * c3 + x * 12 * c4); }
+    CTB_DEV double dV(double x) const
+    {
+        return fma(x, fma(x, fma(x, CTB_MUL(4.0, c4), CTB_MUL(3.0, c3)), CTB_MUL(2.0, c2)), c1);
+    }
+    CTB_DEV double d2V(double x) const { return fma(x, fma(x, CTB_MUL(12.0, c4), CTB_MUL(6.0, c3)), CTB_MUL(2.0, c2)); }
 };
 
 // Tabulated potential (CTB_POT_SPLINE): one cubic per knot interval, per-instance table in global memory
@@ -142,7 +154,7 @@ struct PotSpline {
         const int j = locate(x);
         const double dx = x - __ldg(brk + j);
         const double *c = coef + 4 * j;
-        return __ldg(c) + dx * (__ldg(c + 1) + dx * (__ldg(c + 2) + dx * __ldg(c + 3)));
+        return fma(dx, fma(dx, fma(dx, __ldg(c + 3), __ldg(c + 2)), __ldg(c + 1)), __ldg(c));
     }
     CTB_DEV double V_quad(double x) const { return V(x); }
     CTB_DEV double dV(double x) const
@@ -150,14 +162,14 @@ struct PotSpline {
         const int j = locate(x);
         const double dx = x - __ldg(brk + j);
         const double *c = coef + 4 * j;
-        return __ldg(c + 1) + dx * (2.0 * __ldg(c + 2) + dx * (3.0 * __ldg(c + 3)));
+        return fma(dx, fma(dx, CTB_MUL(3.0, __ldg(c + 3)), CTB_MUL(2.0, __ldg(c + 2))), __ldg(c + 1));
     }
     CTB_DEV double d2V(double x) const
     {
         const int j = locate(x);
         const double dx = x - __ldg(brk + j);
         const double *c = coef + 4 * j;
-        return 2.0 * __ldg(c + 2) + dx * (6.0 * __ldg(c + 3));
+        return fma(dx, CTB_MUL(6.0, __ldg(c + 3)), CTB_MUL(2.0, __ldg(c + 2)));
     }
 };
 
@@ -265,13 +277,14 @@ CTB_DEV double rcp_fast(double x)
 // y -> y (6 - x y^5) / 5 in FP64 (quadratic: 1e-6 -> 1e-12 -> rounding).  Replaces pow(errmax, -0.2).
 CTB_DEV double inv_fifth_root(double x)
 {
-    double y = (double)exp2f(-0.2f * __log2f((float)x));
-    double y2 = y * y;
-    double y5 = y2 * y2 * y;
-    y = y * fma(-0.2 * x, y5, 1.2);
-    y2 = y * y;
-    y5 = y2 * y2 * y;
-    y = y * fma(-0.2 * x, y5, 1.2);
+    double y = (double)exp2f(__fmul_rn(-0.2f, __log2f((float)x)));
+    const double mx = CTB_MUL(-0.2, x);
+    double y2 = CTB_MUL(y, y);
+    double y5 = CTB_MUL(CTB_MUL(y2, y2), y);
+    y = CTB_MUL(y, fma(mx, y5, 1.2));
+    y2 = CTB_MUL(y, y);
+    y5 = CTB_MUL(CTB_MUL(y2, y2), y);
+    y = CTB_MUL(y, fma(mx, y5, 1.2));
     return y;
 }
 
@@ -300,18 +313,19 @@ CTB_DEV double brentq(F f, double xa, double xb, int &err)
             xpre = xcur; xcur = xblk; xblk = xpre;
             fpre = fcur; fcur = fblk; fblk = fpre;
         }
-        delta = (xtol + rtol * fabs(xcur)) / 2;
+        delta = CTB_ADD(xtol, CTB_MUL(rtol, fabs(xcur))) / 2;
         sbis = (xblk - xcur) / 2;
         if (fcur == 0 || fabs(sbis) < delta) return xcur;
         if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
             if (xpre == xblk) {
-                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+                stry = CTB_MUL(-fcur, xcur - xpre) / (fcur - fpre);
             } else {
                 dpre = (fpre - fcur) / (xpre - xcur);
                 dblk = (fblk - fcur) / (xblk - xcur);
-                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+                stry = CTB_MUL(-fcur, CTB_SUB(CTB_MUL(fblk, dblk), CTB_MUL(fpre, dpre)))
+                       / CTB_MUL(CTB_MUL(dblk, dpre), fblk - fpre);
             }
-            double m1 = fabs(spre), m2 = 3 * fabs(sbis) - delta;
+            double m1 = fabs(spre), m2 = CTB_SUB(CTB_MUL(3.0, fabs(sbis)), delta);
             double mn = (m1 < m2) ? m1 : m2;
             if (2 * fabs(stry) < mn) { spre = scur; scur = stry; }
             else { spre = sbis; scur = sbis; }
@@ -567,8 +581,9 @@ struct Sfi {
             return pot.dV(phi);
         } else {
             double eps = phi_eps;
-            return (pot.V(phi - 2 * eps) - 8 * pot.V(phi - eps) + 8 * pot.V(phi + eps) - pot.V(phi + 2 * eps))
-                   * inv_12eps;
+            const double va = pot.V(CTB_SUB(phi, CTB_MUL(2.0, eps))), vb = pot.V(CTB_SUB(phi, eps));
+            const double vc = pot.V(CTB_ADD(phi, eps)), vd = pot.V(CTB_ADD(phi, CTB_MUL(2.0, eps)));
+            return CTB_MUL(CTB_SUB(CTB_ADD(CTB_SUB(va, CTB_MUL(8.0, vb)), CTB_MUL(8.0, vc)), vd), inv_12eps);
         }
     }
     CTB_DEV double d2V(double phi) const
@@ -577,8 +592,13 @@ struct Sfi {
             return pot.d2V(phi);
         } else {
             double eps = phi_eps;
-            return (-pot.V(phi - 2 * eps) + 16 * pot.V(phi - eps) - 30 * pot.V(phi) + 16 * pot.V(phi + eps)
-                    - pot.V(phi + 2 * eps)) / (12. * eps * eps);
+            const double va = pot.V(CTB_SUB(phi, CTB_MUL(2.0, eps))), vb = pot.V(CTB_SUB(phi, eps)), v0 = pot.V(phi);
+            const double vc = pot.V(CTB_ADD(phi, eps)), vd = pot.V(CTB_ADD(phi, CTB_MUL(2.0, eps)));
+            double acc = CTB_ADD(-va, CTB_MUL(16.0, vb));
+            acc = CTB_SUB(acc, CTB_MUL(30.0, v0));
+            acc = CTB_ADD(acc, CTB_MUL(16.0, vc));
+            acc = CTB_SUB(acc, vd);
+            return acc / CTB_MUL(CTB_MUL(12., eps), eps);
         }
     }
     // T1D:163-189
@@ -587,10 +607,10 @@ struct Sfi {
         double phi = phi_abs + delta_phi;
         double dv = dV(phi);
         if (phi_eps > 0) {
-            double dv_ = d2V(phi) * delta_phi;
+            double dv_ = CTB_MUL(d2V(phi), delta_phi);
             double q = delta_phi / phi_eps;
-            double blend = exp(-(q * q));
-            dv = dv_ * blend + dv * (1 - blend);
+            double blend = exp(-CTB_MUL(q, q));
+            dv = CTB_ADD(CTB_MUL(dv_, blend), CTB_MUL(dv, 1 - blend));
         }
         return dv;
     }
@@ -628,7 +648,7 @@ struct Sfi {
     CTB_DEV void eom(double y0, double y1, double r, double &f0, double &f1) const
     {
         f0 = y1;
-        f1 = dV(y0) - (ALPHA * y1) * rcp_fast(r);
+        f1 = fma(-CTB_MUL((double)ALPHA, y1), rcp_fast(r), dV(y0));
     }
 
     // HF:204-236 Cash-Karp step
@@ -646,18 +666,22 @@ struct Sfi {
         const double dc4 = c4 - 13525.0 / 55296.0, dc6 = c6 - 0.25;
         double k20, k21, k30, k31, k40, k41, k50, k51, k60, k61;
         n_rkck++;
-        eom(y0 + b21 * dt * d0, y1 + b21 * dt * d1, t + a2 * dt, k20, k21);
-        eom(y0 + dt * (b31 * d0 + b32 * k20), y1 + dt * (b31 * d1 + b32 * k21), t + a3 * dt, k30, k31);
-        eom(y0 + dt * (b41 * d0 + b42 * k20 + b43 * k30), y1 + dt * (b41 * d1 + b42 * k21 + b43 * k31), t + a4 * dt,
-            k40, k41);
-        eom(y0 + dt * (b51 * d0 + b52 * k20 + b53 * k30 + b54 * k40),
-            y1 + dt * (b51 * d1 + b52 * k21 + b53 * k31 + b54 * k41), t + a5 * dt, k50, k51);
-        eom(y0 + dt * (b61 * d0 + b62 * k20 + b63 * k30 + b64 * k40 + b65 * k50),
-            y1 + dt * (b61 * d1 + b62 * k21 + b63 * k31 + b64 * k41 + b65 * k51), t + a6 * dt, k60, k61);
-        dy0 = dt * (c1 * d0 + c3 * k30 + c4 * k40 + c6 * k60);
-        dy1 = dt * (c1 * d1 + c3 * k31 + c4 * k41 + c6 * k61);
-        e0 = dt * (dc1 * d0 + dc3 * k30 + dc4 * k40 + dc5 * k50 + dc6 * k60);
-        e1 = dt * (dc1 * d1 + dc3 * k31 + dc4 * k41 + dc5 * k51 + dc6 * k61);
+        // (pinned arithmetic: y + dt * (sum_j b_j k_j) with the sum accumulated left to right by FMAs)
+        const double h21 = CTB_MUL(b21, dt);
+        eom(fma(h21, d0, y0), fma(h21, d1, y1), fma(a2, dt, t), k20, k21);
+        eom(fma(dt, fma(b32, k20, CTB_MUL(b31, d0)), y0), fma(dt, fma(b32, k21, CTB_MUL(b31, d1)), y1), fma(a3, dt, t),
+            k30, k31);
+        eom(fma(dt, fma(b43, k30, fma(b42, k20, CTB_MUL(b41, d0))), y0),
+            fma(dt, fma(b43, k31, fma(b42, k21, CTB_MUL(b41, d1))), y1), fma(a4, dt, t), k40, k41);
+        eom(fma(dt, fma(b54, k40, fma(b53, k30, fma(b52, k20, CTB_MUL(b51, d0)))), y0),
+            fma(dt, fma(b54, k41, fma(b53, k31, fma(b52, k21, CTB_MUL(b51, d1)))), y1), fma(a5, dt, t), k50, k51);
+        eom(fma(dt, fma(b65, k50, fma(b64, k40, fma(b63, k30, fma(b62, k20, CTB_MUL(b61, d0))))), y0),
+            fma(dt, fma(b65, k51, fma(b64, k41, fma(b63, k31, fma(b62, k21, CTB_MUL(b61, d1))))), y1), fma(a6, dt, t),
+            k60, k61);
+        dy0 = CTB_MUL(dt, fma(c6, k60, fma(c4, k40, fma(c3, k30, CTB_MUL(c1, d0)))));
+        dy1 = CTB_MUL(dt, fma(c6, k61, fma(c4, k41, fma(c3, k31, CTB_MUL(c1, d1)))));
+        e0 = CTB_MUL(dt, fma(dc6, k60, fma(dc5, k50, fma(dc4, k40, fma(dc3, k30, CTB_MUL(dc1, d0))))));
+        e1 = CTB_MUL(dt, fma(dc6, k61, fma(dc5, k51, fma(dc4, k41, fma(dc3, k31, CTB_MUL(dc1, d1))))));
     }
 
     // HF:113-179; returns 0 or CTB_ST_STEP_UNDERFLOW.  dt is in/out (try -> used).
@@ -668,21 +692,22 @@ struct Sfi {
         for (;;) {
             double e0, e1;
             rkck(y0, y1, d0, d1, t, dt, dy0, dy1, e0, e1);
-            double a0 = fabs(e0) * inv_ea0, b0 = fabs(e0) * rcp_fast((fabs(y0) + 1e-300) * epsfrac);
-            double a1 = fabs(e1) * inv_ea1, b1 = fabs(e1) * rcp_fast((fabs(y1) + 1e-300) * epsfrac);
+            double a0 = CTB_MUL(fabs(e0), inv_ea0), b0 = CTB_MUL(fabs(e0), rcp_fast(CTB_MUL(fabs(y0) + 1e-300, epsfrac)));
+            double a1 = CTB_MUL(fabs(e1), inv_ea1), b1 = CTB_MUL(fabs(e1), rcp_fast(CTB_MUL(fabs(y1) + 1e-300, epsfrac)));
             double m0 = (a0 < b0) ? a0 : b0, m1 = (a1 < b1) ? a1 : b1;
             errmax = (m0 > m1) ? m0 : m1;
             // numpy min/max propagate NaN; nan_to_num: NaN -> 0, +inf -> DBL_MAX
             if (isnan((a0 + b0) + (a1 + b1))) errmax = 0.0; // all four are >= 0: the sum is NaN iff one is
             else if (isinf(errmax)) errmax = 1.7976931348623157e308;
             if (errmax < 1.0) break;
-            double dttemp = 0.9 * dt * rsqrt(sqrt(errmax));
-            if (dt > 0) dt = (dt * .1 > dttemp) ? dt * .1 : dttemp;
-            else dt = (dt * .1 < dttemp) ? dt * .1 : dttemp;
+            double dttemp = CTB_MUL(CTB_MUL(0.9, dt), rsqrt(sqrt(errmax)));
+            const double dt10 = CTB_MUL(dt, .1);
+            if (dt > 0) dt = (dt10 > dttemp) ? dt10 : dttemp;
+            else dt = (dt10 < dttemp) ? dt10 : dttemp;
             if (t + dt == t) return CTB_ST_STEP_UNDERFLOW;
         }
-        if (errmax > 1.89e-4) dtnext = 0.9 * dt * inv_fifth_root(errmax);
-        else dtnext = 5 * dt;
+        if (errmax > 1.89e-4) dtnext = CTB_MUL(CTB_MUL(0.9, dt), inv_fifth_root(errmax));
+        else dtnext = CTB_MUL(5.0, dt);
         return 0;
     }
 };
@@ -695,11 +720,11 @@ struct Cubic {
     CTB_DEV void init(double y0, double dy0, double y1, double dy1)
     {
         const double third = 1.0 / 3.0;
-        double Y1 = y0 + dy0 * third, Y2 = y1 - dy1 * third;
+        double Y1 = fma(dy0, third, y0), Y2 = fma(-dy1, third, y1);
         A0 = y0;
-        A1 = 3.0 * (Y1 - y0);
-        A2 = 3.0 * ((y0 - Y1) + (Y2 - Y1));
-        A3 = (y1 - y0) + 3.0 * (Y1 - Y2);
+        A1 = CTB_MUL(3.0, Y1 - y0);
+        A2 = CTB_MUL(3.0, (y0 - Y1) + (Y2 - Y1));
+        A3 = fma(3.0, Y1 - Y2, y1 - y0);
         Yend = y1;
     }
     CTB_DEV double operator()(double t) const { return fma(t, fma(t, fma(t, A3, A2), A1), A0); }
@@ -950,7 +975,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                         int berr;
                         double xx = brentq([&](double t) { return fr.at(t) - off; }, 0.0, 1.0, berr);
                         if (berr == 1 || berr == 2) { fail((berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN); break; }
-                        rf = r_ + dr * xx;
+                        rf = fma(dr, xx, r_);
                         yf0 = f0.at(xx); yf1 = f1.at(xx);
                         break;
                     }

@@ -77,7 +77,7 @@ __device__ void run_shot(Sfi<Pot, ALPHA> &s, const ShootConsts &c, double x, Sho
             int berr;
             double xx = brentq([&](double t) { return fr.at(t) - off; }, 0.0, 1.0, berr);
             if (berr == 1 || berr == 2) { o.status = (berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN; ctype = -1; break; }
-            rf = r_ + dr * xx;
+            rf = fma(dr, xx, r_);
             yf0 = f0.at(xx); yf1 = f1.at(xx);
             break;
         }
