@@ -32,10 +32,11 @@ WORKLOADS = {
                flop_per_bounce=9.0e4),
 }
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (bounce_kernel),
-# from the `ncu --set full` capture committed as profiles/r1_final_c2_final_metrics.csv
-# (8.07 MB read: 5.6 MB parameters/minima + 2.4 MB phi_bar/rscale/order; the 5.6 MB of results stay in L2)
-NCU_TRAFFIC_BYTES = {"c2": 8.072704e6 + 512.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (the shoot kernel,
+# bounce_kernel<.., MODE_SHOOT>: 0.68 of the 1.0 ms of kernel time per step), from the `ncu --set full`
+# capture committed as profiles/r1_final_c2_split_metrics.csv (8.06 MB read: 5.6 MB parameters/minima +
+# 2.4 MB phi_bar/rscale/order; results and the 2.4 MB hand-over to the save kernel stay in L2)
+NCU_TRAFFIC_BYTES = {"c2": 8.056320e6}
 
 
 def sweep_c(n, rank=0, world=1):
@@ -319,23 +320,24 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "instances_per_gpu": n, "alpha": wl["alpha"], "order": args.order,
-                   "schedule": "work-sorted (setup kernel + device argsort + solve kernel, all inside the timed "
-                               "step)" if sorted_sched else "natural",
+                   "schedule": "work-sorted (setup kernel + device argsort + shoot kernel + save kernel, all inside "
+                               "the timed step)" if sorted_sched else "natural",
                    "timing": "CUDA events around each step's kernel on torch's current stream; 256 MiB L2 flush "
                              "between timed iterations", "wall_s_timed_region": t_wall},
         "solved_fraction": float((status <= 1).mean()),
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak if fp64_peak else None,
                      "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-                     "traffic_note": "bytes per launch of bounce_kernel, ncu dram__bytes_read+write "
-                                     "(profiles/r1_final_c2_final_metrics.csv); algorithmic: 64 B x instances",
+                     "traffic_note": "bytes per launch of the shoot kernel, ncu dram__bytes_read+write "
+                                     "(profiles/r1_final_c2_split_metrics.csv); algorithmic: 64 B x instances",
                      "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "bytes_per_bounce": BYTES_PER_BOUNCE}},
         "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * (2 if sorted_sched else 1),
+        # per step: setup_kernel + shoot kernel + save kernel (work-sorted, split solve); fused otherwise
+        "gpu_launches": args.steps * (3 if sorted_sched else 1),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
