@@ -464,6 +464,26 @@ def test_model1f_tnuc_vs_golden(ctb, gold_dir):
     assert np.all((out["bracket_hi"] - out["bracket_lo"]).cpu().numpy() < 1e-3)
 
 
+def test_c3_full_size_subsample_vs_oracle(ctb, oracle):
+    """BASELINE.json config C3 at full size (1e6 quartic instances, alpha=3) through the production path
+    (work-sorted, split solve); every 500th instance is checked against the CPU oracle."""
+    from cosmotransitions_b200 import _lib, batch, potentials
+    N = 1000000
+    c = 0.02 + 0.475 * (np.arange(N) + 0.5) / N
+    r = _np(batch.find_bounce_batch(_lib.POT_POLY4, potentials.quartic_family_params(c), 1.0, 0.0, alpha=3))
+    assert (r["status"] <= 1).all() and np.all(np.isfinite(r["S"])) and np.all(r["S"] > 0)
+    idx = np.arange(0, N, 500)
+    o = oracle.bounce_batch(oracle.make_config(alpha=3), potentials.quartic_family_params(c[idx]), 1.0, 0.0,
+                            nthreads=os.cpu_count() or 1)
+    assert np.array_equal(r["status"][idx], o["status"])
+    rel = np.abs(r["S"][idx] - o["S"]) / np.abs(o["S"])
+    print("C3 subsample: max rel err S", rel.max())
+    assert rel.max() < S_RTOL_TIGHT
+    assert np.array_equal(r["n_rkck"][idx], o["n_rkck"]) and np.array_equal(r["n_shots"][idx], o["n_shots"])
+    sm = r["S"].reshape(-1, 10000).mean(axis=1)
+    assert np.all(np.diff(sm) > 0)
+
+
 def test_c2_full_size_properties(ctb):
     """BASELINE.json config C2 at full size (1e5 quartic instances, alpha=2): size-independent
     properties -- every instance solves, S(c) is strictly increasing along the thick->thin sweep,
