@@ -195,7 +195,7 @@ __global__ void potential_kernel(const double *params, JTab jb, JTab jf, const d
 {
     extern __shared__ double smem[];
     if (!Pot::analytic) {
-        jb = stage_table(jb, smem);
+        jb = stage_table_compact(jb, smem);
         __syncthreads();
     }
     Pot pot;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) rows_kernel(const double *__restrict__ pa
 {
     extern __shared__ double smem[];
     if (!Pot::analytic) {
-        jb = stage_table(jb, smem);
+        jb = stage_table_compact(jb, smem);
         __syncthreads();
     }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +248,7 @@ __global__ void fp64_peak_kernel(int64_t iters, double *sink)
 
 JTab to_jtab(const ctb_jtable *t)
 {
-    JTab j{nullptr, nullptr, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f};
+    JTab j{nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f};
     if (t) {
         j.brk = t->d_brk; j.coef = t->d_coef; j.nint = t->nint; j.xmin = t->xmin; j.xmax = t->xmax;
         j.loc_scale = (float)t->loc_scale; j.loc_u0 = (float)t->loc_u0; j.loc_inv_du = (float)t->loc_inv_du;
@@ -257,6 +257,7 @@ JTab to_jtab(const ctb_jtable *t)
 }
 
 size_t table_bytes(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES(t->nint) * sizeof(double) : 0; }
+size_t table_bytes_compact(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES_COMPACT(t->nint) * sizeof(double) : 0; }
 
 bool jtab_ok(const ctb_jtable *t) { return t && t->d_brk && t->d_coef && t->nint >= 1 && t->nint <= 5000; }
 
@@ -274,12 +275,12 @@ int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, cons
         break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        rows_kernel<PotModel1Line, MINIMIZE><<<g, 128, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+        rows_kernel<PotModel1Line, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
                                                                              xtol_rel, o0, o1, n);
         break;
     case CTB_POT_MODEL1F:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        rows_kernel<PotModel1F, MINIMIZE><<<g, 128, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+        rows_kernel<PotModel1F, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
                                                                           xtol_rel, o0, o1, n);
         break;
     default: return CTB_ERR_UNSUPPORTED;
@@ -417,7 +418,7 @@ CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = table_bytes(tab);
     int64_t gneed = (n + 256 * 4 - 1) / (256 * 4);
-    int g = (int)(gneed < 148 * 5 ? (gneed < 1 ? 1 : gneed) : 148 * 5); // persistent: 5 blocks x 40 KB per SM
+    int g = (int)(gneed < 148 * 4 ? (gneed < 1 ? 1 : gneed) : 148 * 4); // persistent: 4 blocks x 48 KB per SM
     switch (deriv) {
     case 0: jspline_kernel<0><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
     case 1: jspline_kernel<1><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
@@ -475,7 +476,9 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     if (nblk < min_blocks) nblk = min_blocks;
     if (nblk > (total + VG_THREADS - 1) / VG_THREADS) nblk = (total + VG_THREADS - 1) / VG_THREADS;
     const int64_t chunk = (total + nblk - 1) / nblk;
-    vtot_model1_grid_kernel<<<(unsigned)nblk, VG_THREADS, table_bytes(jb) + VG_ROWCAP * 4 * sizeof(double),
+    const size_t vg_smem = table_bytes(jb) + VG_ROWCAP * 4 * sizeof(double);
+    cudaFuncSetAttribute(vtot_model1_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vg_smem);
+    vtot_model1_grid_kernel<<<(unsigned)nblk, VG_THREADS, vg_smem,
                               (cudaStream_t)stream>>>(m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns,
                                                       d_T, nT, d_out, chunk);
     return (int)cudaGetLastError();
@@ -494,11 +497,11 @@ CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable
     case CTB_POT_SPLINE: potential_kernel<PotSpline><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n); break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotModel1Line><<<g, 256, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        potential_kernel<PotModel1Line><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     case CTB_POT_MODEL1F:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotModel1F><<<g, 256, table_bytes(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        potential_kernel<PotModel1F><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     default: return CTB_ERR_UNSUPPORTED;
     }

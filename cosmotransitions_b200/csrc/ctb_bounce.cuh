@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, bounce_min_blocks<Pot, MODE, OC
     extern __shared__ double ctb_smem[];
     JTab jb = a.jb;
     if (!Pot::analytic) {
-        jb = stage_table(a.jb, ctb_smem);
+        jb = stage_table_compact(a.jb, ctb_smem);
         __syncthreads();
     }
     Sfi<Pot, ALPHA> s;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
     extern __shared__ double ctb_smem[];
     JTab jb = a.jb;
     if (!Pot::analytic) {
-        jb = stage_table(a.jb, ctb_smem);
+        jb = stage_table_compact(a.jb, ctb_smem);
         __syncthreads();
     }
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
 template <class Pot>
 int launch_setup_any(const BounceArgs &a, cudaStream_t st)
 {
-    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double);
+    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double);
     setup_kernel<Pot><<<(unsigned)((a.n + 127) / 128), 128, sm, st>>>(a);
     return (int)cudaGetLastError();
 }
@@ -139,7 +139,7 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     if (block < 32 || block > CTB_MAX_BLOCK || (block & 31)) return CTB_ERR_UNSUPPORTED;
     unsigned grid = (unsigned)((a.n + block - 1) / block);
     const bool prof = a.out.d_prof_R != nullptr;
-    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double);
+    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double);
     // split solve (shoot kernel, then save kernel) when the caller provides scratch and all hand-over arrays
     const bool split = a.scratch && !prof && a.out.d_status && a.out.d_r0 && a.out.d_rf && a.out.d_n_shots &&
                        a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
@@ -167,7 +167,7 @@ template <class Pot>
 int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((a.n + 3) / 4);
-    const size_t sm = (Pot::analytic ? 0 : CTB_TABLE_DOUBLES(a.jb.nint) * sizeof(double))
+    const size_t sm = (Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double))
                       + (size_t)4 * 2 * stage_cap * sizeof(double);
     if (sm > 200 * 1024) return CTB_ERR_UNSUPPORTED;
     const bool prof = a.out.d_prof_R != nullptr;

@@ -28,18 +28,37 @@ namespace ctb {
 // ------------------------------------------------------------------------------------------------
 // Jb / Jf spline tables (piecewise cubic, see ctbounce.h)                      FT:167-174,197-204
 struct JTab {
-    const double *brk;  // [nint + 1]; global or (after stage_table) shared memory
-    const double *coef; // [nint * 4]
+    const double *brk;  // [nint + 1] global memory
+    const double *coef; // [nint * 4] global memory
+    const double *rec;  // after stage_table: shared-memory records {brk_j, c0, c1, c2, c3, brk_{j+1}} (48 B each)
     int nint;
     double xmin, xmax;
     float loc_scale, loc_u0, loc_inv_du; // closed-form locator (see ctbounce.h); loc_inv_du == 0: bisection
 };
 
-#define CTB_TABLE_DOUBLES(nint) ((size_t)(nint) * 5 + 2) // brk (nint+1, padded to even) + coef (4 nint)
+#define CTB_TABLE_DOUBLES(nint) ((size_t)(nint) * 6)
 
-// Copies a table into shared memory (whole block cooperates; caller syncs) and returns a JTab that
-// points at the copy.  coef lands 16-byte aligned.
+// Copies a table into shared memory (whole block cooperates; caller syncs) as one 48-byte record per knot
+// interval -- left breakpoint, the four coefficients, right breakpoint -- so that an evaluation touches
+// exactly three 16-byte words: the interval test and the polynomial come from the same record.
 CTB_DEV JTab stage_table(const JTab &g, double *smem)
+{
+    for (int j = threadIdx.x; j < g.nint; j += blockDim.x) {
+        double *r = smem + 6 * j;
+        r[0] = g.brk[j];
+        r[1] = g.coef[4 * j]; r[2] = g.coef[4 * j + 1]; r[3] = g.coef[4 * j + 2]; r[4] = g.coef[4 * j + 3];
+        r[5] = g.brk[j + 1];
+    }
+    JTab t = g;
+    t.rec = smem;
+    return t;
+}
+
+// Compact staging (40 KB: breakpoints, then coefficients) for the bounce / minimiser kernels, which are
+// register- and L1-hungry (local-memory stack of the out-of-line V): every KB of shared memory they do
+// not take stays L1.  (Measured: the 48 KB record layout slows the finite-T bounce kernel by 40 %.)
+#define CTB_TABLE_DOUBLES_COMPACT(nint) ((size_t)(nint) * 5 + 2)
+CTB_DEV JTab stage_table_compact(const JTab &g, double *smem)
 {
     const int nb = (g.nint + 2) & ~1;
     for (int i = threadIdx.x; i < g.nint + 1; i += blockDim.x) smem[i] = g.brk[i];
@@ -47,7 +66,19 @@ CTB_DEV JTab stage_table(const JTab &g, double *smem)
     JTab t = g;
     t.brk = smem;
     t.coef = smem + nb;
+    t.rec = nullptr;
     return t;
+}
+
+CTB_DEV int jtab_guess(const JTab &t, double x)
+{
+    // FP32 guess of the knot interval from the sinh spacing of the reference's sample grid
+    const int last = t.nint - 1;
+    float z = (float)x * t.loc_scale;
+    float a = fabsf(z);
+    float u = copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), z);
+    float kf = floorf((u - t.loc_u0) * t.loc_inv_du) - 1.0f;
+    return (int)fminf(fmaxf(kf, 0.0f), (float)last);
 }
 
 CTB_DEV int jtab_locate(const JTab &t, double x)
@@ -55,12 +86,7 @@ CTB_DEV int jtab_locate(const JTab &t, double x)
     // largest j in [0, nint-1] with brk[j] <= x  (j = 0 below the table: first piece extrapolates)
     const int last = t.nint - 1;
     if (t.loc_inv_du != 0.0f) {
-        // FP32 guess from the sinh spacing of the reference's sample grid, then exact fix-up in FP64
-        float z = (float)x * t.loc_scale;
-        float a = fabsf(z);
-        float u = copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), z);
-        float kf = floorf((u - t.loc_u0) * t.loc_inv_du) - 1.0f;
-        int j = (int)fminf(fmaxf(kf, 0.0f), (float)last);
+        int j = jtab_guess(t, x);
         while (j > 0 && x < t.brk[j]) --j;
         while (j < last && x >= t.brk[j + 1]) ++j;
         return j;
@@ -77,16 +103,31 @@ template <int DER>
 CTB_DEV double jtab_eval(const JTab &t, double theta)
 {
     double x = (theta < t.xmin) ? t.xmin : theta;
-    int j = jtab_locate(t, x);
-    double dx = x - t.brk[j];
-    const double2 c01 = reinterpret_cast<const double2 *>(t.coef)[2 * j];
-    const double2 c23 = reinterpret_cast<const double2 *>(t.coef)[2 * j + 1];
-    struct { double x, y, z, w; } c = {c01.x, c01.y, c23.x, c23.y};
+    double b0, c0, c1, c2, c3;
+    if (t.rec && t.loc_inv_du != 0.0f) { // staged records + closed-form guess: usually one record read
+        const int last = t.nint - 1;
+        int j = jtab_guess(t, x);
+        for (;;) {
+            const double2 *r = reinterpret_cast<const double2 *>(t.rec + 6 * j);
+            const double2 q0 = r[0], q1 = r[1], q2 = r[2];
+            b0 = q0.x; c0 = q0.y; c1 = q1.x; c2 = q1.y; c3 = q2.x;
+            if (x < b0 && j > 0) { --j; continue; }
+            if (x >= q2.y && j < last) { ++j; continue; }
+            break;
+        }
+    } else {
+        const int j = jtab_locate(t, x);
+        b0 = t.brk[j];
+        const double2 c01 = reinterpret_cast<const double2 *>(t.coef)[2 * j];
+        const double2 c23 = reinterpret_cast<const double2 *>(t.coef)[2 * j + 1];
+        c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y;
+    }
+    const double dx = x - b0;
     double v;
-    if (DER == 0) v = c.x + dx * (c.y + dx * (c.z + dx * c.w));
-    else if (DER == 1) v = c.y + dx * (2.0 * c.z + dx * (3.0 * c.w));
-    else if (DER == 2) v = 2.0 * c.z + dx * (6.0 * c.w);
-    else v = 6.0 * c.w;
+    if (DER == 0) v = c0 + dx * (c1 + dx * (c2 + dx * c3));
+    else if (DER == 1) v = c1 + dx * (2.0 * c2 + dx * (3.0 * c3));
+    else if (DER == 2) v = 2.0 * c2 + dx * (6.0 * c3);
+    else v = 6.0 * c3;
     return (theta > t.xmax) ? 0.0 : v;
 }
 

@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(128, 3) bounce_warp_kernel(const BounceArgs a,
     JTab jb = a.jb;
     double *stage = ctb_smem;
     if (!Pot::analytic) {
-        jb = stage_table(a.jb, ctb_smem);
-        stage = ctb_smem + CTB_TABLE_DOUBLES(a.jb.nint);
+        jb = stage_table_compact(a.jb, ctb_smem);
+        stage = ctb_smem + CTB_TABLE_DOUBLES_COMPACT(a.jb.nint);
         __syncthreads();
     }
     const int wib = threadIdx.x >> 5;
