@@ -225,6 +225,35 @@ def test_schedules_agree(ctb):
     assert a["status"][17] == 3 and b["status"][17] == 3
     for k in a:
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+    # split solve (shoot kernel + save kernel) vs the fused single kernel: separate compilations of the same
+    # pinned arithmetic -> identical to the last bit
+    f = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, schedule="natural", kernel="thread", split=False))
+    g = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, schedule="sorted", kernel="thread", split=True))
+    for k in f:
+        assert np.array_equal(f[k], g[k], equal_nan=True), k
+
+
+def test_thermal_split_and_kernels_agree(ctb):
+    """Finite-T functor (FD derivatives, shared-memory Jb table): fused / split / warp kernels."""
+    from cosmotransitions_b200 import _lib, batch, scan
+    rng = np.random.default_rng(3)
+    P = 20
+    lam, Y, n = 0.12 * rng.uniform(.8, 1.2, P), 0.35 * rng.uniform(.8, 1.2, P), 30. * rng.uniform(.8, 1.2, P)
+    sw = scan.model1f_bounce_scan(lam, Y, n, nT=250)          # 5000 instances: work-sorted + split path
+    params = scan.model1f_params(lam[:, None], Y[:, None], n[:, None], sw["T"]).reshape(-1, 6)
+    pa = sw["phi_abs"].reshape(-1)
+    zero = np.zeros(pa.numel())
+    f = _np(batch.find_bounce_batch(_lib.POT_MODEL1F, params, pa, zero, kernel="thread", split=False,
+                                    schedule="natural"))
+    assert np.array_equal(f["status"], sw["status"].reshape(-1).cpu().numpy())
+    assert np.array_equal(f["S"], sw["S"].reshape(-1).cpu().numpy(), equal_nan=True)
+    assert np.array_equal(f["n_rkck"], sw["n_rkck"].reshape(-1).cpu().numpy())
+    sel = slice(0, 5000, 7)
+    w = _np(batch.find_bounce_batch(_lib.POT_MODEL1F, params[sel], pa[sel], zero[sel], kernel="warp"))
+    ok = f["status"][sel] <= 1
+    assert np.array_equal(w["status"], f["status"][sel]) and ok.mean() > 0.9
+    assert np.array_equal(w["n_rkck"][ok], f["n_rkck"][sel][ok])
+    np.testing.assert_allclose(w["S"][ok], f["S"][sel][ok], rtol=1e-10)
 
 
 def test_scalar_api_overrides(ctb):
