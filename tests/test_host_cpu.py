@@ -32,6 +32,30 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.BounceIn) == 8 * 8
 
 
+def test_ctypes_structs_follow_header_field_order():
+    """Field names and order of every ctypes.Structure must equal the typedef in include/ctbounce.h."""
+    from cosmotransitions_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "ctbounce.h")).read()
+
+    def fields(name):
+        m = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", hdr, re.S)
+        body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            parts = decl.split(",")
+            out.append(parts[0].split()[-1].lstrip("*"))
+            out += [q.strip().lstrip("*") for q in parts[1:]]
+        return out
+
+    for cname, cls in (("ctb_jtable", _lib.JTable), ("ctb_opts", _lib.Opts), ("ctb_bounce_in", _lib.BounceIn),
+                       ("ctb_bounce_out", _lib.BounceOut)):
+        assert fields(cname) == [f[0] for f in cls._fields_], cname
+    assert "#define CTB_ABI_VERSION %d" % _lib.ABI_VERSION in hdr
+
+
 def test_bspline_to_pp_matches_scipy():
     from scipy import interpolate
     from cosmotransitions_b200 import _tables
