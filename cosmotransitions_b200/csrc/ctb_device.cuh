@@ -458,18 +458,23 @@ CTB_DEV double fminbound(F func, double x1, double x2, double xatol)
 // scipy.integrate.simpson on a non-uniform grid, as a STREAM: points are fed in order and only the
 // last three are kept.  N (total number of points) must be known up front.   T1D:787 + scipy
 struct SimpsonStream {
-    // (xa, ya): first point of the open pair; (xb, yb): its middle point; (xp, yp): middle point of
-    // the previous pair (needed by the even-N end correction)
+    // General part (unequal spacing, scipy's formula): (xa, ya) first point of the open pair, (xb, yb) its
+    // middle point, (xp, yp) middle point of the previous pair (needed by the even-N end correction).
     double xa, ya, xb, yb, xp, yp;
     double sum;
-    double usum, h_uniform; // pairs on the uniform part of the grid: usum * h/3 (see feed_uniform)
     int idx, nbasic;
+    // Uniform part: on R = linspace(r0, rf, npoints) (T1D:730) consecutive spacings agree to ~1e-13, the
+    // unequal-spacing weights collapse to h/3 (1, 4, 2, 4, ..., 4, 1) and the rule becomes two running sums
+    // over odd / even global indices (one add per point): see begin_uniform / feed_uniform / finish.
+    double s_odd, s_even, y_g0, yb_prev;
+    bool uniform_on;
     CTB_DEV void init(int N)
     {
         sum = 0.0; idx = 0;
-        usum = 0.0; h_uniform = 0.0;
         nbasic = (N & 1) ? N : N - 1; // even N: composite rule on the first N-1 points
         xa = ya = xb = yb = xp = yp = 0.0;
+        s_odd = s_even = y_g0 = yb_prev = 0.0;
+        uniform_on = false;
     }
     static CTB_DEV double pair(double x0, double y0, double x1, double y1, double x2, double y2)
     {
@@ -495,26 +500,33 @@ struct SimpsonStream {
         }
         idx++;
     }
-    // Same as feed() for a point whose pair lies entirely on the uniform part of the grid
-    // (R = linspace(r0, rf, npoints), T1D:730): there h0 = h1 = h up to the rounding of i*step + r0
-    // (|h0/h1 - 1| ~ 1e-13), and the unequal-spacing weights collapse to h/3 (1, 4, 1).
-    CTB_DEV void feed_uniform(double x, double y, double h)
+    // Call right after feed() of the even-index point g0 from which every further pair lies on the uniform grid.
+    CTB_DEV void begin_uniform()
     {
-        if (idx & 1) {
-            xb = x; yb = y;
-        } else {
-            if (idx < nbasic) { usum += (ya + y) + 4.0 * yb; h_uniform = h; xp = xb; yp = yb; }
-            xa = x; ya = y;
-        }
-        idx++;
+        uniform_on = true;
+        s_even = ya; y_g0 = ya; s_odd = 0.0;
     }
-    CTB_DEV double finish(int N) const
+    // Point with global index parity `odd` on the uniform part (no x needed).
+    CTB_DEV void feed_uniform(double y, bool odd)
     {
-        const double total = sum + usum * (h_uniform * (1.0 / 3.0));
-        if (N & 1) return total;
-        if (N == 2) return 0.5 * (xb - xa) * (yb + ya);
-        // points N-3, N-2, N-1 = (xp, yp), (xa, ya), (xb, yb)
-        double h0 = xa - xp, h1 = xb - xa;
+        if (odd) { yb_prev = yb; yb = y; s_odd += y; }
+        else { s_even += y; ya = y; }
+    }
+    // x_m2, x_m1, x_last: abscissae of the last three points (only used for even N); h: uniform spacing
+    CTB_DEV double finish(int N, double h, double x_m2, double x_m1, double x_last) const
+    {
+        if (!uniform_on) return finish_general(N);
+        const bool even = !(N & 1);
+        // even N: the very last point (odd index) is outside the composite rule; it was added to s_odd
+        const double so = even ? s_odd - yb : s_odd;
+        const double total = sum + (h * (1.0 / 3.0)) * (4.0 * so + 2.0 * s_even - y_g0 - ya);
+        if (!even) return total;
+        return total + end_correction(x_m2, yb_prev, x_m1, ya, x_last, yb);
+    }
+    static CTB_DEV double end_correction(double x0, double y0, double x1, double y1, double x2, double y2)
+    {
+        // Cartwright's last-interval correction (scipy.integrate.simpson, even N)
+        double h0 = x1 - x0, h1 = x2 - x1;
         double num, den, al, be, et;
         num = 2 * h1 * h1 + 3 * h0 * h1; den = 6 * (h1 + h0);
         al = (den != 0) ? num / den : 0.0;
@@ -522,7 +534,14 @@ struct SimpsonStream {
         be = (den != 0) ? num / den : 0.0;
         num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1);
         et = (den != 0) ? num / den : 0.0;
-        return total + (al * yb + be * ya - et * yp);
+        return al * y2 + be * y1 - et * y0;
+    }
+    CTB_DEV double finish_general(int N) const
+    {
+        if (N & 1) return sum;
+        if (N == 2) return 0.5 * (xb - xa) * (yb + ya);
+        // points N-3, N-2, N-1 = (xp, yp), (xa, ya), (xb, yb)
+        return sum + end_correction(xp, yp, xa, ya, xb, yb);
     }
 };
 
@@ -899,11 +918,16 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     int N = 0, i_pt = 1, pidx = 0;
     double step = 0.0, di = 1.0, Ri = 0.0, R_first = 0.0, Phi_first = 0.0;
 
-    auto emit = [&](double r, double phi, double dphi, bool uniform) {
+    int g_dense = 0, g0 = 0; // global index of the next dense-output point; start of the uniform Simpson part
+    auto emit = [&](double r, double phi, double dphi, bool dense) {
         double ra = (ALPHA == 2) ? r * r : r * r * r;
         double integrand = (0.5 * (dphi * dphi) + pot.V_quad(phi) - V_meta) * (ra * afac);
-        if (uniform) simp.feed_uniform(r, integrand, step);
-        else simp.feed(r, integrand);
+        if (dense && simp.uniform_on) simp.feed_uniform(integrand, g_dense & 1);
+        else {
+            simp.feed(r, integrand);
+            if (dense && g_dense == g0 && npoints >= 8) simp.begin_uniform();
+        }
+        if (dense) g_dense++;
         if (PROFILE) { sink.R[pidx] = r; sink.Phi[pidx] = phi; sink.dPhi[pidx] = dphi; pidx++; }
     };
     auto fail = [&](int st) { res.status = st; phase = PH_DONE; };
@@ -969,7 +993,9 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                     emit(ri, e.x, e.y, false);
                 }
             }
-            emit(r0, y00, y01, false);
+            g_dense = nint;
+            g0 = (nint & 1) ? nint + 1 : nint; // first even global index on the dense-output grid
+            emit(r0, y00, y01, true);
             i_pt = 1; di = 1.0;
             Ri = Rl1;
         }
@@ -1028,9 +1054,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                         const double inv_dr = rcp_fast(dr);
                         while (i_pt < npoints && r_ < Ri && Ri <= r1) {
                             double t = (Ri - r_) * inv_dr;
-                            // dense-output point i_pt closes / sits inside a pair that started at a
-                            // dense-output point (index >= 0 of the uniform grid) iff i_pt >= 2
-                            emit(Ri, f0(t), f1(t), i_pt >= 2);
+                            emit(Ri, f0(t), f1(t), true);
                             i_pt++;
                             di += 1.0;
                             Ri = (i_pt == npoints - 1) ? rf : __dadd_rn(__dmul_rn(di, step), r0);
@@ -1042,7 +1066,9 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 dr = drnext;
             }
             if (phase == PH_SAVE) { // findAction : T1D:780-791
-                double S = simp.finish(N);
+                const double x_m2 = (npoints >= 3) ? __dadd_rn(__dmul_rn((double)(npoints - 3), step), r0) : r0;
+                const double x_m1 = (npoints >= 2) ? __dadd_rn(__dmul_rn((double)(npoints - 2), step), r0) : r0;
+                double S = simp.finish(N, step, x_m2, x_m1, rf);
                 double Rd = (ALPHA == 2) ? R_first * R_first * R_first : (R_first * R_first) * (R_first * R_first);
                 S += (Rd * vfac) * (pot.V_quad(Phi_first) - V_meta);
                 res.S = S;
