@@ -347,6 +347,10 @@ def main():
         ok = (res["status"] <= 1) & (status[idx] <= 1)
         rel = np.abs(S_gpu[idx][ok] - res["S"][ok]) / np.abs(res["S"][ok])
         line["cpu_baseline"] = {"value": rate, "unit": "bounces/s", "cores": threads, "kind": "port",
+                                "reference_python_note": "the reference itself is pure Python and does not travel to "
+                                                         "the GPU box; measured in the build container (SURVEY.md "
+                                                         "s.6.2): 28.2 bounces/s on 1 core, 221 bounces/s with "
+                                                         "multiprocessing.Pool(8), same quartic family, alpha=2",
                                 "sample": "every %d-th instance of the workload (%d instances), one pass, C oracle "
                                           "with pthreads" % (stride, idx.size)}
         line["parity"] = {"max_rel_err_S_vs_oracle": float(rel.max()) if rel.size else None,

@@ -18,19 +18,33 @@ __global__ void __launch_bounds__(256) jspline_kernel(JTab g, const double *__re
     extern __shared__ double smem[];
     const JTab t = stage_table(g, smem);
     __syncthreads();
+    // vectorised main part: one double2 (16 B) per thread and access, UNROLL independent accesses in flight;
+    // requires 16-byte aligned arrays (the scalar tail loop handles the rest, or everything if unaligned)
     constexpr int UNROLL = 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
-        double x[UNROLL], y[UNROLL];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t done = 0;
+    if ((((uintptr_t)theta | (uintptr_t)out) & 15) == 0) {
+        const double2 *in2 = reinterpret_cast<const double2 *>(theta);
+        double2 *out2 = reinterpret_cast<double2 *>(out);
+        const int64_t n2 = n >> 1;
+        int64_t i = tid;
+        for (; i + (UNROLL - 1) * stride < n2; i += UNROLL * stride) {
+            double2 x[UNROLL], y[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) x[u] = __ldcs(theta + i + u * stride);
+            for (int u = 0; u < UNROLL; u++) x[u] = __ldcs(in2 + i + u * stride);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) y[u] = jtab_eval<DER>(t, x[u]);
+            for (int u = 0; u < UNROLL; u++) { y[u].x = jtab_eval<DER>(t, x[u].x); y[u].y = jtab_eval<DER>(t, x[u].y); }
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) __stcs(out + i + u * stride, y[u]);
+            for (int u = 0; u < UNROLL; u++) __stcs(out2 + i + u * stride, y[u]);
+        }
+        for (; i < n2; i += stride) {
+            const double2 x = in2[i];
+            out2[i] = make_double2(jtab_eval<DER>(t, x.x), jtab_eval<DER>(t, x.y));
+        }
+        done = n2 << 1;
     }
-    for (; i < n; i += stride) out[i] = jtab_eval<DER>(t, theta[i]);
+    for (int64_t i = done + tid; i < n; i += stride) out[i] = jtab_eval<DER>(t, theta[i]);
 }
 
 // ---- Jb / Jf series variants (finiteT.py:207-296) --------------------------------------------------------
