@@ -11,7 +11,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 6
+ABI_VERSION = 7
+V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE = 0, 1, 2, 3
 SPLINE_MAX_PIECES = 255
@@ -89,7 +90,7 @@ def load():
                                 C.c_int64, C.c_void_p]
     lib.ctb_vtot_model1.restype = C.c_int
     lib.ctb_vtot_model1.argtypes = [C.POINTER(C.c_double), C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_int64, C.c_void_p]
+                                    C.c_int64, C.c_int, C.c_void_p]
     lib.ctb_vtot_model1_grid.restype = C.c_int
     lib.ctb_vtot_model1_grid.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(JTable), C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -137,16 +137,20 @@ __global__ void __launch_bounds__(256) jseries_kernel(int deriv, int nterms, Low
 
 struct Model8 { double l1, l2, mu2, Y1, Y2, nb, rs, v2; };
 
-CTB_DEV double model1_thermal(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
+CTB_DEV double model1_v1t(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
 {
     double yt = jtab_eval<0>(jb, f.m0 * inv_T2) + jtab_eval<0>(jb, f.m1 * inv_T2) + nb * jtab_eval<0>(jb, f.mb * inv_T2);
-    return f.V01 + yt * T4c;
+    return yt * T4c;
+}
+CTB_DEV double model1_thermal(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
+{
+    return f.V01 + model1_v1t(f, nb, jb, inv_T2, T4c);
 }
 
-// Vtot(X_i, T_i) pointwise (generic_potential.py:312-337 for model1)
+// Vtot(X_i, T_i) pointwise (generic_potential.py:312-337 for model1); `parts` selects V0 / V1 / V1T
 __global__ void __launch_bounds__(256) vtot_model1_kernel(Model8 m, JTab g, const double *__restrict__ X,
                                                           const double *__restrict__ T, double *__restrict__ out,
-                                                          int64_t n)
+                                                          int64_t n, int parts)
 {
     extern __shared__ double smem[];
     const JTab jb = stage_table(g, smem);
@@ -157,7 +161,17 @@ __global__ void __launch_bounds__(256) vtot_model1_kernel(Model8 m, JTab g, cons
         const double Ti = T[i];
         const Model1Field f = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, x.x, x.y);
         const double T2 = Ti * Ti + 1e-100;
-        out[i] = model1_thermal(f, m.nb, jb, 1.0 / T2, (Ti * Ti * Ti * Ti) / (2 * CTB_PI * CTB_PI));
+        const double v1t = (parts & CTB_V_THERMAL)
+                               ? model1_v1t(f, m.nb, jb, 1.0 / T2, (Ti * Ti * Ti * Ti) / (2 * CTB_PI * CTB_PI)) : 0.0;
+        double v;
+        if (parts == CTB_V_TOTAL) v = f.V01 + v1t;
+        else {
+            v = 0.0;
+            if (parts & CTB_V_TREE) v += f.V0;
+            if (parts & CTB_V_ONELOOP) v += f.V1;
+            v += v1t;
+        }
+        out[i] = v;
     }
 }
 
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(VG_THREADS) vtot_model1_grid_kernel(Model8 m, 
 {
     extern __shared__ double smem[];
     Model1Field *rowc = reinterpret_cast<Model1Field *>(smem);
-    const JTab jb = stage_table(g, smem + VG_ROWCAP * 4);
+    const JTab jb = stage_table(g, smem + VG_ROWCAP * 6);
     const int64_t total = ns * nT;
     const int64_t p0 = (int64_t)blockIdx.x * chunk;
     const int64_t p1 = (p0 + chunk < total) ? p0 + chunk : total;
@@ -466,13 +480,13 @@ CTB_API int ctb_jseries(int which, int approx, int deriv, int nterms, const doub
 }
 
 CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const double *d_X, const double *d_T, double *d_out,
-                    int64_t n, void *stream)
+                            int64_t n, int parts, void *stream)
 {
-    if (!model8 || !jtab_ok(jb) || n < 0) return CTB_ERR_BAD_ARG;
+    if (!model8 || !jtab_ok(jb) || n < 0 || parts < 1 || parts > CTB_V_TOTAL) return CTB_ERR_BAD_ARG;
     if (n == 0) return CTB_OK;
     if (!d_X || !d_T || !d_out) return CTB_ERR_BAD_ARG;
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
-    vtot_model1_kernel<<<grid_for(n, 256), 256, table_bytes(jb), (cudaStream_t)stream>>>(m, to_jtab(jb), d_X, d_T, d_out, n);
+    vtot_model1_kernel<<<grid_for(n, 256), 256, table_bytes(jb), (cudaStream_t)stream>>>(m, to_jtab(jb), d_X, d_T, d_out, n, parts);
     return (int)cudaGetLastError();
 }
 
@@ -490,7 +504,7 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     if (nblk < min_blocks) nblk = min_blocks;
     if (nblk > (total + VG_THREADS - 1) / VG_THREADS) nblk = (total + VG_THREADS - 1) / VG_THREADS;
     const int64_t chunk = (total + nblk - 1) / nblk;
-    const size_t vg_smem = table_bytes(jb) + VG_ROWCAP * 4 * sizeof(double);
+    const size_t vg_smem = table_bytes(jb) + VG_ROWCAP * 6 * sizeof(double);
     cudaFuncSetAttribute(vtot_model1_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vg_smem);
     vtot_model1_grid_kernel<<<(unsigned)nblk, VG_THREADS, vg_smem,
                               (cudaStream_t)stream>>>(m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns,

@@ -216,7 +216,7 @@ struct PotSpline {
 
 // Field-dependent part of model1's Vtot: the three boson masses (examples/testModel1.py:89-93) and
 // V0 + V1 (examples/testModel1.py:78-80, GP:240-256).  Independent of T.
-struct Model1Field { double m0, m1, mb, V01; };
+struct Model1Field { double m0, m1, mb, V01, V0, V1; };
 CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, double Y2, double nb, double rs, double v2,
                                  double phi1, double phi2)
 {
@@ -234,7 +234,9 @@ CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, do
     y1 += 1.0 * f.m0 * f.m0 * (log(fabs(f.m0 * inv_rs) + 1e-100) - 1.5);
     y1 += 1.0 * f.m1 * f.m1 * (log(fabs(f.m1 * inv_rs) + 1e-100) - 1.5);
     y1 += nb * f.mb * f.mb * (log(fabs(f.mb * inv_rs) + 1e-100) - 1.5);
-    f.V01 = r + y1 * (1.0 / (64 * CTB_PI * CTB_PI));
+    f.V0 = r;
+    f.V1 = y1 * (1.0 / (64 * CTB_PI * CTB_PI));
+    f.V01 = r + f.V1;
     return f;
 }
 

@@ -23,6 +23,19 @@ class model1:
         """Total finite-temperature effective potential; X[..., 2] and T broadcast as in the
         reference (generic_potential.py:318-324).  model1 sets no num_boson_dof, so
         include_radiation changes nothing (generic_potential.py:289-295)."""
+        return self._eval(X, T, _lib.V_TOTAL)
+
+    def V1T_from_X(self, X, T, include_radiation=True):
+        """One-loop finite-temperature part alone (generic_potential.py:298-310)."""
+        return self._eval(X, T, _lib.V_THERMAL)
+
+    def DVtot(self, X, T):
+        """Vtot offset such that V(0, T) = 0 (generic_potential.py:339-345)."""
+        torch = _lib.require_cuda()
+        X0 = np.zeros(self.Ndim)
+        return self._eval(X, T, _lib.V_TOTAL) - self._eval(X0, T, _lib.V_TOTAL)
+
+    def _eval(self, X, T, parts):
         torch = _lib.require_cuda()
         lib = _lib.load()
         is_tensor = isinstance(X, torch.Tensor)
@@ -37,7 +50,7 @@ class model1:
         tabs = _tables.device_tables(dev)
         with torch.cuda.device(dev):
             _lib.check(lib.ctb_vtot_model1(self._m8, tabs.jb, Xf.data_ptr(), Tf.data_ptr(), out.data_ptr(), Tf.numel(),
-                                           torch.cuda.current_stream(dev).cuda_stream), "ctb_vtot_model1")
+                                           parts, torch.cuda.current_stream(dev).cuda_stream), "ctb_vtot_model1")
         out = out.reshape(shape)
         if is_tensor:
             return out if X.is_cuda else out.cpu()

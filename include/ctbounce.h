@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 6
+#define CTB_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -197,8 +197,14 @@ CTB_API int ctb_jseries(int which, int approx, int deriv, int nterms, const doub
 
 /* generic_potential.Vtot (generic_potential.py:312-337) for model1 (examples/testModel1.py:62-116):
  * pointwise, d_X [n,2], d_T [n] -> d_out [n].  model[8] = l1,l2,mu2,Y1,Y2,n_boson,renormScaleSq,v2 (host). */
+/* parts: CTB_V_TOTAL for Vtot, CTB_V_THERMAL alone for generic_potential.V1T_from_X
+ * (generic_potential.py:298-310); any OR of the three pieces is allowed. */
+#define CTB_V_TREE 1      /* V0   examples/testModel1.py:62-80        */
+#define CTB_V_ONELOOP 2   /* V1   generic_potential.py:240-256        */
+#define CTB_V_THERMAL 4   /* V1T  generic_potential.py:258-296        */
+#define CTB_V_TOTAL 7
 CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const double *d_X, const double *d_T,
-                    double *d_out, int64_t n, void *stream);
+                            double *d_out, int64_t n, int parts, void *stream);
 
 /* Same on the outer-product grid X_i = x0 + s_i * nhat, T_j:  d_out[i * nT + j]  (row-major [ns, nT]).
  * line4 = x0[0], x0[1], nhat[0], nhat[1] (host). */

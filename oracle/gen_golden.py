@@ -329,6 +329,8 @@ def gen_model1():
     Xs = rng.uniform(-400, 400, (300, 2))
     Ts = rng.uniform(0, 300, 300)
     out["pts_X"], out["pts_T"], out["pts_V"] = Xs, Ts, m.Vtot(Xs, Ts)
+    out["pts_V1T"] = m.V1T_from_X(Xs, Ts)           # generic_potential.py:298-310
+    out["pts_DV"] = m.DVtot(Xs, Ts)                  # generic_potential.py:339-345
     # finite-T bounces along the straight line between the two phases' minima at each T
     bT, bxl, bxh, res = [], [], [], []
     xl, xh = x_low.copy(), x_high.copy()

@@ -375,6 +375,9 @@ def test_model1_vtot_golden(ctb, gold_dir):
     np.testing.assert_allclose(V, ref, rtol=1e-11, atol=1e-13 * scale)
     Vp = m.Vtot(g["pts_X"], g["pts_T"])
     np.testing.assert_allclose(Vp, g["pts_V"], rtol=1e-11, atol=1e-13 * scale)
+    np.testing.assert_allclose(m.V1T_from_X(g["pts_X"], g["pts_T"]), g["pts_V1T"], rtol=1e-11,
+                               atol=1e-13 * np.max(np.abs(g["pts_V1T"])))
+    np.testing.assert_allclose(m.DVtot(g["pts_X"], g["pts_T"]), g["pts_DV"], rtol=1e-9, atol=1e-12 * scale)
     # broadcasting contract of Vtot (generic_potential.py:318-324)
     X = g["grid_x0"][None, :] + g["grid_s"][:, None] * g["grid_nhat"][None, :]
     Vb = m.Vtot(X[:, None, :], g["grid_T"][None, :])
