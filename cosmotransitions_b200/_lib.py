@@ -11,12 +11,13 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 7
+ABI_VERSION = 8
 V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
-POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE = 0, 1, 2, 3
+POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE, POT_THERMAL1F = 0, 1, 2, 3, 4
 SPLINE_MAX_PIECES = 255
-NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280}
+THERMAL_KINDS = (POT_MODEL1_LINE, POT_MODEL1F, POT_THERMAL1F)   # need the Jb / Jf tables
+NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, POT_THERMAL1F: 64}
 (ST_CONVERGED, ST_XTOL, ST_STABLE, ST_NO_BARRIER, ST_RMAX, ST_DRMIN, ST_STEP_UNDERFLOW, ST_NONFINITE,
  ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN) = range(11)
 

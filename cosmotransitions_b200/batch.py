@@ -92,7 +92,7 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
     lib = _lib.load()
     n = d_phi_abs.numel()
     dev = d_phi_abs.device
-    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
     jb, jf = (tabs.jb, tabs.jf) if tabs else (None, None)
     bo = _bounce_out(out, profiles)
     st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
@@ -130,7 +130,7 @@ def bounce_setup(kind, params, phi_absMin, phi_metaMin, phi_bar=None, rscale=Non
     d_bar = _as_device(torch, [phi_bar], dev, (n,)) if phi_bar is not None else None
     d_rs = _as_device(torch, [rscale], dev, (n,)) if rscale is not None else None
     out = alloc_out(torch, n, dev)
-    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
     _lib.check(lib.ctb_bounce_setup(kind, _bounce_in(d_params, d_abs, d_meta, d_bar, d_rs),
                                     tabs.jb if tabs else None, tabs.jf if tabs else None, _bounce_out(out), None,
                                     torch.cuda.current_stream(dev).cuda_stream), "ctb_bounce_setup")

@@ -301,6 +301,11 @@ int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, cons
     case CTB_POT_SPLINE:
         rows_kernel<PotSpline, MINIMIZE><<<g, 128, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b, xtol_rel, o0, o1, n);
         break;
+    case CTB_POT_THERMAL1F:
+        if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
+        rows_kernel<PotThermal1F, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+                                                                            xtol_rel, o0, o1, n);
+        break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
         rows_kernel<PotModel1Line, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
@@ -397,6 +402,7 @@ CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_op
     if (o->kernel == CTB_KERNEL_AUTO) warp = a.n < 4096 && stage_cap <= 2048;
     if (o->kernel < 0 || o->kernel > 2 || (warp && stage_cap > 2048)) return CTB_ERR_UNSUPPORTED;
     if ((pot_kind == CTB_POT_MODEL1_LINE || pot_kind == CTB_POT_MODEL1F) && !jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+    if (pot_kind == CTB_POT_THERMAL1F && !(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
     switch (pot_kind) {
     case CTB_POT_POLY4:
         return warp ? ctb::launch_bounce_warp_poly4(a, o->alpha, stage_cap, st)
@@ -404,6 +410,9 @@ CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_op
     case CTB_POT_SPLINE:
         return warp ? ctb::launch_bounce_warp_spline(a, o->alpha, stage_cap, st)
                     : ctb::launch_bounce_spline(a, o->alpha, block, st);
+    case CTB_POT_THERMAL1F:
+        return warp ? ctb::launch_bounce_warp_thermal1f(a, o->alpha, stage_cap, st)
+                    : ctb::launch_bounce_thermal1f(a, o->alpha, block, st);
     case CTB_POT_MODEL1_LINE:
         return warp ? ctb::launch_bounce_warp_model1_line(a, o->alpha, stage_cap, st)
                     : ctb::launch_bounce_model1_line(a, o->alpha, block, st);
@@ -427,6 +436,9 @@ CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jt
     switch (pot_kind) {
     case CTB_POT_POLY4: return ctb::launch_setup_poly4(a, st);
     case CTB_POT_SPLINE: return ctb::launch_setup_spline(a, st);
+    case CTB_POT_THERMAL1F:
+        if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
+        return ctb::launch_setup_thermal1f(a, st);
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
         return ctb::launch_setup_model1_line(a, st);
@@ -523,6 +535,10 @@ CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable
     switch (pot_kind) {
     case CTB_POT_POLY4: potential_kernel<PotPoly4><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n); break;
     case CTB_POT_SPLINE: potential_kernel<PotSpline><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n); break;
+    case CTB_POT_THERMAL1F:
+        if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
+        potential_kernel<PotThermal1F><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
         potential_kernel<PotModel1Line><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);

@@ -185,6 +185,9 @@ int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaSt
     return (int)cudaGetLastError();
 }
 
+int launch_bounce_thermal1f(const BounceArgs &a, int alpha, int block, cudaStream_t st);
+int launch_setup_thermal1f(const BounceArgs &a, cudaStream_t st);
+int launch_bounce_warp_thermal1f(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);
 int launch_bounce_spline(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_setup_spline(const BounceArgs &a, cudaStream_t st);
 int launch_bounce_warp_spline(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);

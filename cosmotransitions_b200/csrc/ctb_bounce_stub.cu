@@ -11,4 +11,7 @@ int launch_bounce_warp_model1f(const BounceArgs &, int, int, cudaStream_t) { ret
 int launch_bounce_spline(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
 int launch_setup_spline(const BounceArgs &, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
 int launch_bounce_warp_spline(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_bounce_thermal1f(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_setup_thermal1f(const BounceArgs &, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
+int launch_bounce_warp_thermal1f(const BounceArgs &, int, int, cudaStream_t) { return CTB_ERR_UNSUPPORTED; }
 } // namespace ctb

@@ -1,0 +1,14 @@
+// bounce kernel instantiation for the PotThermal1F potential functor (see ctb_bounce.cuh)
+#include "ctb_bounce.cuh"
+
+namespace ctb {
+int launch_bounce_thermal1f(const BounceArgs &a, int alpha, int block, cudaStream_t st)
+{
+    return launch_bounce_any<PotThermal1F>(a, alpha, block, st);
+}
+int launch_setup_thermal1f(const BounceArgs &a, cudaStream_t st) { return launch_setup_any<PotThermal1F>(a, st); }
+int launch_bounce_warp_thermal1f(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st)
+{
+    return launch_bounce_warp_any<PotThermal1F>(a, alpha, stage_cap, st);
+}
+} // namespace ctb

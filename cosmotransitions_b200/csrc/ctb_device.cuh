@@ -299,6 +299,51 @@ struct PotModel1F {
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
 
+// General one-field thermal potential (CTB_POT_THERMAL1F, layout in ctbounce.h).  The parameter row stays
+// in global memory (L1-resident, 512 B per instance); V is one out-of-line function.
+struct PotThermal1F {
+    static constexpr bool analytic = false;
+    static constexpr int min_blocks = CTB_THERMAL_MIN_BLOCKS;
+    static constexpr int nparam = CTB_NPARAM_THERMAL1F;
+    const double *p;
+    double inv_rs, T2, inv_T2, T4c;
+    int nb, nf;
+    JTab jb, jf;
+    CTB_DEV void load(const double *p_, const JTab *jb_, const JTab *jf_)
+    {
+        p = p_;
+        const double T = p[6];
+        inv_rs = 1.0 / p[5];
+        T2 = T * T;
+        inv_T2 = 1.0 / (T2 + 1e-100);
+        T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
+        nb = min(max((int)p[7], 0), CTB_THERMAL1F_MAX_BOSONS);
+        nf = min(max((int)p[8], 0), CTB_THERMAL1F_MAX_FERMIONS);
+        jb = *jb_;
+        jf = *jf_;
+    }
+    __device__ __noinline__ double V(double phi) const
+    {
+        const double p2 = phi * phi;
+        double r = __ldg(p) + phi * (__ldg(p + 1) + phi * (__ldg(p + 2) + phi * (__ldg(p + 3) + phi * __ldg(p + 4))));
+        double y1 = 0.0, yt = 0.0;
+        for (int i = 0; i < nb; i++) { // GP:249-251, 285-286
+            const double *q = p + 9 + 5 * i;
+            const double m2 = __ldg(q) + __ldg(q + 1) * p2 + __ldg(q + 2) * T2, dof = __ldg(q + 3);
+            y1 += dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - __ldg(q + 4));
+            yt += dof * jtab_eval<0>(jb, m2 * inv_T2);
+        }
+        for (int j = 0; j < nf; j++) { // GP:252-255, 287-288
+            const double *q = p + 49 + 3 * j;
+            const double m2 = __ldg(q) + __ldg(q + 1) * p2, dof = __ldg(q + 2);
+            y1 -= dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - 1.5);
+            yt += dof * jtab_eval<0>(jf, m2 * inv_T2);
+        }
+        return r + y1 * (1.0 / (64 * CTB_PI * CTB_PI)) + yt * T4c;
+    }
+    CTB_DEV double V_quad(double phi) const { return V(phi); }
+};
+
 // ------------------------------------------------------------------------------------------------
 // small helpers
 CTB_DEV double sgn(double x) { return (double)((x > 0) - (x < 0)); }

@@ -90,6 +90,36 @@ class SplinePotential(DevicePotential):
         return cls(tck) if tck is not None else None
 
 
+def thermal1f_params(V0_coefs, renormScaleSq, T, bosons=(), fermions=()):
+    """Rows of CTB_POT_THERMAL1F (include/ctbounce.h): a one-field generic_potential with
+    V0 = sum_k V0_coefs[k] phi^k (k <= 4), bosons = [(a, b, t, dof, c), ...] with m^2 = a + b phi^2 + t T^2,
+    fermions = [(a, b, dof), ...] with m^2 = a + b phi^2.  T may be an array: one row per temperature."""
+    T = np.atleast_1d(np.asarray(T, dtype=np.float64))
+    if len(bosons) > 8 or len(fermions) > 4:
+        raise ValueError("at most 8 bosons and 4 fermions")
+    row = np.zeros(_lib.NPARAM[_lib.POT_THERMAL1F])
+    c = np.zeros(5)
+    c[:len(V0_coefs)] = V0_coefs
+    row[0:5] = c
+    row[5], row[7], row[8] = renormScaleSq, len(bosons), len(fermions)
+    for i, b in enumerate(bosons):
+        row[9 + 5 * i:14 + 5 * i] = b
+    for j, f in enumerate(fermions):
+        row[49 + 3 * j:52 + 3 * j] = f
+    rows = np.tile(row, (T.size, 1))
+    rows[:, 6] = T
+    return rows
+
+
+class Thermal1FPotential(DevicePotential):
+    """General one-field thermal potential (see thermal1f_params) at one temperature."""
+    kind = _lib.POT_THERMAL1F
+    needs_tables = True
+
+    def __init__(self, V0_coefs, renormScaleSq, T, bosons=(), fermions=()):
+        super().__init__(thermal1f_params(V0_coefs, renormScaleSq, T, bosons, fermions)[0])
+
+
 def model1_model8(m1=120., m2=50., mu=25., Y1=.1, Y2=.15, n=30, v2=246. ** 2):
     """(l1, l2, mu2, Y1, Y2, n, renormScaleSq, v2) of examples/testModel1.py:19-47."""
     return np.array([.5 * m1 ** 2 / v2, .5 * m2 ** 2 / v2, mu ** 2, Y1, Y2, float(n), v2, v2])

@@ -24,7 +24,7 @@ def potential_batch(kind, params, phi):
     lib = _lib.load()
     dev, p, n, (ph,) = _prep(torch, kind, params, phi)
     out = torch.empty(n, dtype=torch.float64, device=dev)
-    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
     with torch.cuda.device(dev):
         _lib.check(lib.ctb_potential_batch(kind, p.data_ptr(), tabs.jb if tabs else None, tabs.jf if tabs else None,
                                            ph.data_ptr(), out.data_ptr(), n,
@@ -40,7 +40,7 @@ def minimize_1d(kind, params, lo, hi, xtol_rel=1e-10):
     dev, p, n, (a, b) = _prep(torch, kind, params, lo, hi)
     x = torch.empty(n, dtype=torch.float64, device=dev)
     v = torch.empty(n, dtype=torch.float64, device=dev)
-    tabs = _tables.device_tables(dev) if kind != _lib.POT_POLY4 else None
+    tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
     with torch.cuda.device(dev):
         _lib.check(lib.ctb_minimize_1d(kind, p.data_ptr(), tabs.jb if tabs else None, tabs.jf if tabs else None,
                                        a.data_ptr(), b.data_ptr(), float(xtol_rel), n, x.data_ptr(), v.data_ptr(),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 7
+#define CTB_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -73,7 +73,18 @@ extern "C" {
 #define CTB_POT_SPLINE 3
 #define CTB_SPLINE_MAX_PIECES 255
 
+/* General one-field generic_potential (generic_potential.py:132-337): quartic tree-level potential plus up
+ * to 8 bosons and 4 fermions with field-dependent masses m^2 = a + b phi^2 (+ t T^2 for bosons), Vtot = V0 + V1
+ * + V1T with Jb for bosons and Jf for fermions; dV, d2V by the 5-point stencils.  params[64] =
+ *   c0..c4 (V0 = sum c_k phi^k), renormScaleSq, T, n_bosons, n_fermions,
+ *   bosons  8 x {a, b, t, dof, c}   (params[9 + 5 i ...]),
+ *   fermions 4 x {a, b, dof}        (params[49 + 3 j ...]),  3 unused.                                      */
+#define CTB_POT_THERMAL1F 4
+#define CTB_THERMAL1F_MAX_BOSONS 8
+#define CTB_THERMAL1F_MAX_FERMIONS 4
+
 #define CTB_NPARAM_POLY4 5
+#define CTB_NPARAM_THERMAL1F 64
 #define CTB_NPARAM_SPLINE 1280
 #define CTB_NPARAM_MODEL1_LINE 13
 #define CTB_NPARAM_MODEL1F 6

@@ -66,7 +66,7 @@ enum {
 enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
 
 /* potential kinds */
-enum { POT_POLY4 = 0, POT_MODEL1_LINE = 1, POT_MODEL1F = 2, POT_SPLINE = 3 };
+enum { POT_POLY4 = 0, POT_MODEL1_LINE = 1, POT_MODEL1F = 2, POT_SPLINE = 3, POT_THERMAL1F = 4 };
 
 typedef struct {
     int n;           /* number of knots  */
@@ -228,6 +228,31 @@ static double vtot_model1f(const double *p, const spline_t *jb, double phi, doub
     return r;
 }
 
+/* General one-field generic_potential (generic_potential.py:240-337): quartic V0, bosons with
+ * m^2 = a + b phi^2 + t T^2 (dof, c), fermions with m^2 = a + b phi^2 (dof).
+ * p = [c0..c4, renormScaleSq, T, nb, nf, 8 x {a,b,t,dof,c}, 4 x {a,b,dof}, pad]                       */
+static double vtot_thermal1f(const double *p, const spline_t *jb, const spline_t *jf, double phi)
+{
+    double rs = p[5], T = p[6];
+    int nb = (int)p[7], nf = (int)p[8];
+    double r = p[0] + phi * (p[1] + phi * (p[2] + phi * (p[3] + phi * p[4])));
+    double T2 = T * T + 1e-100, T4 = T * T * T * T;
+    double y1 = 0.0, yt = 0.0;
+    for (int i = 0; i < nb; i++) {
+        const double *q = p + 9 + 5 * i;
+        double m2 = q[0] + q[1] * phi * phi + q[2] * T * T;
+        y1 += q[3] * m2 * m2 * (log(fabs(m2 / rs) + 1e-100) - q[4]);
+        yt += q[3] * J_spline(jb, m2 / T2, 0);
+    }
+    for (int j = 0; j < nf; j++) {
+        const double *q = p + 49 + 3 * j;
+        double m2 = q[0] + q[1] * phi * phi;
+        y1 -= q[2] * m2 * m2 * (log(fabs(m2 / rs) + 1e-100) - 1.5);
+        yt += q[2] * J_spline(jf, m2 / T2, 0);
+    }
+    return r + y1 / (64 * M_PI * M_PI) + yt * T4 / (2 * M_PI * M_PI);
+}
+
 static double pot_V(const pot_t *P, double phi)
 {
     const double *p = P->p;
@@ -238,6 +263,8 @@ static double pot_V(const pot_t *P, double phi)
         return vtot_model1(p, P->jb, p[9] + phi * p[11], p[10] + phi * p[12], p[8]);
     case POT_MODEL1F:
         return vtot_model1f(p, P->jb, phi, p[5]);
+    case POT_THERMAL1F:
+        return vtot_thermal1f(p, P->jb, P->jf, phi);
     case POT_SPLINE: { /* pathDeformation.SplinePath.V: splev(x, tck); p = [n, t[n], c[n]] */
         spline_t s = {(int)p[0], 3, p + 1, p + 1 + (int)p[0], 0, 0};
         return splev(&s, phi, 0);

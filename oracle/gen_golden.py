@@ -16,6 +16,7 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
   tests/golden/units.npz        exactSolution / rkqs unit vectors
   tests/golden/model1.npz       generic_potential.Vtot for examples/testModel1.py + finite-T bounces
   tests/golden/model1f.json     one-field thermal model sweep
+  tests/golden/thermal1f.json   general one-field generic_potential (bosons + fermions, Jb and Jf): Vtot, bounces
   tests/golden/splinepath.npz   every 1-D solve inside pathDeformation.fullTunneling (examples/fullTunneling.py,
                                 model1.findAllTransitions): the SplinePath potential spline, profile, action
   tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
@@ -349,6 +350,77 @@ def gen_model1():
     np.savez(os.path.join(GOLD, "model1.npz"), **out)
 
 
+class SMlike(gp.generic_potential):
+    """One-field model with the particle content layout of CTB_POT_THERMAL1F: a Higgs-like field with gauge
+    bosons, Goldstones, a heavy portal scalar multiplet with a thermal mass, and a top-like fermion -- written
+    against the real generic_potential so that V1 / V1T / Jb_spline / Jf_spline are the reference's own code."""
+    v2 = 246. ** 2
+
+    def init(self, lam=0.13, g2=0.42, gz2=0.55, yt2=0.98, Yp=0.9, np_=12., tp=0.15):
+        self.Ndim = 1
+        self.renormScaleSq = self.v2
+        self.lam, self.g2, self.gz2, self.yt2, self.Yp, self.np_, self.tp = lam, g2, gz2, yt2, Yp, np_, tp
+        self.mu2 = lam * self.v2
+
+    def V0(self, X):
+        phi = np.asanyarray(X)[..., 0]
+        return -.5 * self.mu2 * phi ** 2 + .25 * self.lam * phi ** 4
+
+    def bosons_spec(self):   # (a, b, t, dof, c)
+        return [(-self.mu2, 3 * self.lam, 0.0, 1., 1.5), (-self.mu2, self.lam, 0.0, 3., 1.5),
+                (0.0, self.g2 / 4, 0.0, 6., 5. / 6), (0.0, self.gz2 / 4, 0.0, 3., 5. / 6),
+                (0.0, self.Yp, self.tp, self.np_, 1.5)]
+
+    def fermions_spec(self):  # (a, b, dof)
+        return [(0.0, self.yt2 / 2, 12.)]
+
+    def boson_massSq(self, X, T):
+        phi = np.asanyarray(X)[..., 0]
+        T = np.asanyarray(T, dtype=float)
+        spec = self.bosons_spec()
+        M = np.array([a + b * phi * phi + t * T * T for (a, b, t, n, c) in spec])
+        M = np.rollaxis(M, 0, len(M.shape))
+        return M, np.array([s_[3] for s_ in spec]), np.array([s_[4] for s_ in spec])
+
+    def fermion_massSq(self, X):
+        phi = np.asanyarray(X)[..., 0]
+        spec = self.fermions_spec()
+        M = np.array([a + b * phi * phi for (a, b, n) in spec])
+        M = np.rollaxis(M, 0, len(M.shape))
+        return M, np.array([s_[2] for s_ in spec])
+
+
+def gen_thermal1f():
+    from scipy import optimize
+    m = SMlike()
+    V = lambda phi, T: m.Vtot(np.asarray(phi, dtype=float)[..., None], T)
+    rng = np.random.default_rng(31)
+    phis, Ts = rng.uniform(-50, 400, 400), rng.uniform(0, 250, 400)
+    out = dict(V0_coefs=[0.0, 0.0, -.5 * m.mu2, 0.0, .25 * m.lam], renorm=m.renormScaleSq, bosons=m.bosons_spec(),
+               fermions=m.fermions_spec(), pts_phi=phis.tolist(), pts_T=Ts.tolist(),
+               pts_V=[float(V(p_, t_)) for p_, t_ in zip(phis, Ts)])
+    # temperature window: phi = 0 metastable, broken minimum deeper
+    def curv0(T):
+        return float(V(0.5, T) - V(0.0, T))
+    def broken_min(T):
+        return float(optimize.minimize_scalar(lambda p: float(V(p, T)), bounds=(30, 500), method="bounded",
+                                              options=dict(xatol=1e-10)).x)
+    T0 = optimize.brentq(curv0, 5, 400)
+    Tc = optimize.brentq(lambda T: float(V(broken_min(T), T) - V(0.0, T)), T0 + 0.2, 400)
+    out.update(T0=float(T0), Tc=float(Tc))
+    cases = []
+    for frac in (0.2, 0.5, 0.75, 0.92):
+        T = T0 + frac * (Tc - T0)
+        pa = broken_min(T)
+        r = run_case(lambda phi, T=T: V(phi, T), None, None, pa, 0.0, 2)
+        r.update(T=float(T), phi_abs=pa)
+        cases.append(r)
+        print("thermal1f T=%.3f" % T, {q: r.get(q) for q in ("S", "npts", "n_shots", "n_rkck", "error")})
+    out["bounces"] = cases
+    with open(os.path.join(GOLD, "thermal1f.json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
 def gen_splinepath():
     """The reference's OWN multi-field flow: pathDeformation.fullTunneling on examples/fullTunneling.py
     (BASELINE.json configs[0]) and model1.findAllTransitions().  Every time fullTunneling instantiates the
@@ -472,7 +544,7 @@ def gen_model1f():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "splinepath"]
+                               "thermal1f", "splinepath"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

@@ -12,8 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libctb_oracle.so")
 
-POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE = 0, 1, 2, 3
-NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: None}  # spline: 1 + 2 n_knots
+POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE, POT_THERMAL1F = 0, 1, 2, 3, 4
+NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: None, POT_THERMAL1F: 64}  # spline: 1 + 2 n_knots
 
 STATUS_NAMES = {
     0: "converged", 1: "xtol", 2: "stable, not metastable", 3: "no barrier", 4: "r > rmax",

@@ -533,6 +533,34 @@ def test_random_affine_quartics_vs_oracle(ctb, oracle, alpha):
     assert (g["n_shots"][ok] != o["n_shots"][ok]).mean() < 1e-2
 
 
+def test_thermal1f_general_model(ctb, oracle, tables, gold_dir):
+    """General one-field thermal functor (bosons with thermal masses + a fermion: Jb and Jf tables) against
+    the reference's generic_potential.Vtot and SingleFieldInstanton on the same model."""
+    from cosmotransitions_b200 import _lib, batch, potentials, scan, tunneling1D as t1
+    g = json.load(open(os.path.join(gold_dir, "thermal1f.json")))
+    rows = potentials.thermal1f_params(g["V0_coefs"], g["renorm"], g["pts_T"], g["bosons"], g["fermions"])
+    V = scan.potential_batch(_lib.POT_THERMAL1F, rows, g["pts_phi"]).cpu().numpy()
+    np.testing.assert_allclose(V, g["pts_V"], rtol=1e-11, atol=1e-3)
+    Ts = [c["T"] for c in g["bounces"]]
+    rows = potentials.thermal1f_params(g["V0_coefs"], g["renorm"], Ts, g["bosons"], g["fermions"])
+    pa = np.array([c["phi_abs"] for c in g["bounces"]])
+    S_ref = np.array([c["S"] for c in g["bounces"]])
+    for kern in ("thread", "warp"):
+        r = _np(batch.find_bounce_batch(_lib.POT_THERMAL1F, rows, pa, 0.0, kernel=kern))
+        assert (r["status"] <= 1).all()
+        rel = np.abs(r["S"] - S_ref) / S_ref
+        print(kern, "thermal1f max rel vs reference", rel.max())
+        assert rel.max() < S_RTOL
+        assert np.array_equal(r["n_points"], [c["npts"] for c in g["bounces"]])
+        assert np.array_equal(r["n_shots"], [c["n_shots"] for c in g["bounces"]])
+    # device-side phi_absMin(T) and the scalar class on the functor object
+    x, _ = scan.minimize_1d(_lib.POT_THERMAL1F, rows, np.full(len(Ts), 30.0), np.full(len(Ts), 500.0))
+    np.testing.assert_allclose(x.cpu().numpy(), pa, rtol=0, atol=2e-4)
+    pot = potentials.Thermal1FPotential(g["V0_coefs"], g["renorm"], Ts[1], g["bosons"], g["fermions"])
+    inst = t1.SingleFieldInstanton(pa[1], 0.0, pot)
+    assert abs(inst.findAction(inst.findProfile()) - S_ref[1]) < S_RTOL * S_ref[1]
+
+
 def test_c3_full_size_subsample_vs_oracle(ctb, oracle):
     """BASELINE.json config C3 at full size (1e6 quartic instances, alpha=3) through the production path
     (work-sorted, split solve); every 500th instance is checked against the CPU oracle."""

@@ -213,3 +213,23 @@ def test_splinepath_solves(oracle, gold_dir):
         assert len(r["R"]) == len(g["R%d" % i])
         np.testing.assert_allclose(r["Phi"], g["Phi%d" % i], rtol=0, atol=1e-9 * abs(pm - pa))
     print("splinepath worst rel err", worst)
+
+
+def _thermal1f_rows(g, T):
+    sys_path_hack = None
+    from cosmotransitions_b200 import potentials
+    return potentials.thermal1f_params(g["V0_coefs"], g["renorm"], T, g["bosons"], g["fermions"])
+
+
+def test_thermal1f_general_model(oracle, tables, gold_dir):
+    """General one-field generic_potential (5 bosons incl. a thermal mass, 1 fermion -> Jb AND Jf)."""
+    g = json.load(open(os.path.join(gold_dir, "thermal1f.json")))
+    cfg = oracle.make_config(kind=oracle.POT_THERMAL1F, tables=tables)
+    rows = _thermal1f_rows(g, g["pts_T"])
+    V = oracle.potential_rows(cfg, rows, g["pts_phi"])
+    np.testing.assert_allclose(V, g["pts_V"], rtol=1e-12, atol=1e-4)
+    for c in g["bounces"]:
+        r = oracle.bounce_one(cfg, _thermal1f_rows(g, c["T"])[0], c["phi_abs"], 0.0)
+        assert c["error"] is None and r["status"] in (0, 1)
+        assert abs(r["S"] - c["S"]) < 1e-6 * abs(c["S"]), (c["T"], r["S"], c["S"])
+        assert r["n_points"] == c["npts"] and r["n_shots"] == c["n_shots"]
