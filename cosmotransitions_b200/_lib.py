@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 8
+ABI_VERSION = 9
 V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE, POT_THERMAL1F = 0, 1, 2, 3, 4
@@ -22,7 +22,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
  ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN) = range(11)
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
-           "ctb_bounce_setup", "ctb_potential_batch", "ctb_minimize_1d",
+           "ctb_bounce_setup", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
            "ctb_jspline", "ctb_jseries", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
 
 
@@ -104,6 +104,10 @@ def load():
     lib.ctb_minimize_1d.restype = C.c_int
     lib.ctb_minimize_1d.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                     C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ctb_find_action.restype = C.c_int
+    lib.ctb_find_action.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
+                                    C.c_void_p]
     lib.ctb_fp64_peak.restype = C.c_int
     lib.ctb_fp64_peak.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     if lib.ctb_abi_version() != ABI_VERSION:

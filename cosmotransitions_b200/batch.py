@@ -22,8 +22,9 @@ def make_opts(alpha=2, phi_eps=1e-3, block_threads=0, kernel="auto", **knobs):
         if k not in kw:
             raise TypeError("unexpected findProfile argument %r" % k)
         kw[k] = v
-    if alpha not in (2, 3):
-        raise NotImplementedError("alpha must be 2 or 3 (nu = 1/2 or 1 Bessel start)")
+    if alpha not in (1, 2, 3, 4):
+        raise NotImplementedError("alpha must be 1, 2, 3 or 4 (d = alpha + 1 dimensions; Bessel start of order "
+                                  "nu = (alpha - 1)/2 = 0, 1/2, 1, 3/2)")
     o = _lib.Opts()
     o.xtol, o.phitol, o.thinCutoff, o.rmin, o.rmax = kw["xtol"], kw["phitol"], kw["thinCutoff"], kw["rmin"], kw["rmax"]
     o.phi_eps = phi_eps
@@ -135,6 +136,44 @@ def bounce_setup(kind, params, phi_absMin, phi_metaMin, phi_bar=None, rscale=Non
                                     tabs.jb if tabs else None, tabs.jf if tabs else None, _bounce_out(out), None,
                                     torch.cuda.current_stream(dev).cuda_stream), "ctb_bounce_setup")
     return int(out["status"][0]), float(out["phi_bar"][0]), float(out["rscale"][0])
+
+
+def find_action_batch(potential_kind, params, phi_metaMin, R, Phi, dPhi, n_points=None, alpha=2, device=None):
+    """SingleFieldInstanton.findAction(profile) (tunneling1D.py:763-791) for N given profiles.
+
+    params [N, K], phi_metaMin [N]; R, Phi, dPhi [N, P] (row i: Profile1D.R / .Phi / .dPhi of instance i, the first
+    n_points[i] entries are used; default: all P).  alpha may be any real >= 0.  Returns S [N] (on the device of R if R
+    is a CUDA tensor, else a CPU tensor)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    kind = getattr(potential_kind, "kind", potential_kind)
+    if kind not in _lib.NPARAM:
+        raise ValueError("unknown potential kind %r" % (potential_kind,))
+    on_host = not (isinstance(R, torch.Tensor) and R.is_cuda)
+    if device is None:
+        device = R.device if not on_host else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    d_R = _as_device(torch, R, device)
+    d_R = d_R.reshape(1, -1) if d_R.dim() == 1 else d_R
+    n, stride = d_R.shape
+    d_Phi, d_dPhi = _as_device(torch, Phi, device, (n, stride)), _as_device(torch, dPhi, device, (n, stride))
+    d_params = _as_device(torch, params, device).reshape(-1, _lib.NPARAM[kind])
+    if d_params.shape[0] != n:
+        d_params = d_params.expand(n, -1).contiguous()
+    d_meta = _as_device(torch, phi_metaMin, device, (n,))
+    if n_points is None:
+        d_np = torch.full((n,), stride, dtype=torch.int32, device=device)
+    else:
+        d_np = torch.as_tensor(n_points, dtype=torch.int32).to(device).expand(n).contiguous()
+    S = torch.empty(n, dtype=torch.float64, device=device)
+    tabs = _tables.device_tables(device) if kind in _lib.THERMAL_KINDS else None
+    if n:
+        with torch.cuda.device(device):
+            _lib.check(lib.ctb_find_action(kind, d_params.data_ptr(), tabs.jb if tabs else None, tabs.jf if tabs else None,
+                                           d_meta.data_ptr(), d_R.data_ptr(), d_Phi.data_ptr(), d_dPhi.data_ptr(), stride,
+                                           d_np.data_ptr(), n, float(alpha), S.data_ptr(),
+                                           torch.cuda.current_stream(device).cuda_stream), "ctb_find_action")
+    return S.cpu() if on_host else S
 
 
 def alloc_out(torch, n, device):

@@ -322,6 +322,89 @@ int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, cons
 }
 
 
+// findAction for arbitrary Profile1D arrays (tunneling1D.py:763-791): one WARP per profile.
+// scipy.integrate.simpson on the non-uniform R is linear in the integrand, S = sum_j w_j y_j: lane-strided
+// points, each lane forms its point's weight from the five neighbouring abscissae (coalesced reads) and
+// evaluates the integrand once; warp-shuffle reduction; lane 0 adds the bulk term of the bubble interior.
+CTB_DEV void simpson_pair_w(double x0, double x1, double x2, double &w0, double &w1, double &w2)
+{
+    const double h0 = x1 - x0, h1 = x2 - x1, hsum = h0 + h1, hprod = h0 * h1;
+    const double h0divh1 = (h1 != 0) ? h0 / h1 : 0.0; // scipy's guarded divisions
+    const double inv = (h0divh1 != 0) ? 1.0 / h0divh1 : 0.0;
+    const double q = (hprod != 0) ? hsum / hprod : 0.0;
+    const double c = hsum / 6.0;
+    w0 = c * (2.0 - inv); w1 = c * (hsum * q); w2 = c * (2.0 - h0divh1);
+}
+
+template <class Pot>
+__global__ void __launch_bounds__(128) find_action_kernel(const double *__restrict__ params, JTab jb, JTab jf,
+                                                          const double *__restrict__ phi_meta,
+                                                          const double *__restrict__ R, const double *__restrict__ Phi,
+                                                          const double *__restrict__ dPhi, int64_t stride,
+                                                          const int32_t *__restrict__ npts, int64_t n, double alpha,
+                                                          double afac, double vfac, double *__restrict__ S)
+{
+    extern __shared__ double smem[];
+    if (!Pot::analytic) {
+        jb = stage_table_compact(jb, smem);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return; // whole warp
+    Pot pot;
+    pot.load(params + i * Pot::nparam, &jb, &jf);
+    const double *r = R + i * stride, *ph = Phi + i * stride, *dp = dPhi + i * stride;
+    const int N = npts[i];
+    if (N < 1 || N > stride) { if (lane == 0) S[i] = nan(""); return; }
+    const double Vm = pot.V_quad(phi_meta[i]);
+    const int nb = (N & 1) ? N : N - 1; // composite rule on the first nb points
+    const int ialpha = (alpha == (double)(int)alpha) ? (int)alpha : -1;
+    double acc = 0.0;
+    for (int j = lane; j < N; j += 32) {
+        double w = 0.0, w0, w1, w2;
+        if (N == 2) {
+            w = 0.5 * (r[1] - r[0]);
+        } else {
+            if (j & 1) {
+                if (j <= nb - 2) { simpson_pair_w(r[j - 1], r[j], r[j + 1], w0, w1, w2); w = w1; }
+            } else {
+                if (j >= 2 && j <= nb - 1) { simpson_pair_w(r[j - 2], r[j - 1], r[j], w0, w1, w2); w = w2; }
+                if (j <= nb - 3) { simpson_pair_w(r[j], r[j + 1], r[j + 2], w0, w1, w2); w += w0; }
+            }
+            if (!(N & 1) && j >= N - 3) { // even N: Cartwright's correction for the last interval
+                const double h0 = r[N - 2] - r[N - 3], h1 = r[N - 1] - r[N - 2];
+                double num, den;
+                if (j == N - 1) { num = 2 * h1 * h1 + 3 * h0 * h1; den = 6 * (h1 + h0); w += (den != 0) ? num / den : 0.0; }
+                else if (j == N - 2) { num = h1 * h1 + 3.0 * h0 * h1; den = 6 * h0; w += (den != 0) ? num / den : 0.0; }
+                else { num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1); w -= (den != 0) ? num / den : 0.0; }
+            }
+        }
+        const double rj = r[j], d = dp[j];
+        const double ra = (ialpha == 2) ? rj * rj : (ialpha == 3) ? rj * rj * rj : (ialpha == 0) ? 1.0 : pow(rj, alpha);
+        acc += w * ((0.5 * (d * d) + pot.V_quad(ph[j]) - Vm) * (ra * afac));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const double r0 = r[0];
+        const double rd = (ialpha == 2) ? r0 * r0 * r0 : (ialpha == 3) ? (r0 * r0) * (r0 * r0) : pow(r0, alpha + 1.0);
+        S[i] = acc + (rd * vfac) * (pot.V_quad(ph[0]) - Vm);
+    }
+}
+
+template <class Pot>
+int launch_find_action(const double *params, const ctb_jtable *jb, const ctb_jtable *jf, const double *phi_meta,
+                       const double *R, const double *Phi, const double *dPhi, int64_t stride, const int32_t *npts,
+                       int64_t n, double alpha, double *S, cudaStream_t st)
+{
+    const double d = alpha + 1.0; // T1D:782-790
+    const double afac = 2.0 * pow(CTB_PI, 0.5 * d) / tgamma(0.5 * d), vfac = pow(CTB_PI, 0.5 * d) / tgamma(0.5 * d + 1.0);
+    const size_t sm = Pot::analytic ? 0 : table_bytes_compact(jb);
+    find_action_kernel<Pot><<<(unsigned)((n + 3) / 4), 128, sm, st>>>(params, to_jtab(jb), to_jtab(jf), phi_meta, R, Phi,
+                                                                      dPhi, stride, npts, n, alpha, afac, vfac, S);
+    return (int)cudaGetLastError();
+}
+
 int grid_for(int64_t n, int block)
 {
     int64_t g = (n + block - 1) / block;
@@ -340,7 +423,7 @@ CTB_API const char *ctb_strerror(int code)
     switch (code) {
     case CTB_OK: return "ok";
     case CTB_ERR_BAD_ARG: return "bad argument";
-    case CTB_ERR_UNSUPPORTED: return "unsupported option (alpha must be 2 or 3, 2 <= npoints <= 4096, known pot_kind)";
+    case CTB_ERR_UNSUPPORTED: return "unsupported option (alpha must be 1..4, 2 <= npoints <= 4096, known pot_kind)";
     case CTB_ERR_NO_DEVICE: return "no usable CUDA device (needs sm_100)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
@@ -569,6 +652,32 @@ CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtab
     if (n == 0) return CTB_OK;
     if (!d_params || !d_lo || !d_hi || !d_xmin) return CTB_ERR_BAD_ARG;
     return launch_rows<true>(pot_kind, d_params, jb, jf, d_lo, d_hi, xtol_rel, d_xmin, d_vmin, n, (cudaStream_t)stream);
+}
+
+CTB_API int ctb_find_action(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                            const double *d_phi_meta, const double *d_R, const double *d_Phi, const double *d_dPhi,
+                            int64_t stride, const int32_t *d_npts, int64_t n, double alpha, double *d_S, void *stream)
+{
+    if (n < 0 || stride < 1 || !(alpha >= 0)) return CTB_ERR_BAD_ARG;
+    if (n == 0) return CTB_OK;
+    if (!d_params || !d_phi_meta || !d_R || !d_Phi || !d_dPhi || !d_npts || !d_S) return CTB_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pot_kind) {
+    case CTB_POT_POLY4:
+        return launch_find_action<PotPoly4>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
+    case CTB_POT_SPLINE:
+        return launch_find_action<PotSpline>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
+    case CTB_POT_THERMAL1F:
+        if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
+        return launch_find_action<PotThermal1F>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
+    case CTB_POT_MODEL1_LINE:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        return launch_find_action<PotModel1Line>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
+    case CTB_POT_MODEL1F:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        return launch_find_action<PotModel1F>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
+    }
+    return CTB_ERR_UNSUPPORTED;
 }
 
 CTB_API int ctb_fp64_peak(int64_t iters, int blocks, int threads, double *d_sink, float *ms_out, void *stream)

@@ -143,8 +143,8 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     // split solve (shoot kernel, then save kernel) when the caller provides scratch and all hand-over arrays
     const bool split = a.scratch && !prof && a.out.d_status && a.out.d_r0 && a.out.d_rf && a.out.d_n_shots &&
                        a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
-    if (alpha != 2 && alpha != 3) return CTB_ERR_UNSUPPORTED;
-    if (split) {
+    if (alpha < 1 || alpha > 4) return CTB_ERR_UNSUPPORTED;
+    if (split && (alpha == 2 || alpha == 3)) {
         const bool big = Pot::analytic && a.n >= 300000; // throughput regime: trade registers for warps
         if (alpha == 2) {
             if (big) bounce_kernel<Pot, 2, false, MODE_SHOOT, 4><<<grid, block, sm, st>>>(a);
@@ -155,10 +155,21 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
             else bounce_kernel<Pot, 3, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
             bounce_kernel<Pot, 3, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
         }
-    } else if (alpha == 2 && !prof) bounce_kernel<Pot, 2, false, MODE_FUSED><<<grid, block, sm, st>>>(a);
-    else if (alpha == 3 && !prof) bounce_kernel<Pot, 3, false, MODE_FUSED><<<grid, block, sm, st>>>(a);
-    else if (alpha == 2) bounce_kernel<Pot, 2, true, MODE_FUSED><<<grid, block, sm, st>>>(a);
-    else bounce_kernel<Pot, 3, true, MODE_FUSED><<<grid, block, sm, st>>>(a);
+    } else {
+        // single-kernel form; the only one compiled for alpha = 1 and 4 (d = 2 and 5 dimensions)
+#define CTB_LAUNCH_FUSED(AL)                                                                     \
+    do {                                                                                         \
+        if (prof) bounce_kernel<Pot, AL, true, MODE_FUSED><<<grid, block, sm, st>>>(a);          \
+        else bounce_kernel<Pot, AL, false, MODE_FUSED><<<grid, block, sm, st>>>(a);              \
+    } while (0)
+        switch (alpha) {
+        case 1: CTB_LAUNCH_FUSED(1); break;
+        case 2: CTB_LAUNCH_FUSED(2); break;
+        case 3: CTB_LAUNCH_FUSED(3); break;
+        default: CTB_LAUNCH_FUSED(4); break;
+        }
+#undef CTB_LAUNCH_FUSED
+    }
     return (int)cudaGetLastError();
 }
 
@@ -180,6 +191,10 @@ int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaSt
     else if (alpha == 3 && !prof) CTB_LAUNCH_WARP(3, false);
     else if (alpha == 2) CTB_LAUNCH_WARP(2, true);
     else if (alpha == 3) CTB_LAUNCH_WARP(3, true);
+    else if (alpha == 1 && !prof) CTB_LAUNCH_WARP(1, false);
+    else if (alpha == 4 && !prof) CTB_LAUNCH_WARP(4, false);
+    else if (alpha == 1) CTB_LAUNCH_WARP(1, true);
+    else if (alpha == 4) CTB_LAUNCH_WARP(4, true);
     else return CTB_ERR_UNSUPPORTED;
 #undef CTB_LAUNCH_WARP
     return (int)cudaGetLastError();

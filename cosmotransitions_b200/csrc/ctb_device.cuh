@@ -605,6 +605,27 @@ struct ProfileSink { // optional Profile1D dump
 
 enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
 
+// Geometry factors of findAction (T1D:782-790) for d = ALPHA + 1 dimensions, ALPHA in {1, 2, 3, 4}:
+// area of the unit ALPHA-sphere 2 pi^(d/2) / Gamma(d/2), volume of the unit d-ball pi^(d/2) / Gamma(d/2 + 1).
+template <int ALPHA> CTB_DEV double area_fac()
+{
+    return (ALPHA == 1) ? 6.283185307179586 : (ALPHA == 2) ? 12.566370614359172 : (ALPHA == 3) ? 19.739208802178716
+                                                                                               : 26.318945069571623;
+}
+template <int ALPHA> CTB_DEV double vol_fac()
+{
+    return (ALPHA == 1) ? 3.141592653589793 : (ALPHA == 2) ? 4.1887902047863905 : (ALPHA == 3) ? 4.934802200544679
+                                                                                               : 5.263789013914325;
+}
+template <int ALPHA> CTB_DEV double pow_alpha(double r) // r^ALPHA
+{
+    return (ALPHA == 1) ? r : (ALPHA == 2) ? r * r : (ALPHA == 3) ? r * r * r : (r * r) * (r * r);
+}
+template <int ALPHA> CTB_DEV double pow_dim(double r) // r^(ALPHA+1)
+{
+    return (ALPHA == 1) ? r * r : (ALPHA == 2) ? r * r * r : (ALPHA == 3) ? (r * r) * (r * r) : (r * r) * (r * r) * r;
+}
+
 // T1D:294-373  phi(r), phi'(r) of the linearised equation of motion around phi0.
 // nu = (ALPHA-1)/2: closed forms for nu = 1/2, I0/I1/J0/J1 + recurrences for nu = 1.
 // ONE out-of-line copy per ALPHA: the transcendental bodies (exp, sinh, sincos, Bessel) are large and
@@ -628,10 +649,12 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
     if (z < 1e-2) {
         const double s = (d2v > 0) ? 1.0 : -1.0;
         // Gamma(k+1) Gamma(k+1+nu), k = 1..3 ; Gamma(nu+1)
-        const double G1 = (ALPHA == 2) ? 1.3293403881791370 : 2.0;
-        const double G2 = (ALPHA == 2) ? 2.0 * 3.3233509704478426 : 12.0;
-        const double G3 = (ALPHA == 2) ? 6.0 * 11.631728396567448 : 144.0;
-        const double g = (ALPHA == 2) ? 0.88622692545275801 : 1.0;
+        const double G1 = (ALPHA == 1) ? 1.0 : (ALPHA == 2) ? 1.3293403881791370 : (ALPHA == 3) ? 2.0 : 3.3233509704478426;
+        const double G2 = (ALPHA == 1) ? 4.0 : (ALPHA == 2) ? 2.0 * 3.3233509704478426 : (ALPHA == 3) ? 12.0
+                                                                                                   : 2.0 * 11.631728396567448;
+        const double G3 = (ALPHA == 1) ? 36.0 : (ALPHA == 2) ? 6.0 * 11.631728396567448 : (ALPHA == 3) ? 144.0
+                                                                                                     : 6.0 * 52.34277778455352;
+        const double g = (ALPHA == 1) ? 1.0 : (ALPHA == 2) ? 0.88622692545275801 : (ALPHA == 3) ? 1.0 : 1.3293403881791370;
         double h2 = (0.5 * z) * (0.5 * z);
         double t1 = s / G1, t2 = h2 / G2, t3 = h2 * h2 * s / G3;
         double p = t1 + t2 + t3;
@@ -656,6 +679,51 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
         }
         phi = (sh / z - 1.0) * ratio + phi0;
         dphi = ((ch - sh / z) / r) * ratio;
+    } else if (ALPHA == 1) {
+        // nu = 0: I_0(z) - 1 and (I_{-1} + I_1)/2 = I_1 ; J: J_0(z) - 1 and (J_{-1} - J_1)/2 = -J_1
+        if (modified) {
+            phi = (cyl_bessel_i0(z) - 1.0) * ratio + phi0;
+            dphi = (beta * cyl_bessel_i1(z)) * ratio;
+        } else {
+            phi = (j0(z) - 1.0) * ratio + phi0;
+            dphi = (-beta * j1(z)) * ratio;
+        }
+    } else if (ALPHA == 4) {
+        // nu = 3/2: f(z) = Gamma(5/2) (z/2)^(-3/2) I_{3/2}(z) = 3 (cosh z - sinh z / z) / z^2  (J: sin z / z - cos z),
+        // phi - phi0 = (f - 1) V'/V'', phi' = beta f'(z) V'/V''.  The closed forms cancel like z^-4 for small z:
+        // below z = 1 the ascending series sum_k (+-z^2/4)^k Gamma(5/2) / (k! Gamma(k + 5/2)) is used instead.
+        double fm1, fp;
+        if (z < 1.0) {
+            const double q = (modified ? 0.25 : -0.25) * z * z;
+            double t = 1.0, sf = 0.0, sd = 0.0;
+#pragma unroll
+            for (int k = 1; k <= 11; k++) {
+                t *= q / ((double)k * ((double)k + 1.5));
+                sf += t;
+                sd += (double)k * t;
+            }
+            fm1 = sf;
+            fp = 2.0 * sd / z;
+        } else {
+            const double iz = 1.0 / z, iz2 = iz * iz;
+            double sh, ch;
+            if (modified && z >= 700.0) { // sinh = cosh = e^z / 2 (overflows with I_nu: phi -> inf, not NaN)
+                const double e2 = exp(0.5 * z), E = (0.5 * e2) * e2;
+                fm1 = (3.0 * iz2 * (1.0 - iz)) * E - 1.0;
+                fp = (3.0 * iz2 * (1.0 - 3.0 * iz + 3.0 * iz2)) * E;
+            } else if (modified) {
+                double ez = exp(z), emz = rcp_fast(ez);
+                sh = 0.5 * (ez - emz); ch = 0.5 * (ez + emz);
+                fm1 = 3.0 * (ch - sh * iz) * iz2 - 1.0;
+                fp = 3.0 * iz2 * (sh - 3.0 * ch * iz + 3.0 * sh * iz2);
+            } else {
+                sincos(z, &sh, &ch);
+                fm1 = 3.0 * (sh * iz - ch) * iz2 - 1.0;
+                fp = 3.0 * iz2 * (sh + 3.0 * ch * iz - 3.0 * sh * iz2);
+            }
+        }
+        phi = fm1 * ratio + phi0;
+        dphi = (beta * fp) * ratio;
     } else {
         double hp = 2.0 / z; // (z/2)^-1, Gamma(2) = 1
         double Inu, Im, Ip, sg;
@@ -948,8 +1016,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     const double inv_ea0 = 1.0 / ea0, inv_ea1 = 1.0 / ea1;
     const double cutoff = k.thinCutoff * delta_phi;
     const int npoints = k.npoints;
-    const double afac = (ALPHA == 2) ? 12.566370614359172 : 19.739208802178716; // 2 pi^(d/2) / Gamma(d/2)
-    const double vfac = (ALPHA == 2) ? 4.1887902047863905 : 4.934802200544679;  // pi^(d/2) / Gamma(d/2+1)
+    const double afac = area_fac<ALPHA>(), vfac = vol_fac<ALPHA>();
 
     bool have_rf = false;
     double rf = qnan, r0 = qnan, y00 = qnan, y01 = qnan, delta_phi0 = qnan, dv0 = qnan, d2v0 = qnan;
@@ -967,7 +1034,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
 
     int g_dense = 0, g0 = 0; // global index of the next dense-output point; start of the uniform Simpson part
     auto emit = [&](double r, double phi, double dphi, bool dense) {
-        double ra = (ALPHA == 2) ? r * r : r * r * r;
+        double ra = pow_alpha<ALPHA>(r);
         double integrand = (0.5 * (dphi * dphi) + pot.V_quad(phi) - V_meta) * (ra * afac);
         if (dense && simp.uniform_on) simp.feed_uniform(integrand, g_dense & 1);
         else {
@@ -1116,7 +1183,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 const double x_m2 = (npoints >= 3) ? __dadd_rn(__dmul_rn((double)(npoints - 3), step), r0) : r0;
                 const double x_m1 = (npoints >= 2) ? __dadd_rn(__dmul_rn((double)(npoints - 2), step), r0) : r0;
                 double S = simp.finish(N, step, x_m2, x_m1, rf);
-                double Rd = (ALPHA == 2) ? R_first * R_first * R_first : (R_first * R_first) * (R_first * R_first);
+                double Rd = pow_dim<ALPHA>(R_first);
                 S += (Rd * vfac) * (pot.V_quad(Phi_first) - V_meta);
                 res.S = S;
                 res.status = status;

@@ -102,11 +102,13 @@ class SingleFieldInstanton:
 
     def findAction(self, profile):
         """Euclidean action of `profile` (tunneling1D.py:763-791).  For the profile findProfile just
-        returned this is the value the kernel accumulated while producing it (fused quadrature)."""
+        returned this is the value the kernel accumulated while producing it (fused quadrature); any
+        other Profile1D (anything with .R, .Phi, .dPhi) goes through the stand-alone quadrature kernel."""
         if self._last is not None and profile is self._last[0]:
             return self._last[1]
-        raise NotImplementedError("findAction is fused with findProfile on the device; pass the Profile1D "
-                                  "returned by the most recent findProfile() call")
+        S = batch.find_action_batch(self.V.kind, self.V.params[None, :], [self.phi_metaMin], np.asarray(profile.R, float),
+                                    np.asarray(profile.Phi, float), np.asarray(profile.dPhi, float), alpha=self.alpha)
+        return float(S[0])
 
     def evenlySpacedPhi(self, phi, dphi, npoints=100, k=1, fixAbs=True):
         """

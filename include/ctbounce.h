@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 8
+#define CTB_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -38,7 +38,7 @@ extern "C" {
 /* ---- return codes --------------------------------------------------------------------------- */
 #define CTB_OK 0
 #define CTB_ERR_BAD_ARG (-1)      /* NULL pointer, n < 0, bad enum ...                       */
-#define CTB_ERR_UNSUPPORTED (-2)  /* alpha not in {2,3}, npoints out of range, unknown kind   */
+#define CTB_ERR_UNSUPPORTED (-2)  /* alpha not in 1..4, npoints out of range, unknown kind     */
 #define CTB_ERR_NO_DEVICE (-3)    /* no CUDA device / not an sm_100 device                   */
 
 /* ---- per-instance status (int32) ------------------------------------------------------------ */
@@ -118,7 +118,7 @@ typedef struct ctb_opts {
     double xguess;            /* NaN = None */
     int32_t npoints;          /* 500; 2 <= npoints <= 4096 */
     int32_t max_interior_pts; /* -1 = None (npoints/2) */
-    int32_t alpha;            /* 2 (O(3), finite T) or 3 (O(4), zero T) */
+    int32_t alpha;            /* 1..4: d = alpha + 1 dimensions; 2 = O(3) finite T, 3 = O(4) zero T */
     int32_t block_threads;    /* 0 = library default (thread-per-instance kernel only) */
     int32_t kernel;           /* CTB_KERNEL_AUTO / _THREAD / _WARP, see below */
     int32_t reserved;
@@ -183,6 +183,15 @@ CTB_API int ctb_device_ok(void);
  * jb/jf may be NULL for POLY4. */
 CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_opts *opts, const ctb_jtable *jb,
                              const ctb_jtable *jf, const ctb_bounce_out *out, void *stream);
+
+/* SingleFieldInstanton.findAction(profile) (tunneling1D.py:763-791) for n given profiles: row i of d_R / d_Phi /
+ * d_dPhi ([n, stride], row-major) holds d_npts[i] points of Profile1D.R / .Phi / .dPhi; S_i = simpson of
+ * (phi'^2/2 + V_i(phi) - V_i(phi_meta_i)) Omega_alpha r^alpha over the non-uniform R (scipy.integrate.simpson's
+ * rule, including its even-N end correction) + the bulk term of the bubble interior.  alpha: any real >= 0
+ * (the quadrature has no Bessel start).  A profile with d_npts[i] < 1 or > stride gives NaN. */
+CTB_API int ctb_find_action(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
+                            const double *d_phi_meta, const double *d_R, const double *d_Phi, const double *d_dPhi,
+                            int64_t stride, const int32_t *d_npts, int64_t n, double alpha, double *d_S, void *stream);
 
 /* SingleFieldInstanton.__init__ alone (tunneling1D.py:128-149): metastability check,
  * findBarrierLocation, findRScale.  Fills out->d_phi_bar, d_rscale, d_status (0, CTB_ST_STABLE or

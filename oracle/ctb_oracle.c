@@ -36,7 +36,7 @@
  *   scipy.integrate.simpson    (_quadrature.py: non-uniform composite Simpson + Cartwright
  *                               last-interval correction for even N)                -> simpson
  *   scipy.interpolate.splev    (FITPACK splev / splder / fpbspl, de Boor)           -> splev
- *   scipy.special.iv / jv / gamma for nu = (alpha-1)/2, alpha in {2,3}:
+ *   scipy.special.iv / jv / gamma for nu = (alpha-1)/2, alpha in {1,2,3,4}:
  *        closed forms (nu=1/2) and series/asymptotic I0,I1 + libm j0,j1 (nu=1)      -> bessel_*
  */
 #include <math.h>
@@ -510,7 +510,7 @@ static double simpson(const double *y, const double *x, int N)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Bessel functions for nu = (alpha-1)/2, alpha in {2, 3}                                      */
+/* Bessel functions for nu = (alpha-1)/2, alpha in {1, 2, 3, 4}                                */
 
 /* I_0, I_1: ascending series for z < 30, Hankel asymptotic series beyond (overflow -> inf). */
 static double bessel_in_series(int n, double z)
@@ -545,6 +545,25 @@ static double bessel_i(int n, double z)
 {
     if (z < 30.0) return bessel_in_series(n, z);
     return bessel_in_asym(n, z);
+}
+
+/* I_nu (sg = +1) or J_nu (sg = -1) for nu = 1/2, 3/2, 5/2 by the ascending series
+ * (z/2)^nu sum_k (sg z^2/4)^k / (k! Gamma(k + nu + 1)); used for z < 1 only. */
+static void bessel_half_series(double sg, double z, double *b12, double *b32, double *b52)
+{
+    double nus[3] = {0.5, 1.5, 2.5}, out[3];
+    double q = sg * 0.25 * z * z;
+    for (int m = 0; m < 3; m++) {
+        double nu = nus[m];
+        double term = pow(0.5 * z, nu) / tgamma(nu + 1.0), sum = term;
+        for (int k = 1; k < 60; k++) {
+            term *= q / ((double)k * ((double)k + nu));
+            sum += term;
+            if (fabs(term) < 1e-18 * fabs(sum)) break;
+        }
+        out[m] = sum;
+    }
+    *b12 = out[0]; *b32 = out[1]; *b52 = out[2];
 }
 
 /* tunneling1D.py:294-373 */
@@ -585,13 +604,42 @@ static void exact_solution(sfi_t *s, double r, double phi0, double dV, double d2
                 double sn = sin(z), cs = cos(z);
                 Inu = pre * sn; Inum1 = pre * cs; Inup1 = pre * (sn / z - cs);
             }
-        } else { /* alpha == 3, nu = 1 */
+        } else if (s->alpha == 3) { /* nu = 1 */
             if (modified) {
                 double i0 = bessel_i(0, z), i1 = bessel_i(1, z);
                 Inu = i1; Inum1 = i0; Inup1 = i0 - 2.0 * i1 / z;
             } else {
                 double j0_ = j0(z), j1_ = j1(z);
                 Inu = j1_; Inum1 = j0_; Inup1 = 2.0 * j1_ / z - j0_;
+            }
+        } else if (s->alpha == 1) { /* nu = 0: I_{-1} = I_1, J_{-1} = -J_1 */
+            if (modified) {
+                double i0 = bessel_i(0, z), i1 = bessel_i(1, z);
+                Inu = i0; Inum1 = i1; Inup1 = i1;
+            } else {
+                double j0_ = j0(z), j1_ = j1(z);
+                Inu = j0_; Inum1 = -j1_; Inup1 = j1_;
+            }
+        } else { /* alpha == 4, nu = 3/2: spherical Bessel closed forms; ascending series below z = 1,
+                    where the closed forms cancel */
+            double pre = sqrt(2.0 / (M_PI * z));
+            if (z < 1.0) {
+                bessel_half_series(modified ? 1.0 : -1.0, z, &Inum1, &Inu, &Inup1);
+            } else if (modified && z >= 700.0) { /* sinh = cosh = e^z / 2; overflow only when I_nu does */
+                double e2 = exp(0.5 * z), q = (pre * 0.5 * e2) * e2;
+                Inum1 = q;
+                Inu = q * (1.0 - 1.0 / z);
+                Inup1 = q * ((1.0 + 3.0 / (z * z)) - 3.0 / z);
+            } else if (modified) {
+                double sh = sinh(z), ch = cosh(z);
+                Inum1 = pre * sh;
+                Inu = pre * (ch - sh / z);
+                Inup1 = pre * ((1.0 + 3.0 / (z * z)) * sh - 3.0 * ch / z);
+            } else {
+                double sn = sin(z), cs = cos(z);
+                Inum1 = pre * sn;
+                Inu = pre * (sn / z - cs);
+                Inup1 = pre * ((3.0 / (z * z) - 1.0) * sn - 3.0 * cs / z);
             }
         }
         double hp = pow(0.5 * beta_r, -nu);
@@ -914,7 +962,7 @@ static void solve_one(const pot_t *pot, double phi_absMin, double phi_metaMin, c
     res->phi_bar = s->phi_bar; res->rscale = s->rscale;
     if (st) { res->status = st; return; }
     int npoints = o->npoints;
-    if (npoints < 2 || npoints > MAXPTS / 2 || (o->alpha != 2 && o->alpha != 3)) { res->status = ST_BAD_ARG; return; }
+    if (npoints < 2 || npoints > MAXPTS / 2 || (o->alpha < 1 || o->alpha > 4)) { res->status = ST_BAD_ARG; return; }
 
     /* tunneling1D.py:676-700 */
     double xtol = o->xtol, phitol = o->phitol;
@@ -1009,7 +1057,7 @@ static void solve_one(const pot_t *pot, double phi_absMin, double phi_metaMin, c
         double Vmeta = pot_V(pot, phi_metaMin);
         double afac_pi = pow(M_PI, d * .5), afac_g = tgamma(d * .5);
         for (int i = 0; i < n; i++) {
-            double ra = (s->alpha == 2) ? R[i] * R[i] : pow(R[i], 3.0);
+            double ra = (s->alpha == 2) ? R[i] * R[i] : pow(R[i], (double)s->alpha);
             double area = ra * 2 * afac_pi / afac_g;
             double ig = 0.5 * (dPhi[i] * dPhi[i]) + pot_V(pot, Phi[i]) - Vmeta;
             integrand[i] = ig * area;
@@ -1265,6 +1313,27 @@ CTBO_API void ctbo_potential_rows(const ctbo_config *cfg, const double *params, 
         pot_t pot = {cfg->kind, params + i * cfg->nparam, &jb, &jf};
         out[i] = pot_V(&pot, phi[i]);
     }
+}
+
+/* SingleFieldInstanton.findAction(profile) for a given profile (tunneling1D.py:763-791); alpha is a real number */
+CTBO_API double ctbo_find_action(const ctbo_config *cfg, const double *params, double phi_meta, double alpha,
+                                 const double *R, const double *Phi, const double *dPhi, int n)
+{
+    opts_t o; spline_t jb, jf;
+    cfg_to(cfg, &o, &jb, &jf);
+    pot_t pot = {cfg->kind, params, &jb, &jf};
+    double d = alpha + 1.0;
+    double Vmeta = pot_V(&pot, phi_meta);
+    double *integrand = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        double area = pow(R[i], alpha) * 2 * pow(M_PI, d * .5) / tgamma(d * .5);
+        integrand[i] = (0.5 * (dPhi[i] * dPhi[i]) + pot_V(&pot, Phi[i]) - Vmeta) * area;
+    }
+    double S = simpson(integrand, R, n);
+    double volume = pow(R[0], d) * pow(M_PI, d * .5) / tgamma(d * .5 + 1);
+    S += volume * (pot_V(&pot, Phi[0]) - Vmeta);
+    free(integrand);
+    return S;
 }
 
 static double posV(double x, void *v) { return pot_V((const pot_t *)v, x); }

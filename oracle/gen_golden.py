@@ -19,6 +19,8 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
   tests/golden/thermal1f.json   general one-field generic_potential (bosons + fermions, Jb and Jf): Vtot, bounces
   tests/golden/splinepath.npz   every 1-D solve inside pathDeformation.fullTunneling (examples/fullTunneling.py,
                                 model1.findAllTransitions): the SplinePath potential spline, profile, action
+  tests/golden/alpha14.json     alpha = 1 and 4 (d = 2, 5): quartic bounces and exactSolution unit vectors
+  tests/golden/findaction.json  findAction on given (truncated / strided) profiles, alpha in {1, 2, 2.5, 3, 4}
   tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
 """
 import json
@@ -541,10 +543,69 @@ def gen_model1f():
         json.dump(cases, f, indent=0)
 
 
+def gen_findaction():
+    """findAction on GIVEN profiles (tunneling1D.py:763-791): the three profiles of profiles.npz, truncated to
+    odd / even / tiny lengths, with alpha in {1, 2, 2.5, 3, 4} -> tests/golden/findaction.json"""
+    g = np.load(os.path.join(GOLD, "profiles.npz"))
+    cases = []
+    for name in ("thin2", "thick2", "mid3"):
+        c = float(g[name + "_c"])
+        V, dV, d2V = quartic_lambdas(c)
+        R, Phi, dPhi = g[name + "_R"], g[name + "_Phi"], g[name + "_dPhi"]
+        for alpha in (1, 2, 2.5, 3, 4):
+            o = t1.SingleFieldInstanton(1.0, 0.0, V, dV, d2V, alpha=alpha)
+            for sl in (slice(None), slice(0, 2), slice(0, 3), slice(0, 4), slice(0, 5), slice(0, 100), slice(3, 104),
+                       slice(250, None), slice(0, None, 7)):
+                p = o.profile_rval(R[sl], Phi[sl], dPhi[sl], None)
+                cases.append(dict(name=name, c=c, alpha=alpha, sl=[sl.start, sl.stop, sl.step], n=int(len(p.R)),
+                                  S=float(o.findAction(p))))
+    with open(os.path.join(GOLD, "findaction.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+    print(len(cases), "findAction cases")
+
+
+def gen_alpha14():
+    """alpha = 1 and 4 (d = 2 and 5 dimensions, Bessel order nu = 0 and 3/2): quartic family, a few knob sets,
+    and exactSolution unit vectors -> tests/golden/alpha14.json"""
+    cases = []
+    cs = list(np.round(0.02 + 0.475 * (np.arange(16) + 0.5) / 16, 12)) + [0.01, 0.47, 0.495]
+    for alpha in (1, 4):
+        for c in cs:
+            V, dV, d2V = quartic_lambdas(c)
+            r = run_case(V, dV, d2V, 1.0, 0.0, alpha)
+            r.update(kind="family", c=float(c), alpha=alpha, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0,
+                     phi_meta=0.0, opts={})
+            cases.append(r)
+        for c in (0.1, 0.45):
+            for kw in (dict(phitol=1e-6, xtol=1e-6), dict(npoints=301, thinCutoff=0.05), dict(max_interior_pts=0)):
+                V, dV, d2V = quartic_lambdas(c)
+                r = run_case(V, dV, d2V, 1.0, 0.0, alpha, prof_kw=kw)
+                r.update(kind="knobs", c=float(c), alpha=alpha, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0,
+                         phi_meta=0.0, opts=kw)
+                cases.append(r)
+    rng = np.random.default_rng(14)
+    rows, vals = [], []
+    for alpha in (1, 4):
+        o = t1.SingleFieldInstanton(1.0, 0.0, *quartic_lambdas(0.3), alpha=alpha)
+        for k in range(400):
+            r = 10 ** rng.uniform(-5, 3)
+            phi0 = rng.uniform(-2, 2)
+            dV = rng.normal() * 10 ** rng.uniform(-20, 1)
+            d2V = rng.normal() * 10 ** rng.uniform(-3, 1)
+            with np.errstate(all="ignore"):
+                ph, dph = o.exactSolution(r, phi0, dV, d2V)
+            rows.append([alpha, r, phi0, dV, d2V])
+            vals.append([float(ph), float(dph)])
+    with open(os.path.join(GOLD, "alpha14.json"), "w") as f:
+        json.dump(dict(cases=cases, exact_in=rows, exact_out=vals), f, indent=0)
+    for c_ in cases:
+        print("alpha14", c_["alpha"], c_["c"], c_["opts"], {q: c_.get(q) for q in ("S", "npts", "n_shots", "error")})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath"]
+                               "thermal1f", "splinepath", "alpha14", "findaction"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

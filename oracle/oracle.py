@@ -210,6 +210,16 @@ def vtot_model1_grid(cfg, params, s, T):
     return out
 
 
+def find_action(cfg, params, phi_meta, alpha, R, Phi, dPhi):
+    """SingleFieldInstanton.findAction for a given profile (tunneling1D.py:763-791)."""
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(cfg.nparam)
+    R, Phi, dPhi = (np.ascontiguousarray(a, dtype=np.float64) for a in (R, Phi, dPhi))
+    f = lib().ctbo_find_action
+    f.restype = C.c_double
+    return f(C.byref(cfg), _dp(params), C.c_double(phi_meta), C.c_double(alpha), _dp(R), _dp(Phi), _dp(dPhi),
+             C.c_int(len(R)))
+
+
 def brentq_poly(coefs_high_to_low, a, b):
     p = np.array([len(coefs_high_to_low) - 1] + list(coefs_high_to_low), dtype=np.float64)
     err, nf = C.c_int(0), C.c_int(0)

@@ -32,10 +32,12 @@ def _np(d):
 ERR2STATUS = {"PotentialError:stable, not metastable": 2, "PotentialError:no barrier": 3}
 
 
+@pytest.mark.parametrize("fname", ["quartic.json", "alpha14.json"])
 @pytest.mark.parametrize("kernel", ["thread", "warp"])
-def test_quartic_golden(ctb, gold_dir, kernel):
+def test_quartic_golden(ctb, gold_dir, kernel, fname):
     from cosmotransitions_b200 import _lib, batch
-    cases = json.load(open(os.path.join(gold_dir, "quartic.json")))
+    cases = json.load(open(os.path.join(gold_dir, fname)))
+    cases = cases["cases"] if isinstance(cases, dict) else cases   # alpha14.json: alpha = 1, 4 (d = 2, 5)
     worst = 0.0
     for case in cases:
         opts = dict(case.get("opts", {}))
@@ -88,6 +90,37 @@ def test_profiles_golden(ctb, gold_dir):
         inst = t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(c))
         S = inst.findAction(inst.findProfile())
         assert abs(S - float(g[name + "_S"])) < S_RTOL * abs(float(g[name + "_S"]))
+
+
+def test_find_action_given_profiles(ctb, gold_dir):
+    """ctb_find_action (warp-per-profile quadrature kernel) vs the reference's findAction on given profiles:
+    odd / even / tiny N, strided and truncated grids, alpha in {1, 2, 2.5, 3, 4}; batched with ragged n_points."""
+    from cosmotransitions_b200 import _lib, batch, tunneling1D as t1, potentials
+    g = np.load(os.path.join(gold_dir, "profiles.npz"))
+    cases = json.load(open(os.path.join(gold_dir, "findaction.json")))
+    for alpha in (1, 2, 2.5, 3, 4):
+        sub = [c for c in cases if c["alpha"] == alpha]
+        P = max(c["n"] for c in sub)
+        R, Phi, dPhi = (np.zeros((len(sub), P)) for _ in range(3))
+        for i, c in enumerate(sub):
+            sl = slice(*c["sl"])
+            for arr, key in ((R, "_R"), (Phi, "_Phi"), (dPhi, "_dPhi")):
+                arr[i, :c["n"]] = g[c["name"] + key][sl]
+        params = np.array([[0, 0, c["c"] / 2, -(1 + c["c"]) / 3, 0.25] for c in sub])
+        S = batch.find_action_batch(_lib.POT_POLY4, params, 0.0, R, Phi, dPhi, n_points=[c["n"] for c in sub],
+                                    alpha=alpha).numpy()
+        ref = np.array([c["S"] for c in sub])
+        np.testing.assert_allclose(S, ref, rtol=1e-11, atol=0)
+    # scalar API: a foreign profile object goes through the kernel, the last findProfile result through the cache
+    inst = t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(float(g["thin2_c"])), alpha=2)
+    prof = inst.findProfile()
+    S_fused = inst.findAction(prof)
+    S_kernel = inst.findAction(inst.profile_rval(prof.R.copy(), prof.Phi.copy(), prof.dPhi.copy(), None))
+    assert abs(S_fused - S_kernel) <= 1e-12 * abs(S_fused)
+    assert abs(S_kernel - float(g["thin2_S"])) <= S_RTOL_TIGHT * abs(S_kernel)
+    # bad n_points -> NaN for that row only
+    S = batch.find_action_batch(_lib.POT_POLY4, params[:2], 0.0, R[:2], Phi[:2], dPhi[:2], n_points=[0, 5], alpha=2).numpy()
+    assert np.isnan(S[0]) and np.isfinite(S[1])
 
 
 def test_splinepath_drop_in(ctb, gold_dir):
@@ -153,7 +186,7 @@ def test_scalar_api_errors(ctb):
         t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(0.499)).findProfile()
 
 
-@pytest.mark.parametrize("alpha", [2, 3])
+@pytest.mark.parametrize("alpha", [1, 2, 3, 4])
 def test_quartic_sweep_vs_oracle(ctb, oracle, alpha):
     """4096-instance thin->thick sweep (config C2/C3 family) + shuffled order, against the CPU oracle."""
     from cosmotransitions_b200 import _lib, batch, potentials
@@ -168,7 +201,9 @@ def test_quartic_sweep_vs_oracle(ctb, oracle, alpha):
     assert ok.mean() > 0.99
     rel = np.abs(g["S"][ok] - o["S"][ok]) / np.abs(o["S"][ok])
     print("alpha", alpha, "max rel", rel.max(), "mismatched n_rkck", int((g["n_rkck"] != o["n_rkck"]).sum()))
-    assert rel.max() < S_RTOL_TIGHT
+    # alpha = 4: S reaches 4e9 on the thin-wall end and the nu = 3/2 closed forms of the device and of the
+    # oracle are arranged differently (both within a few ulp of scipy's iv / jv)
+    assert rel.max() < (S_RTOL_TIGHT if alpha != 4 else 1e-8)
     assert np.array_equal(g["n_shots"][ok], o["n_shots"][ok])
     assert np.array_equal(g["n_points"][ok], o["n_points"][ok])
     assert (g["n_rkck"][ok] != o["n_rkck"][ok]).mean() < 1e-3
@@ -183,7 +218,7 @@ def test_quartic_sweep_vs_oracle(ctb, oracle, alpha):
         assert np.array_equal(gs[k], g[k][perm]), k
 
 
-@pytest.mark.parametrize("alpha", [2, 3])
+@pytest.mark.parametrize("alpha", [1, 2, 3, 4])
 def test_warp_and_thread_kernels_agree(ctb, alpha):
     """The warp-per-instance kernel resolves the same shooting sequence speculatively: identical shot and
     step counts, identical phi0 / rf / x, S equal up to the summation order of the quadrature."""
@@ -196,7 +231,7 @@ def test_warp_and_thread_kernels_agree(ctb, alpha):
     b = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, alpha=alpha, kernel="warp", return_profiles=True))
     assert np.array_equal(a["status"], b["status"])
     ok = a["status"] <= 1
-    assert ok.mean() > 0.9 and (~ok).sum() > 1
+    assert ok.mean() > 0.9 and (~ok).sum() >= (1 if alpha == 1 else 2)   # (alpha = 1: no brentq-failure zone below c = 0.499)
     for k in ("n_shots", "n_rkck", "n_points"):
         assert np.array_equal(a[k][ok], b[k][ok]), k
     for k in ("phi0", "x", "phi_bar", "rscale"):

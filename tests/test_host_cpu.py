@@ -93,7 +93,8 @@ def test_opts_marshalling_and_defaults():
     with pytest.raises(TypeError):
         batch.make_opts(bogus=1)
     with pytest.raises(NotImplementedError):
-        batch.make_opts(alpha=4)
+        batch.make_opts(alpha=5)
+    assert batch.make_opts(alpha=1).alpha == 1 and batch.make_opts(alpha=4).alpha == 4
 
 
 def test_partition_roundtrip():

@@ -29,9 +29,15 @@ def _cfg(oracle, case, **kw):
     return oracle.make_config(alpha=case["alpha"], **opts, **kw)
 
 
-def test_quartic_cases(oracle, gold_dir):
-    cases = json.load(open(os.path.join(gold_dir, "quartic.json")))
-    assert len(cases) > 150
+def _load_cases(gold_dir, fname):
+    cases = json.load(open(os.path.join(gold_dir, fname)))
+    return cases["cases"] if isinstance(cases, dict) else cases
+
+
+@pytest.mark.parametrize("fname,nmin", [("quartic.json", 150), ("alpha14.json", 40)])
+def test_quartic_cases(oracle, gold_dir, fname, nmin):
+    cases = _load_cases(gold_dir, fname)
+    assert len(cases) > nmin
     worst = 0.0
     for case in cases:
         cfg = _cfg(oracle, case)
@@ -81,8 +87,29 @@ def test_profiles(oracle, gold_dir):
         assert abs(r["S"] - float(g[name + "_S"])) < 1e-8 * abs(float(g[name + "_S"]))
 
 
-def test_exact_solution_units(oracle, gold_dir):
-    g = np.load(os.path.join(gold_dir, "units.npz"))
+def _profile_slice(g, case):
+    sl = slice(*case["sl"])
+    return tuple(g[case["name"] + k][sl] for k in ("_R", "_Phi", "_dPhi"))
+
+
+def test_find_action_given_profiles(oracle, gold_dir):
+    """findAction on given profiles (odd / even / tiny N, alpha incl. non-integer): oracle vs reference."""
+    g = np.load(os.path.join(gold_dir, "profiles.npz"))
+    cases = json.load(open(os.path.join(gold_dir, "findaction.json")))
+    assert len(cases) > 100
+    for case in cases:
+        R, Phi, dPhi = _profile_slice(g, case)
+        assert len(R) == case["n"]
+        S = oracle.find_action(oracle.make_config(), oracle.quartic_params(case["c"])[0], 0.0, case["alpha"], R, Phi, dPhi)
+        assert abs(S - case["S"]) <= 1e-12 * abs(case["S"]) + 1e-300, case
+
+
+@pytest.mark.parametrize("fname", ["units.npz", "alpha14.json"])
+def test_exact_solution_units(oracle, gold_dir, fname):
+    if fname.endswith(".npz"):
+        g = np.load(os.path.join(gold_dir, fname))
+    else:
+        g = {k: np.array(v) for k, v in json.load(open(os.path.join(gold_dir, fname))).items() if k != "cases"}
     bad = 0
     for row, ref in zip(g["exact_in"], g["exact_out"]):
         alpha, r, phi0, dV, d2V = row
