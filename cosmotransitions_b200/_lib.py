@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 ABI_VERSION = 9
 V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
+EXACT_X, EXACT_DX, EXACT_THETA = 0, 1, 2
 POT_POLY4, POT_MODEL1_LINE, POT_MODEL1F, POT_SPLINE, POT_THERMAL1F = 0, 1, 2, 3, 4
 SPLINE_MAX_PIECES = 255
 THERMAL_KINDS = (POT_MODEL1_LINE, POT_MODEL1F, POT_THERMAL1F)   # need the Jb / Jf tables
@@ -23,7 +24,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
-           "ctb_jspline", "ctb_jseries", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
+           "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
 
 
 class JTable(C.Structure):
@@ -89,6 +90,8 @@ def load():
     lib.ctb_jseries.restype = C.c_int
     lib.ctb_jseries.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p]
+    lib.ctb_jexact.restype = C.c_int
+    lib.ctb_jexact.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ctb_vtot_model1.restype = C.c_int
     lib.ctb_vtot_model1.argtypes = [C.POINTER(C.c_double), C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_int, C.c_void_p]

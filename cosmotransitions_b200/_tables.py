@@ -56,6 +56,8 @@ class HostTables:
         self.xbmin, self.xbmax = float(d["xbmin"]), float(d["xbmax"])
         self.xfmin, self.xfmax = float(d["xfmin"]), float(d["xfmax"])
         self.tb, self.cb, self.tf, self.cf = d["tb"], d["cb"], d["tf"], d["cf"]
+        # the 2 x 1000 exact-integral samples the splines interpolate (finiteT.py:151-196)
+        self.xb, self.yb, self.xf, self.yf = d["xb"], d["yb"], d["xf"], d["yf"]
         self.low_b, self.low_f = np.ascontiguousarray(d["low_b"]), np.ascontiguousarray(d["low_f"])
         self.brk_b, self.coef_b = bspline_to_pp(self.tb, self.cb)
         self.brk_f, self.coef_f = bspline_to_pp(self.tf, self.cf)

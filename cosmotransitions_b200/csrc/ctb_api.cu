@@ -135,6 +135,107 @@ __global__ void __launch_bounds__(256) jseries_kernel(int deriv, int nterms, Low
     }
 }
 
+// ---- Jb / Jf "exact": the defining integrals (finiteT.py:40-147), by quadrature on the device -------------
+// The reference hands them to QUADPACK (scipy.integrate.quad, tolerance 1.49e-8).  Here:
+//  theta = x^2 >= 0:  y = x sinh u makes the integrand y^2 log(1 -+ exp(-sqrt(y^2 + x^2))) dy an even, entire
+//    function of u on the real line with double-exponential decay (nearest singularity at |Im u| = pi/2), so the
+//    plain trapezoidal rule in u converges like exp(-pi^2/h): h = 0.2 (narrowed like 1/sqrt(x) for the Gaussian
+//    peak at large x) is exact to rounding.  Same substitution for dJ/dx (finiteT.py:104-111).
+//  theta < 0 (finiteT.py:54-66,84-96), a = sqrt(-theta), s = sqrt(|y^2 - a^2|):
+//    int_0^inf s sqrt(s^2 + a^2) log(1 -+ e^-s) ds      -- double-exponential rule s = exp(pi/2 sinh t)
+//    + int_0^a s sqrt(a^2 - s^2) log(2 |sin or cos (s/2)|) ds -- tanh-sinh panels between the logarithmic
+//      singularities (s = 2 pi k for Jb, pi (2k+1) for Jf), integrand evaluated from the distance to the nearer
+//      panel end so that the singular factors keep full relative accuracy.
+CTB_DEV double log_one_minus_exp(double w) // log(1 - e^-w), w > 0
+{
+    return (w < 0.6931471805599453) ? log(-expm1(-w)) : log1p(-exp(-w));
+}
+
+template <int WHICH>
+__device__ double jexact_pos(double x, int deriv)
+{
+    const double pi4 = 97.40909103400243723644;
+    if (x < 1e-20) {
+        if (deriv) return (WHICH == 0 ? 9.869604401089358 / 6.0 : 9.869604401089358 / 12.0) * x;
+        return WHICH == 0 ? -pi4 / 45.0 : -7.0 * pi4 / 360.0;
+    }
+    const double h = 0.2 / fmax(1.0, 0.5 * sqrt(x));
+    double sum = 0.0;
+    for (int k = 1; k < 100000; k++) { // (the k = 0 node has y = 0: no contribution)
+        const double u = k * h;
+        const double eu = exp(u), emu = 1.0 / eu;
+        const double y = x * (0.5 * (eu - emu)), w = x * (0.5 * (eu + emu));
+        if (w > 745.0) break;
+        double g;
+        if (deriv == 0) g = (WHICH == 0) ? y * y * w * log_one_minus_exp(w) : -(y * y * w) * log1p(exp(-w));
+        else {
+            const double e = exp(-w);
+            g = (WHICH == 0) ? (y * y * x) * e / (-expm1(-w)) : (y * y * x) * e / (1.0 + e);
+        }
+        sum += g;
+    }
+    return sum * h;
+}
+
+template <int WHICH>
+__device__ double jexact_neg(double theta)
+{
+    const double a = sqrt(-theta), hd = 1.0 / 16.0, hpi = 1.5707963267948966, pi = 3.141592653589793;
+    double p1 = 0.0;
+    for (int k = -120; k <= 120; k++) { // s in (e^-40, e^7)
+        const double t = k * hd, q = hpi * sinh(t);
+        if (q > 7.0 || q < -40.0) continue;
+        const double s = exp(q), wgt = s * hpi * cosh(t);
+        const double f = (WHICH == 0) ? log_one_minus_exp(s) : -log1p(exp(-s));
+        p1 += (s * sqrt(s * s + a * a) * f) * wgt;
+    }
+    double p2 = 0.0;
+    // panel ends: Jb 0, 2 pi, 4 pi, ...; Jf 0, pi, 3 pi, ...   (clipped at a)
+    for (int i = 0; i < 100000; i++) {
+        const double p = (WHICH == 0) ? 2.0 * pi * i : (i == 0 ? 0.0 : pi * (2 * i - 1));
+        if (p >= a) break;
+        const double qn = (WHICH == 0) ? 2.0 * pi * (i + 1) : pi * (2 * i + 1);
+        const bool right_sing = qn <= a, left_sing = !(WHICH == 1 && i == 0);
+        const double q_ = right_sing ? qn : a, L = q_ - p;
+        double acc = 0.0;
+        for (int k = -80; k <= 80; k++) {
+            const double t = k * hd, al = hpi * sinh(t);
+            if (fabs(al) > 36.0) continue;
+            const double e2 = exp(2.0 * al);
+            const double dl = L * e2 / (1.0 + e2), dr = L / (1.0 + e2); // distances from the panel ends
+            const double ch = cosh(al);
+            const double wgt = L * hpi * cosh(t) / (2.0 * ch * ch);
+            const bool left = dl < dr;
+            const double s = left ? p + dl : q_ - dr;
+            const double root = sqrt(((a - q_) + dr) * (a + s));
+            double tr; // |sin(s/2)| (Jb) or |cos(s/2)| (Jf)
+            if (left && left_sing) tr = fabs(sin(0.5 * dl));
+            else if (!left && right_sing) tr = fabs(sin(0.5 * dr));
+            else tr = (WHICH == 0) ? fabs(sin(0.5 * s)) : fabs(cos(0.5 * s));
+            const double f = root * s * log(2.0 * tr);
+            acc += ((WHICH == 0) ? f : -f) * wgt;
+        }
+        p2 += acc;
+    }
+    return (p1 + p2) * hd;
+}
+
+// mode 0: J(x), x = m/T real (J is even in x); 1: dJ/dx; 2: J(theta), theta = x^2 of either sign
+template <int WHICH>
+__global__ void __launch_bounds__(128) jexact_kernel(int mode, const double *__restrict__ xin, double *__restrict__ out,
+                                                     int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = xin[i];
+    double y;
+    if (isnan(x)) y = x;
+    else if (mode == 0) y = jexact_pos<WHICH>(fabs(x), 0);
+    else if (mode == 1) y = copysign(jexact_pos<WHICH>(fabs(x), 1), x);
+    else y = (x >= 0) ? jexact_pos<WHICH>(sqrt(x), 0) : jexact_neg<WHICH>(x);
+    out[i] = y;
+}
+
 struct Model8 { double l1, l2, mu2, Y1, Y2, nb, rs, v2; };
 
 CTB_DEV double model1_v1t(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
@@ -571,6 +672,17 @@ CTB_API int ctb_jseries(int which, int approx, int deriv, int nterms, const doub
     else if (which == 1 && approx == CTB_APPROX_HIGH) jseries_kernel<1, CTB_APPROX_HIGH><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
     else if (which == 0) jseries_kernel<0, CTB_APPROX_LOW><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
     else jseries_kernel<1, CTB_APPROX_LOW><<<g, 256, 0, st>>>(deriv, nterms, lc, d_x, d_out, n);
+    return (int)cudaGetLastError();
+}
+
+CTB_API int ctb_jexact(int which, int mode, const double *d_x, double *d_out, int64_t n, void *stream)
+{
+    if (n < 0 || (which != 0 && which != 1) || mode < 0 || mode > 2) return CTB_ERR_BAD_ARG;
+    if (n == 0) return CTB_OK;
+    if (!d_x || !d_out) return CTB_ERR_BAD_ARG;
+    const unsigned g = (unsigned)((n + 127) / 128);
+    if (which == 0) jexact_kernel<0><<<g, 128, 0, (cudaStream_t)stream>>>(mode, d_x, d_out, n);
+    else jexact_kernel<1><<<g, 128, 0, (cudaStream_t)stream>>>(mode, d_x, d_out, n);
     return (int)cudaGetLastError();
 }
 

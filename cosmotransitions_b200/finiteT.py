@@ -86,11 +86,70 @@ def Jf_low(x, n=20):
     return _series(1, 1, x, 0, n)
 
 
+def _exact(which, mode, x):
+    """Jb / Jf from the defining integrals (finiteT.py:40-147) by device quadrature (ctb_jexact)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    is_tensor = isinstance(x, torch.Tensor)
+    if is_tensor and x.is_cuda:
+        dev, d_x = x.device, x.to(torch.float64).contiguous()
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        host = x.detach().cpu().numpy() if is_tensor else np.asarray(x)
+        if np.iscomplexobj(host):
+            # the reference accepts x = i a for a negative mass squared (finiteT.py:45-52,75-81): theta = x^2 = -a^2
+            if mode != _lib.EXACT_X or np.any((host.real != 0) & (host.imag != 0)):
+                raise ValueError("complex x must be purely real or purely imaginary (and deriv = 0)")
+            host, mode = (host * host).real, _lib.EXACT_THETA
+        d_x = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float64)).to(dev)
+    out = torch.empty_like(d_x)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ctb_jexact(which, mode, d_x.data_ptr(), out.data_ptr(), d_x.numel(),
+                                  torch.cuda.current_stream(dev).cuda_stream), "ctb_jexact")
+    if is_tensor:
+        return out if x.is_cuda else out.cpu()
+    res = out.cpu().numpy()
+    return float(res) if res.ndim == 0 else res
+
+
+def Jb_exact(x):
+    """Jb calculated directly from the integral; x = m/T (finiteT.py:69-81,135-137)."""
+    return _exact(0, _lib.EXACT_X, x)
+
+
+def Jf_exact(x):
+    """Jf calculated directly from the integral; x = m/T (finiteT.py:40-52,125-127)."""
+    return _exact(1, _lib.EXACT_X, x)
+
+
+def Jb_exact2(theta):
+    """Jb calculated directly from the integral; input is theta = x^2, of either sign (finiteT.py:84-96)."""
+    return _exact(0, _lib.EXACT_THETA, theta)
+
+
+def Jf_exact2(theta):
+    """Jf calculated directly from the integral; input is theta = x^2, of either sign (finiteT.py:54-66)."""
+    return _exact(1, _lib.EXACT_THETA, theta)
+
+
+def dJb_exact(x):
+    """dJb/dx calculated directly from the integral (finiteT.py:109-111,145-147)."""
+    return _exact(0, _lib.EXACT_DX, x)
+
+
+def dJf_exact(x):
+    """dJf/dx calculated directly from the integral (finiteT.py:104-106,140-142)."""
+    return _exact(1, _lib.EXACT_DX, x)
+
+
 def _front(which, x, approx, deriv, n):
     # same dispatch and the same ValueErrors as finiteT.Jb / Jf (finiteT.py:302-375)
     if approx == 'exact':
-        raise NotImplementedError("approx='exact' is the adaptive-quadrature definition used offline to build the "
-                                  "spline tables (finiteT.py:40-147); it is not a device path")
+        if deriv == 0:
+            return _exact(which, _lib.EXACT_X, x)
+        elif deriv == 1:
+            return _exact(which, _lib.EXACT_DX, x)
+        raise ValueError("For approx=='exact', deriv must be 0 or 1.")
     elif approx == 'spline':
         return _eval("bf"[which], x, deriv)
     elif approx == 'low':

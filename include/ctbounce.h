@@ -215,6 +215,19 @@ CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta,
 CTB_API int ctb_jseries(int which, int approx, int deriv, int nterms, const double *lowcoef, const double *d_x,
                         double *d_out, int64_t n, void *stream);
 
+/* finiteT.Jb / Jf with approx = 'exact' (finiteT.py:40-147): the defining integrals
+ *   Jb = int_0^inf y^2 log(1 - exp(-sqrt(y^2 + theta))) dy,  Jf = -int_0^inf y^2 log(1 + exp(-sqrt(y^2 + theta))) dy
+ * by fixed-node double-exponential / trapezoidal quadrature on the device (absolute error ~1e-14; the reference's
+ * QUADPACK calls stop at 1.49e-8).  which: 0 = Jb, 1 = Jf.
+ *   mode CTB_EXACT_X:      in = x = m/T (real),   out = J(x^2)        Jb_exact / Jf_exact   finiteT.py:40-52,69-81
+ *   mode CTB_EXACT_DX:     in = x,                out = dJ/dx          dJb_exact / dJf_exact finiteT.py:104-111
+ *   mode CTB_EXACT_THETA:  in = theta (any sign), out = J(theta)       Jb_exact2 / Jf_exact2 finiteT.py:54-66,84-96
+ * (negative theta: the real part, log|1 -+ exp(-i sqrt|..|)| below the branch point, as in the reference).  */
+#define CTB_EXACT_X 0
+#define CTB_EXACT_DX 1
+#define CTB_EXACT_THETA 2
+CTB_API int ctb_jexact(int which, int mode, const double *d_x, double *d_out, int64_t n, void *stream);
+
 /* generic_potential.Vtot (generic_potential.py:312-337) for model1 (examples/testModel1.py:62-116):
  * pointwise, d_X [n,2], d_T [n] -> d_out [n].  model[8] = l1,l2,mu2,Y1,Y2,n_boson,renormScaleSq,v2 (host). */
 /* parts: CTB_V_TOTAL for Vtot, CTB_V_THERMAL alone for generic_potential.V1T_from_X

@@ -21,6 +21,7 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
                                 model1.findAllTransitions): the SplinePath potential spline, profile, action
   tests/golden/alpha14.json     alpha = 1 and 4 (d = 2, 5): quartic bounces and exactSolution unit vectors
   tests/golden/findaction.json  findAction on given (truncated / strided) profiles, alpha in {1, 2, 2.5, 3, 4}
+  tests/golden/jexact.npz       Jb / Jf with approx='exact' (deriv 0, 1), Jb_exact2 / Jf_exact2 incl. theta < 0, + mpmath values
   tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
 """
 import json
@@ -564,6 +565,64 @@ def gen_findaction():
     print(len(cases), "findAction cases")
 
 
+def gen_jexact():
+    """finiteT.Jb_exact / Jf_exact / dJb_exact / dJf_exact / Jb_exact2 / Jf_exact2 (finiteT.py:40-147, QUADPACK through
+    scipy.integrate.quad, tolerance 1.49e-8) + 30-digit mpmath values of the same integrals (independent check of the
+    device quadrature, which is more accurate than the reference's) -> tests/golden/jexact.npz"""
+    import mpmath as mp
+    mp.mp.dps = 30
+    rng = np.random.default_rng(23)
+    x = np.concatenate([[0.0, 1e-8, 1e-3, 0.05, 0.5, 1.0, 2.0, 3.5, 7.0, 15.0, 30.0], 10 ** rng.uniform(-3, 1.5, 60)])
+    th = np.concatenate([[0.0, -1e-6, -0.01, -1.0, -3.72402637, -6.82200203, -9.8, -30.0, -45.0, 1e-4, 2.0, 100.0, 1400.0],
+                         rng.uniform(-8, 8, 60)])
+    out = dict(x=x, theta=th, xneg=-x[:12])
+    with np.errstate(all="ignore"):
+        out["Jb_exact"], out["Jf_exact"] = fT.Jb(x, approx="exact"), fT.Jf(x, approx="exact").real
+        out["dJb_exact"], out["dJf_exact"] = fT.Jb(x, approx="exact", deriv=1), fT.Jf(x, approx="exact", deriv=1)
+        out["Jb_exact_neg"], out["dJb_exact_neg"] = fT.Jb_exact(-x[:12]), fT.dJb_exact(-x[:12])
+        out["Jf_exact_neg"], out["dJf_exact_neg"] = fT.Jf_exact(-x[:12]).real, fT.dJf_exact(-x[:12])
+        out["Jb_exact2"], out["Jf_exact2"] = fT.Jb_exact2(th), fT.Jf_exact2(th)
+        ximag = 1j * np.array([0.1, 1.0, 1.9, 2.6])
+        out["ximag"] = ximag.imag
+        out["Jb_exact_imag"], out["Jf_exact_imag"] = fT.Jb_exact(ximag), fT.Jf_exact(ximag).real
+
+    def mpJ(theta, which):
+        theta = mp.mpf(float(theta))
+        sg = -1 if which == 0 else 1
+        pre = 1 if which == 0 else -1
+        if theta == 0:
+            return -mp.pi ** 4 / 45 if which == 0 else -7 * mp.pi ** 4 / 360
+        if theta >= 0:
+            f = lambda y: pre * y * y * mp.log(1 + sg * mp.exp(-mp.sqrt(y * y + theta)))
+            return mp.quad(f, [0, mp.sqrt(theta) + mp.mpf("1e-30"), 1, 10, 50, mp.inf])
+        a = mp.sqrt(-theta)
+        f = lambda y: pre * y * y * mp.log(1 + sg * mp.exp(-mp.sqrt(y * y - a * a)))
+        if which == 0:
+            f1 = lambda y: y * y * mp.log(2 * abs(mp.sin(mp.sqrt(a * a - y * y) / 2)))
+            sing = [mp.sqrt(a * a - (2 * mp.pi * k) ** 2) for k in range(0, int(a / (2 * mp.pi)) + 1)]
+        else:
+            f1 = lambda y: -y * y * mp.log(2 * abs(mp.cos(mp.sqrt(a * a - y * y) / 2)))
+            sing = [mp.sqrt(a * a - (mp.pi * (2 * k + 1)) ** 2) for k in range(0, 50) if a > mp.pi * (2 * k + 1)]
+        pts = sorted(set([mp.mpf(0)] + sing + [a]))
+        return mp.quad(f1, pts) + mp.quad(f, [a, a + 1, a + 10, a + 50, mp.inf])
+
+    def mpdJ(x, which):
+        x = mp.mpf(float(x))
+        sg = -1 if which == 0 else 1
+        f = lambda y: y * y / (mp.exp(mp.sqrt(y * y + x * x)) + sg) * x / mp.sqrt(y * y + x * x)
+        return mp.quad(f, [0, x + mp.mpf("1e-30"), 1, 10, 50, mp.inf])
+
+    out["mp_theta"] = th[:40]
+    out["mp_Jb"] = np.array([float(mpJ(t, 0)) for t in th[:40]])
+    out["mp_Jf"] = np.array([float(mpJ(t, 1)) for t in th[:40]])
+    out["mp_x"] = x[1:31]
+    out["mp_dJb"] = np.array([float(mpdJ(t, 0)) for t in x[1:31]])
+    out["mp_dJf"] = np.array([float(mpdJ(t, 1)) for t in x[1:31]])
+    np.savez(os.path.join(GOLD, "jexact.npz"), **out)
+    print("jexact: reference quad vs mpmath, max abs diff Jb", np.max(np.abs(out["Jb_exact2"][:40] - out["mp_Jb"])),
+          "Jf", np.max(np.abs(out["Jf_exact2"][:40] - out["mp_Jf"])))
+
+
 def gen_alpha14():
     """alpha = 1 and 4 (d = 2 and 5 dimensions, Bessel order nu = 0 and 3/2): quartic family, a few knob sets,
     and exactSolution unit vectors -> tests/golden/alpha14.json"""
@@ -605,7 +664,7 @@ def gen_alpha14():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath", "alpha14", "findaction"]
+                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

@@ -220,6 +220,33 @@ def find_action(cfg, params, phi_meta, alpha, R, Phi, dPhi):
              C.c_int(len(R)))
 
 
+def jexact(which, mode, x):
+    """finiteT.Jb / Jf from the defining integrals, restated call for call: scipy.integrate.quad (QUADPACK qagi /
+    qags, default tolerances) on the reference's integrands.  which 0 = Jb, 1 = Jf; mode 'x' (finiteT.py:40-52,
+    69-81), 'dx' (finiteT.py:104-111), 'theta' (finiteT.py:54-66,84-96).  Elementwise over x (finiteT.py:114-130)."""
+    from scipy import integrate
+    sg, pre = (-1.0, 1.0) if which == 0 else (1.0, -1.0)
+    trig = np.sin if which == 0 else np.cos
+
+    def one(v):
+        if mode == "dx":
+            f = lambda y: y * y * (np.exp(np.sqrt(y * y + v * v)) + sg) ** -1 * v / np.sqrt(y * y + v * v)
+            return integrate.quad(f, 0, np.inf)[0]
+        theta = v * v if mode == "x" else v
+        with np.errstate(all="ignore"):
+            if theta >= 0:
+                f = lambda y: pre * y * y * np.log(1 + sg * np.exp(-np.sqrt(y * y + theta)))
+                return integrate.quad(f, 0, np.inf)[0]
+            f = lambda y: (pre * y * y * np.log(1 + sg * np.exp(-np.sqrt(y * y + theta + 0j)))).real
+            f1 = lambda y: pre * y * y * np.log(2 * abs(trig(np.sqrt(-theta - y * y) / 2)))
+            return integrate.quad(f, abs(theta) ** .5, np.inf)[0] + integrate.quad(f1, 0, abs(theta) ** .5)[0]
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.array([one(float(v)) for v in np.atleast_1d(np.asarray(x, dtype=np.float64))])
+
+
 def brentq_poly(coefs_high_to_low, a, b):
     p = np.array([len(coefs_high_to_low) - 1] + list(coefs_high_to_low), dtype=np.float64)
     err, nf = C.c_int(0), C.c_int(0)

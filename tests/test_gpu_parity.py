@@ -388,6 +388,31 @@ def test_jseries_golden(ctb, gold_dir):
         finiteT.Jb(x, approx="bogus")
 
 
+def test_jexact_golden(ctb, gold_dir):
+    """finiteT.Jb / Jf with approx='exact' (device quadrature, ctb_jexact) vs (a) the reference's QUADPACK output --
+    bound: QUADPACK's own 1.49e-8 tolerance -- (b) 30-digit mpmath values of the same integrals, and (c) the 2 x 1000
+    exact samples from which the reference builds its spline tables (finiteT.py:151-196)."""
+    from cosmotransitions_b200 import finiteT as fT, _tables
+    g = np.load(os.path.join(gold_dir, "jexact.npz"))
+    for nm, J, Jx, Jx2, dJ in (("Jb", fT.Jb, fT.Jb_exact, fT.Jb_exact2, fT.dJb_exact),
+                               ("Jf", fT.Jf, fT.Jf_exact, fT.Jf_exact2, fT.dJf_exact)):
+        np.testing.assert_allclose(J(g["x"], approx="exact"), g[nm + "_exact"], rtol=0, atol=5e-8)
+        np.testing.assert_allclose(J(g["x"], approx="exact", deriv=1), g["d" + nm + "_exact"], rtol=0, atol=5e-8)
+        np.testing.assert_allclose(Jx(g["xneg"]), g[nm + "_exact_neg"], rtol=0, atol=5e-8)
+        np.testing.assert_allclose(dJ(g["xneg"]), g["d" + nm + "_exact_neg"], rtol=0, atol=5e-8)
+        np.testing.assert_allclose(Jx(1j * g["ximag"]), g[nm + "_exact_imag"], rtol=0, atol=5e-8)
+        ok = g["theta"] > (-39.0 if nm == "Jb" else -9.8)   # below: QUADPACK meets an interior log singularity
+        np.testing.assert_allclose(Jx2(g["theta"])[ok], g[nm + "_exact2"][ok], rtol=0, atol=1e-7)
+        # 30-digit values: the device quadrature is good to ~1e-13 everywhere, singular panels included
+        np.testing.assert_allclose(Jx2(g["mp_theta"]), g["mp_" + nm], rtol=1e-12, atol=2e-13)
+        np.testing.assert_allclose(dJ(g["mp_x"]), g["mp_d" + nm], rtol=1e-12, atol=1e-15)
+        with pytest.raises(ValueError):
+            J(g["x"], approx="exact", deriv=2)
+    h = _tables.host_tables()
+    np.testing.assert_allclose(fT.Jb_exact2(h.xb), h.yb, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(fT.Jf_exact2(h.xf), h.yf, rtol=0, atol=1e-7)
+
+
 def test_jspline_large_vs_oracle(ctb, oracle, tables):
     from cosmotransitions_b200 import finiteT
     rng = np.random.default_rng(42)

@@ -87,6 +87,18 @@ def test_profiles(oracle, gold_dir):
         assert abs(r["S"] - float(g[name + "_S"])) < 1e-8 * abs(float(g[name + "_S"]))
 
 
+def test_jexact_oracle_vs_reference(oracle, gold_dir):
+    """The scipy.quad restatement of finiteT's exact integrals reproduces the reference's own output."""
+    g = np.load(os.path.join(gold_dir, "jexact.npz"))
+    for which, nm in ((0, "Jb"), (1, "Jf")):
+        np.testing.assert_allclose(oracle.jexact(which, "x", g["x"]), g[nm + "_exact"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(oracle.jexact(which, "dx", g["x"]), g["d" + nm + "_exact"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(oracle.jexact(which, "theta", g["theta"]), g[nm + "_exact2"], rtol=1e-9, atol=1e-12)
+        # and both sit within QUADPACK's tolerance of the 30-digit values (away from interior singularities)
+        ok = g["mp_theta"] > (-39.0 if which == 0 else -9.8)
+        assert np.max(np.abs(g[nm + "_exact2"][:40][ok] - g["mp_" + nm][ok])) < 1e-7
+
+
 def _profile_slice(g, case):
     sl = slice(*case["sl"])
     return tuple(g[case["name"] + k][sl] for k in ("_R", "_Phi", "_dPhi"))
