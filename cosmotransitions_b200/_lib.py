@@ -23,7 +23,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
  ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN) = range(11)
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
-           "ctb_bounce_setup", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
+           "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
            "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
 
 
@@ -38,6 +38,12 @@ class Opts(C.Structure):
                 ("rmax", C.c_double), ("phi_eps", C.c_double), ("xguess", C.c_double), ("npoints", C.c_int32),
                 ("max_interior_pts", C.c_int32), ("alpha", C.c_int32), ("block_threads", C.c_int32),
                 ("kernel", C.c_int32), ("reserved", C.c_int32)]
+
+
+class WallOpts(C.Structure):
+    _fields_ = [("Fguess", C.c_double), ("Ftol", C.c_double), ("phitol", C.c_double), ("rmin", C.c_double),
+                ("rmax", C.c_double), ("phi0_rel", C.c_double), ("phi_eps", C.c_double), ("npoints", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class BounceIn(C.Structure):
@@ -107,6 +113,9 @@ def load():
     lib.ctb_minimize_1d.restype = C.c_int
     lib.ctb_minimize_1d.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                     C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ctb_wall_batch.restype = C.c_int
+    lib.ctb_wall_batch.argtypes = [C.c_int, C.POINTER(BounceIn), C.POINTER(WallOpts), C.POINTER(JTable),
+                                   C.POINTER(JTable), C.POINTER(BounceOut), C.c_void_p]
     lib.ctb_find_action.restype = C.c_int
     lib.ctb_find_action.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,

@@ -138,6 +138,48 @@ def bounce_setup(kind, params, phi_absMin, phi_metaMin, phi_bar=None, rscale=Non
     return int(out["status"][0]), float(out["phi_bar"][0]), float(out["rscale"][0])
 
 
+def find_wall_batch(potential_kind, params, phi_absMin, phi_metaMin, phi_eps=1e-3, device=None, return_profiles=False,
+                    Fguess=None, Ftol=1e-4, phitol=1e-4, npoints=500, rmin=1e-4, rmax=1e4, phi0_rel=1e-3):
+    """WallWithConstFriction(...).findProfile(...) (tunneling1D.py:829-999) for N independent instances.
+
+    Returns a dict of tensors: F (the friction that lets the wall interpolate between the minima), rf, phi0, phi_bar,
+    rscale, status, n_shots, n_rkck, n_points and, if return_profiles, R / Phi / dPhi [N, npoints]."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    kind = getattr(potential_kind, "kind", potential_kind)
+    if kind not in _lib.NPARAM:
+        raise ValueError("unknown potential kind %r" % (potential_kind,))
+    on_host = not (isinstance(params, torch.Tensor) and params.is_cuda)
+    if device is None:
+        device = params.device if not on_host else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    d_params = _as_device(torch, params, device).reshape(-1, _lib.NPARAM[kind])
+    n = d_params.shape[0]
+    d_abs, d_meta = _as_device(torch, phi_absMin, device, (n,)), _as_device(torch, phi_metaMin, device, (n,))
+    o = _lib.WallOpts()
+    o.Fguess = math.nan if Fguess is None else float(Fguess)
+    o.Ftol, o.phitol, o.rmin, o.rmax, o.phi0_rel, o.phi_eps = Ftol, phitol, rmin, rmax, phi0_rel, phi_eps
+    o.npoints = int(npoints)
+    out = alloc_out(torch, n, device)
+    prof = None
+    if return_profiles:
+        prof = {k: torch.full((n, o.npoints), float("nan"), dtype=torch.float64, device=device)
+                for k in ("R", "Phi", "dPhi")}
+    tabs = _tables.device_tables(device) if kind in _lib.THERMAL_KINDS else None
+    if n:
+        with torch.cuda.device(device):
+            _lib.check(lib.ctb_wall_batch(kind, _bounce_in(d_params, d_abs, d_meta), o, tabs.jb if tabs else None,
+                                          tabs.jf if tabs else None, _bounce_out(out, prof),
+                                          torch.cuda.current_stream(device).cuda_stream), "ctb_wall_batch")
+    out["F"] = out.pop("x")
+    del out["S"]
+    if prof is not None:
+        out.update(prof)
+    if on_host:
+        out = {k: v.cpu() for k, v in out.items()}
+    return out
+
+
 def find_action_batch(potential_kind, params, phi_metaMin, R, Phi, dPhi, n_points=None, alpha=2, device=None):
     """SingleFieldInstanton.findAction(profile) (tunneling1D.py:763-791) for N given profiles.
 

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include "ctb_device.cuh"
 #include "ctb_bounce.cuh"
+#include "ctb_wall.cuh"
 
 using namespace ctb;
 
@@ -764,6 +765,36 @@ CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtab
     if (n == 0) return CTB_OK;
     if (!d_params || !d_lo || !d_hi || !d_xmin) return CTB_ERR_BAD_ARG;
     return launch_rows<true>(pot_kind, d_params, jb, jf, d_lo, d_hi, xtol_rel, d_xmin, d_vmin, n, (cudaStream_t)stream);
+}
+
+CTB_API int ctb_wall_batch(int pot_kind, const ctb_bounce_in *in, const ctb_wall_opts *o, const ctb_jtable *jb,
+                           const ctb_jtable *jf, const ctb_bounce_out *out, void *stream)
+{
+    if (!in || !out || !o || in->n < 0) return CTB_ERR_BAD_ARG;
+    if (in->n == 0) return CTB_OK;
+    if (!in->d_params || !in->d_phi_abs || !in->d_phi_meta) return CTB_ERR_BAD_ARG;
+    if (o->npoints < 2 || o->npoints > 4096) return CTB_ERR_UNSUPPORTED;
+    if (out->d_prof_R && (!out->d_prof_Phi || !out->d_prof_dPhi || out->prof_stride < o->npoints)) return CTB_ERR_BAD_ARG;
+    WallArgs a;
+    a.params = in->d_params; a.phi_abs = in->d_phi_abs; a.phi_meta = in->d_phi_meta; a.n = in->n;
+    a.knobs = WallKnobs{o->Fguess, o->Ftol, o->phitol, o->rmin, o->rmax, o->phi0_rel, o->phi_eps, o->npoints};
+    a.jb = to_jtab(jb); a.jf = to_jtab(jf);
+    a.out = *out;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pot_kind) {
+    case CTB_POT_POLY4: return ctb::launch_wall_poly4(a, st);
+    case CTB_POT_SPLINE: return ctb::launch_wall_spline(a, st);
+    case CTB_POT_THERMAL1F:
+        if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
+        return ctb::launch_wall_thermal1f(a, st);
+    case CTB_POT_MODEL1_LINE:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        return ctb::launch_wall_model1_line(a, st);
+    case CTB_POT_MODEL1F:
+        if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+        return ctb::launch_wall_model1f(a, st);
+    }
+    return CTB_ERR_UNSUPPORTED;
 }
 
 CTB_API int ctb_find_action(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,

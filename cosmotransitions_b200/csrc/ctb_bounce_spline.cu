@@ -1,5 +1,6 @@
 // bounce kernel instantiation for the PotSpline potential functor (see ctb_bounce.cuh)
 #include "ctb_bounce.cuh"
+#include "ctb_wall.cuh"
 
 namespace ctb {
 int launch_bounce_spline(const BounceArgs &a, int alpha, int block, cudaStream_t st)
@@ -11,4 +12,5 @@ int launch_bounce_warp_spline(const BounceArgs &a, int alpha, int stage_cap, cud
 {
     return launch_bounce_warp_any<PotSpline>(a, alpha, stage_cap, st);
 }
+int launch_wall_spline(const WallArgs &a, cudaStream_t st) { return launch_wall_any<PotSpline>(a, st); }
 } // namespace ctb

@@ -1,5 +1,6 @@
 // bounce kernel instantiation for the PotThermal1F potential functor (see ctb_bounce.cuh)
 #include "ctb_bounce.cuh"
+#include "ctb_wall.cuh"
 
 namespace ctb {
 int launch_bounce_thermal1f(const BounceArgs &a, int alpha, int block, cudaStream_t st)
@@ -11,4 +12,5 @@ int launch_bounce_warp_thermal1f(const BounceArgs &a, int alpha, int stage_cap, 
 {
     return launch_bounce_warp_any<PotThermal1F>(a, alpha, stage_cap, st);
 }
+int launch_wall_thermal1f(const WallArgs &a, cudaStream_t st) { return launch_wall_any<PotThermal1F>(a, st); }
 } // namespace ctb

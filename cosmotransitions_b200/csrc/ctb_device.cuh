@@ -742,10 +742,13 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
     return make_double2(phi, dphi);
 }
 
+#define CTB_ALPHA_WALL (-1) // WallWithConstFriction (T1D:829-999): friction term F phi' instead of (alpha / r) phi'
+
 template <class Pot, int ALPHA>
 struct Sfi {
     Pot pot;
     double phi_abs, phi_meta, phi_eps, inv_12eps;
+    double friction; // used by ALPHA == CTB_ALPHA_WALL only
     int n_rkck;
     CTB_DEV void set_phi_eps(double e) { phi_eps = e; inv_12eps = 1.0 / (12. * e); }
 
@@ -823,7 +826,8 @@ struct Sfi {
     CTB_DEV void eom(double y0, double y1, double r, double &f0, double &f1) const
     {
         f0 = y1;
-        f1 = fma(-CTB_MUL((double)ALPHA, y1), rcp_fast(r), dV(y0));
+        if constexpr (ALPHA == CTB_ALPHA_WALL) f1 = fma(-friction, y1, dV(y0)); // T1D:912-916
+        else f1 = fma(-CTB_MUL((double)ALPHA, y1), rcp_fast(r), dV(y0));
     }
 
     // HF:204-236 Cash-Karp step

@@ -134,3 +134,47 @@ class SingleFieldInstanton:
             from scipy import interpolate
             dp = interpolate.splev(p, interpolate.splrep(phi[i], dphi[i], k=k))
         return p, dp
+
+
+class WallWithConstFriction(SingleFieldInstanton):
+    """GPU-backed counterpart of tunneling1D.WallWithConstFriction (tunneling1D.py:829-999): the bubble-wall
+    profile with a constant friction term, phi'' + F phi' = V'(phi), found by over/undershooting in F.
+    Same constructor as SingleFieldInstanton; rscale comes from the quadratic fit of the overridden findRScale
+    (tunneling1D.py:838-864); findProfile returns Profile1D(R, Phi, dPhi, F, Rerr)."""
+
+    profile_rval = namedtuple("Profile1D", "R Phi dPhi F Rerr")
+
+    def __init__(self, phi_absMin, phi_metaMin, V, dV=None, d2V=None, phi_eps=1e-3, alpha=2, phi_bar=None,
+                 rscale=None):
+        if not isinstance(V, DevicePotential):
+            from .potentials import SplinePotential
+            V = SplinePotential.from_callable(V) or V
+        if not isinstance(V, DevicePotential):
+            raise TypeError("V must be a cosmotransitions_b200.potentials.DevicePotential (device functor); "
+                            "arbitrary Python callables cannot run on the GPU and there is no CPU fallback")
+        if phi_bar is not None or rscale is not None:
+            raise NotImplementedError("phi_bar / rscale overrides are not wired for WallWithConstFriction")
+        self.phi_absMin, self.phi_metaMin = float(phi_absMin), float(phi_metaMin)
+        self.V = V
+        self.alpha = alpha   # unused by the wall's equation of motion; findAction (inherited) still reads it
+        self._phi_eps_rel = phi_eps
+        self.phi_eps = phi_eps * abs(self.phi_absMin - self.phi_metaMin)
+        self._last = None
+        # __init__ of the reference validates the potential (tunneling1D.py:133-147): a two-point profile is the
+        # cheapest call that runs exactly that code on the device
+        r = batch.find_wall_batch(V.kind, V.params[None, :], [self.phi_absMin], [self.phi_metaMin], phi_eps=phi_eps,
+                                  npoints=2)
+        self.phi_bar, self.rscale = float(r["phi_bar"][0]), float(r["rscale"][0])
+        if int(r["status"][0]) in (_lib.ST_STABLE, _lib.ST_NO_BARRIER):
+            if int(r["status"][0]) == _lib.ST_NO_BARRIER:
+                raise PotentialError("Cannot fit the potential to a negative quadratic.", "no barrier")
+            raise_for_status(r["status"][0])
+
+    def findProfile(self, Fguess=None, Ftol=1e-4, phitol=1e-4, npoints=500, rmin=1e-4, rmax=1e4, phi0_rel=1e-3):
+        r = batch.find_wall_batch(self.V.kind, self.V.params[None, :], [self.phi_absMin], [self.phi_metaMin],
+                                  phi_eps=self._phi_eps_rel, return_profiles=True, Fguess=Fguess, Ftol=Ftol, phitol=phitol,
+                                  npoints=npoints, rmin=rmin, rmax=rmax, phi0_rel=phi0_rel)
+        raise_for_status(r["status"][0])
+        n = int(r["n_points"][0])
+        return self.profile_rval(r["R"][0, :n].numpy().copy(), r["Phi"][0, :n].numpy().copy(),
+                                 r["dPhi"][0, :n].numpy().copy(), float(r["F"][0]), None)

@@ -184,6 +184,26 @@ CTB_API int ctb_device_ok(void);
 CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_opts *opts, const ctb_jtable *jb,
                              const ctb_jtable *jf, const ctb_bounce_out *out, void *stream);
 
+/* WallWithConstFriction(phi_absMin, phi_metaMin, V, dV, d2V, phi_eps).findProfile(Fguess, Ftol, phitol, npoints,
+ * rmin, rmax, phi0_rel) (tunneling1D.py:829-999) for n instances: the wall profile phi'' + F phi' = V'(phi) between the
+ * two minima, found by over/undershooting in the constant friction F; rscale from the quadratic fit of
+ * WallWithConstFriction.findRScale (tunneling1D.py:838-864).  Uses in->d_params / d_phi_abs / d_phi_meta / n only.
+ * Outputs (ctb_bounce_out): d_x = F, d_phi0 = phi(r = 0), d_r0 = 0, d_rf, d_phi_bar, d_rscale, d_status, d_n_shots,
+ * d_n_rkck, d_n_points (= npoints) and the optional profile dump; d_S is not written.                          */
+typedef struct ctb_wall_opts {
+    double Fguess;   /* NaN = None: Delta_V rscale / delta_phi^2 (tunneling1D.py:965-969) */
+    double Ftol;     /* 1e-4, relative to the first F */
+    double phitol;   /* 1e-4 */
+    double rmin;     /* 1e-4 (relative to rscale) */
+    double rmax;     /* 1e4  (relative to rscale) */
+    double phi0_rel; /* 1e-3 */
+    double phi_eps;  /* 1e-3 (relative to |phi_absMin - phi_metaMin|) */
+    int32_t npoints; /* 500; 2 <= npoints <= 4096 */
+    int32_t reserved;
+} ctb_wall_opts;
+CTB_API int ctb_wall_batch(int pot_kind, const ctb_bounce_in *in, const ctb_wall_opts *opts, const ctb_jtable *jb,
+                           const ctb_jtable *jf, const ctb_bounce_out *out, void *stream);
+
 /* SingleFieldInstanton.findAction(profile) (tunneling1D.py:763-791) for n given profiles: row i of d_R / d_Phi /
  * d_dPhi ([n, stride], row-major) holds d_npts[i] points of Profile1D.R / .Phi / .dPhi; S_i = simpson of
  * (phi'^2/2 + V_i(phi) - V_i(phi_meta_i)) Omega_alpha r^alpha over the non-uniform R (scipy.integrate.simpson's

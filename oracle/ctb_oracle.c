@@ -300,6 +300,8 @@ typedef struct {
     pot_t pot;
     double phi_absMin, phi_metaMin, phi_bar, rscale, phi_eps; /* phi_eps already rescaled */
     int alpha;
+    int wall;        /* WallWithConstFriction: equation of motion with a constant friction term */
+    double friction;
     /* counters */
     int n_rkck, n_exact;
 } sfi_t;
@@ -713,7 +715,8 @@ static int initial_conditions(sfi_t *s, double delta_phi0, double rmin, double d
 static void eom(sfi_t *s, const double y[2], double r, double out[2])
 {
     out[0] = y[1];
-    out[1] = sfi_dV(s, y[0]) - s->alpha * y[1] / r;
+    if (s->wall) out[1] = sfi_dV(s, y[0]) - s->friction * y[1]; /* tunneling1D.py:912-916 */
+    else out[1] = sfi_dV(s, y[0]) - s->alpha * y[1] / r;
 }
 
 /* helper_functions.py:204-236 */
@@ -918,6 +921,7 @@ static int sfi_setup(sfi_t *s, const pot_t *pot, double phi_absMin, double phi_m
     s->phi_absMin = phi_absMin; s->phi_metaMin = phi_metaMin;
     s->n_rkck = s->n_exact = 0;
     s->alpha = o->alpha;
+    s->wall = 0; s->friction = 0.0;
     s->phi_eps = 0; s->phi_bar = NAN; s->rscale = NAN;
     if (pot_V(pot, phi_metaMin) <= pot_V(pot, phi_absMin)) return ST_STABLE;
     if (isnan(phi_bar_in)) {
@@ -1313,6 +1317,100 @@ CTBO_API void ctbo_potential_rows(const ctbo_config *cfg, const double *params, 
         pot_t pot = {cfg->kind, params + i * cfg->nparam, &jb, &jf};
         out[i] = pot_V(&pot, phi[i]);
     }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* WallWithConstFriction (tunneling1D.py:829-999): findRScale by a quadratic fit (:838-864), start at r = 0 on the
+ * exponential solution near phi_absMin (:866-910), shooting in the friction F (:960-990), dense output (:992-997).
+ * dout = F, rf, phi_bar, rscale, phi0, dphi0 ; iout = status, n_shots, n_rkck, n_points                          */
+CTBO_API void ctbo_wall_one(const ctbo_config *cfg, const double *params, double phi_absMin, double phi_metaMin,
+                            double Fguess, double Ftol, double phi0_rel, double *dout, int *iout, double *prof_R,
+                            double *prof_Phi, double *prof_dPhi, int prof_cap)
+{
+    opts_t o; spline_t jb, jf;
+    cfg_to(cfg, &o, &jb, &jf);
+    pot_t pot = {cfg->kind, params, &jb, &jf};
+    sfi_t S_, *s = &S_;
+    for (int i = 0; i < 6; i++) dout[i] = NAN;
+    iout[0] = ST_BAD_ARG; iout[1] = iout[2] = iout[3] = 0;
+    memset(s, 0, sizeof(*s));
+    s->pot = pot; s->phi_absMin = phi_absMin; s->phi_metaMin = phi_metaMin;
+    s->alpha = o.alpha; s->wall = 1;
+    /* __init__ (tunneling1D.py:128-149) with the overridden findRScale */
+    if (pot_V(&pot, phi_metaMin) <= pot_V(&pot, phi_absMin)) { iout[0] = ST_STABLE; return; }
+    {
+        double phi_tol = fabs(phi_metaMin - phi_absMin) * 1e-12;
+        double V_phimeta = pot_V(&pot, phi_metaMin);
+        double phi1 = phi_metaMin, phi2 = phi_absMin, phi0 = 0.5 * (phi1 + phi2);
+        while (fabs(phi1 - phi2) > phi_tol) {
+            double V0 = pot_V(&pot, phi0);
+            if (V0 > V_phimeta) phi1 = phi0; else phi2 = phi0;
+            phi0 = 0.5 * (phi1 + phi2);
+        }
+        s->phi_bar = phi0;
+    }
+    dout[2] = s->phi_bar;
+    {
+        double pA = phi_absMin, pB = 0.5 * (s->phi_bar + phi_metaMin), pC = phi_metaMin;
+        double yA = pot_V(&pot, pA), yB = pot_V(&pot, pB), yC = pot_V(&pot, pC);
+        double lmda = 2 * ((yA - yB) / (pA - pB) - (yB - yC) / (pB - pC)) / (pC - pA);
+        if (lmda <= 0.0) { iout[0] = ST_NO_BARRIER; return; }
+        s->rscale = M_PI / sqrt(lmda);
+    }
+    dout[3] = s->rscale;
+    s->phi_eps = o.phi_eps * fabs(phi_absMin - phi_metaMin);
+    int npoints = o.npoints;
+    if (npoints < 2 || npoints > MAXPTS) { iout[0] = ST_BAD_ARG; return; }
+    /* findProfile (tunneling1D.py:918-999) */
+    double rmin = o.rmin * s->rscale;
+    double dr0 = rmin, drmin = 0.01 * rmin, rmax = o.rmax * s->rscale;
+    double delta_phi = phi_metaMin - phi_absMin;
+    double epsabs[2] = {fabs(delta_phi * o.phitol), fabs(delta_phi / s->rscale * o.phitol)};
+    double epsfrac[2] = {o.phitol, o.phitol};
+    double Fmin = 0.0, Fmax = INFINITY, F;
+    if (!isnan(Fguess)) F = Fguess;
+    else {
+        double Delta_V = pot_V(&pot, phi_metaMin) - pot_V(&pot, phi_absMin);
+        F = Delta_V * s->rscale / (delta_phi * delta_phi);
+    }
+    Ftol *= F;
+    const double Fincrease = 5.0;
+    double rf = NAN, r0 = 0.0, y0[2] = {NAN, NAN}, yf[2];
+    int nshots = 0, ctype = -1, status = ST_XTOL;
+    double d2V_abs = sfi_d2V(s, phi_absMin);
+    for (;;) {
+        /* initialConditions (tunneling1D.py:866-910) */
+        double k = 0.5 * (sqrt(F * F + 4 * d2V_abs) - F);
+        r0 = 0.0;
+        y0[0] = phi_absMin + phi0_rel * (phi_metaMin - phi_absMin);
+        y0[1] = k * (y0[0] - phi_absMin);
+        s->friction = F;
+        int e = integrate_profile(s, r0, y0, dr0, epsfrac, epsabs, drmin, rmax, &rf, yf, &ctype);
+        if (e) { iout[0] = e; iout[1] = nshots; iout[2] = s->n_rkck; return; }
+        nshots++;
+        if (ctype == CT_CONVERGED) { status = ST_CONVERGED; break; }
+        else if (ctype == CT_UNDERSHOOT) { Fmax = F; F = (Fmin == 0.0) ? F / Fincrease : .5 * (Fmin + Fmax); }
+        else { Fmin = F; F = (Fmax == INFINITY) ? F * Fincrease : .5 * (Fmin + Fmax); }
+        if ((Fmax - Fmin) < Ftol) { status = ST_XTOL; break; }
+    }
+    /* second pass with the CURRENT F (tunneling1D.py:992-997) */
+    {
+        static __thread double R[MAXPTS], Phi[MAXPTS], dPhi[MAXPTS];
+        double step = (rf - r0) / (npoints - 1);
+        for (int i = 0; i < npoints; i++) R[i] = i * step + r0;
+        R[npoints - 1] = rf;
+        s->friction = F;
+        int e = integrate_and_save(s, R, npoints, y0, dr0, epsfrac, epsabs, drmin, Phi, dPhi);
+        if (e) { iout[0] = e; iout[1] = nshots; iout[2] = s->n_rkck; return; }
+        if (prof_R) {
+            int m = npoints < prof_cap ? npoints : prof_cap;
+            memcpy(prof_R, R, m * sizeof(double));
+            memcpy(prof_Phi, Phi, m * sizeof(double));
+            memcpy(prof_dPhi, dPhi, m * sizeof(double));
+        }
+    }
+    dout[0] = F; dout[1] = rf; dout[4] = y0[0]; dout[5] = y0[1];
+    iout[0] = status; iout[1] = nshots; iout[2] = s->n_rkck; iout[3] = npoints;
 }
 
 /* SingleFieldInstanton.findAction(profile) for a given profile (tunneling1D.py:763-791); alpha is a real number */

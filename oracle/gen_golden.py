@@ -22,6 +22,7 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
   tests/golden/alpha14.json     alpha = 1 and 4 (d = 2, 5): quartic bounces and exactSolution unit vectors
   tests/golden/findaction.json  findAction on given (truncated / strided) profiles, alpha in {1, 2, 2.5, 3, 4}
   tests/golden/jexact.npz       Jb / Jf with approx='exact' (deriv 0, 1), Jb_exact2 / Jf_exact2 incl. theta < 0, + mpmath values
+  tests/golden/wall.json        WallWithConstFriction.findProfile on the quartic family (F, rf, sampled profile, errors)
   tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
 """
 import json
@@ -623,6 +624,52 @@ def gen_jexact():
           "Jf", np.max(np.abs(out["Jf_exact2"][:40] - out["mp_Jf"])))
 
 
+def gen_wall():
+    """WallWithConstFriction.findProfile (tunneling1D.py:829-999) on the quartic family, default and non-default
+    knobs, error cases -> tests/golden/wall.json (profiles sampled every 20th point)"""
+    class Wall(t1.WallWithConstFriction):
+        nshots = 0
+
+        def integrateProfile(self, *a):
+            self.nshots += 1
+            return super().integrateProfile(*a)
+
+    cases = []
+    runs = [(c, {}) for c in (0.05, 0.1, 0.15, 0.2, 0.25, 0.3, 0.35, 0.4, 0.45, 0.48, 0.49, 0.499)]
+    runs += [(0.3, dict(phitol=1e-6, Ftol=1e-6)), (0.4, dict(npoints=201)), (0.25, dict(Fguess=0.5)),
+             (0.45, dict(phi0_rel=1e-2, rmin=1e-3)), (0.2, dict(rmax=2.0)), (0.35, dict(npoints=2))]
+    for c, kw in runs:
+        V, dV, d2V = quartic_lambdas(c)
+        _counts["rkck"] = 0
+        r = dict(c=float(c), coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0, phi_meta=0.0, opts=kw, error=None)
+        try:
+            w = Wall(1.0, 0.0, V, dV, d2V)
+            r.update(phi_bar=float(w.phi_bar), rscale=float(w.rscale))
+            p = w.findProfile(**kw)
+            r.update(F=float(p.F), rf=float(p.R[-1]), npts=int(len(p.R)), n_shots=w.nshots, n_rkck=_counts["rkck"],
+                     R=[float(x) for x in p.R[::20]], Phi=[float(x) for x in p.Phi[::20]],
+                     dPhi=[float(x) for x in p.dPhi[::20]], Phi_last=float(p.Phi[-1]), dPhi_last=float(p.dPhi[-1]))
+        except t1.PotentialError as e:
+            r["error"] = "PotentialError:" + e.args[1]
+        except hf.IntegrationError as e:
+            r["error"] = "IntegrationError:" + str(e.args[0])
+        cases.append(r)
+        print("wall", c, kw, {q: r.get(q) for q in ("F", "rf", "n_shots", "n_rkck", "error")})
+    for name, coef, pa, pm in [("stable", [0, 0, 0.1, -0.4, 0.25], 0.0, 1.0)]:
+        V, dV, d2V = poly_funcs(coef)
+        r = dict(name=name, coef=[float(x) for x in coef], phi_abs=pa, phi_meta=pm, opts={}, error=None)
+        try:
+            Wall(pa, pm, V, dV, d2V).findProfile()
+        except t1.PotentialError as e:
+            r["error"] = "PotentialError:" + e.args[1]
+        except hf.IntegrationError as e:
+            r["error"] = "IntegrationError:" + str(e.args[0])
+        cases.append(r)
+        print("wall", name, r["error"])
+    with open(os.path.join(GOLD, "wall.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+
+
 def gen_alpha14():
     """alpha = 1 and 4 (d = 2 and 5 dimensions, Bessel order nu = 0 and 3/2): quartic family, a few knob sets,
     and exactSolution unit vectors -> tests/golden/alpha14.json"""
@@ -664,7 +711,7 @@ def gen_alpha14():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact"]
+                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

@@ -210,6 +210,20 @@ def vtot_model1_grid(cfg, params, s, T):
     return out
 
 
+def wall_one(cfg, params, phi_abs, phi_meta, Fguess=None, Ftol=1e-4, phi0_rel=1e-3, prof_cap=4096):
+    """WallWithConstFriction(phi_abs, phi_meta, V, ...).findProfile(Fguess, Ftol, phitol, npoints, rmin, rmax, phi0_rel)
+    (tunneling1D.py:829-999); phitol / npoints / rmin / rmax / phi_eps come from cfg."""
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(cfg.nparam)
+    dout, iout = np.zeros(6), np.zeros(4, dtype=np.int32)
+    R, Phi, dPhi = (np.zeros(prof_cap) for _ in range(3))
+    lib().ctbo_wall_one(C.byref(cfg), _dp(params), C.c_double(phi_abs), C.c_double(phi_meta),
+                        C.c_double(float("nan") if Fguess is None else Fguess), C.c_double(Ftol), C.c_double(phi0_rel),
+                        _dp(dout), _dp(iout), _dp(R), _dp(Phi), _dp(dPhi), C.c_int(prof_cap))
+    n = int(iout[3])
+    return dict(F=dout[0], rf=dout[1], phi_bar=dout[2], rscale=dout[3], phi0=dout[4], dphi0=dout[5], status=int(iout[0]),
+                n_shots=int(iout[1]), n_rkck=int(iout[2]), n_points=n, R=R[:n], Phi=Phi[:n], dPhi=dPhi[:n])
+
+
 def find_action(cfg, params, phi_meta, alpha, R, Phi, dPhi):
     """SingleFieldInstanton.findAction for a given profile (tunneling1D.py:763-791)."""
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(cfg.nparam)

@@ -123,6 +123,44 @@ def test_find_action_given_profiles(ctb, gold_dir):
     assert np.isnan(S[0]) and np.isfinite(S[1])
 
 
+def test_wall_with_const_friction(ctb, oracle, gold_dir):
+    """WallWithConstFriction on the device (ctb_wall_batch): scalar class vs the reference's goldens, batched entry vs
+    the CPU oracle on a 600-instance sweep."""
+    from cosmotransitions_b200 import _lib, batch, tunneling1D as t1, potentials, helper_functions as hf
+    cases = json.load(open(os.path.join(gold_dir, "wall.json")))
+    for case in cases:
+        pot = potentials.Poly4Potential(*case["coef"])
+        if case["error"] is not None:
+            exc = t1.PotentialError if case["error"].startswith("PotentialError") else hf.IntegrationError
+            with pytest.raises(exc) as ei:
+                t1.WallWithConstFriction(case["phi_abs"], case["phi_meta"], pot).findProfile(**case["opts"])
+            if exc is t1.PotentialError:
+                assert ei.value.args[1] == case["error"].split(":", 1)[1]
+            continue
+        w = t1.WallWithConstFriction(case["phi_abs"], case["phi_meta"], pot)
+        assert abs(w.rscale - case["rscale"]) <= 1e-12 * case["rscale"] and abs(w.phi_bar - case["phi_bar"]) <= 1e-12
+        p = w.findProfile(**case["opts"])
+        assert p._fields == ("R", "Phi", "dPhi", "F", "Rerr") and p.Rerr is None
+        assert abs(p.F - case["F"]) <= 1e-12 * case["F"], case
+        assert len(p.R) == case["npts"] and abs(p.R[-1] - case["rf"]) <= 1e-6 * case["rf"]
+        np.testing.assert_allclose(p.R[::20], case["R"], rtol=1e-6)
+        np.testing.assert_allclose(p.Phi[::20], case["Phi"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(p.dPhi[::20], case["dPhi"], rtol=0, atol=1e-7)
+    N = 600
+    c = 0.12 + 0.385 * (np.arange(N) + 0.5) / N     # reaches into the r > rmax zone at the thick end
+    params = potentials.quartic_family_params(c)
+    g = _np(batch.find_wall_batch(_lib.POT_POLY4, params, 1.0, 0.0))
+    cfg = oracle.make_config()
+    o = [oracle.wall_one(cfg, params[i], 1.0, 0.0) for i in range(N)]
+    assert np.array_equal(g["status"], [r["status"] for r in o])
+    ok = g["status"] <= 1
+    assert ok.mean() > 0.8 and (~ok).sum() > 3
+    np.testing.assert_allclose(g["F"][ok], np.array([r["F"] for r in o])[ok], rtol=1e-12)
+    np.testing.assert_allclose(g["rf"][ok], np.array([r["rf"] for r in o])[ok], rtol=1e-6)
+    assert np.array_equal(g["n_shots"][ok], np.array([r["n_shots"] for r in o])[ok])
+    assert (g["n_rkck"][ok] != np.array([r["n_rkck"] for r in o])[ok]).mean() < 0.01
+
+
 def test_splinepath_drop_in(ctb, gold_dir):
     """The class as pathDeformation.fullTunneling uses it (pathDeformation.py:959-968, 1000):
     tunneling_class(0.0, path.L, path.V, path.dV, path.d2V).findProfile() -> evenlySpacedPhi -> findAction,

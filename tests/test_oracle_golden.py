@@ -99,6 +99,29 @@ def test_jexact_oracle_vs_reference(oracle, gold_dir):
         assert np.max(np.abs(g[nm + "_exact2"][:40][ok] - g["mp_" + nm][ok])) < 1e-7
 
 
+def test_wall_with_const_friction(oracle, gold_dir):
+    """WallWithConstFriction.findProfile: oracle restatement vs the reference (F, rf, profile, shot / step counts)."""
+    cases = json.load(open(os.path.join(gold_dir, "wall.json")))
+    assert len(cases) >= 19
+    for case in cases:
+        kw = dict(case["opts"])
+        wkw = {k: kw.pop(k) for k in ("Fguess", "Ftol", "phi0_rel") if k in kw}
+        r = oracle.wall_one(oracle.make_config(**kw), case["coef"], case["phi_abs"], case["phi_meta"], **wkw)
+        if case["error"] is not None:
+            assert r["status"] == _status_for(case["error"]), (case, r["status"])
+            continue
+        assert r["status"] in (0, 1)
+        assert r["n_shots"] == case["n_shots"] and r["n_rkck"] == case["n_rkck"] and r["n_points"] == case["npts"]
+        assert abs(r["F"] - case["F"]) <= 1e-13 * case["F"]
+        assert abs(r["rf"] - case["rf"]) <= 1e-8 * case["rf"]
+        assert abs(r["rscale"] - case["rscale"]) <= 1e-12 * case["rscale"]
+        assert abs(r["phi_bar"] - case["phi_bar"]) <= 1e-12
+        np.testing.assert_allclose(r["R"][::20], case["R"], rtol=1e-8)
+        np.testing.assert_allclose(r["Phi"][::20], case["Phi"], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(r["dPhi"][::20], case["dPhi"], rtol=0, atol=1e-8)
+        assert abs(r["Phi"][-1] - case["Phi_last"]) < 1e-8 and abs(r["dPhi"][-1] - case["dPhi_last"]) < 1e-8
+
+
 def _profile_slice(g, case):
     sl = slice(*case["sl"])
     return tuple(g[case["name"] + k][sl] for k in ("_R", "_Phi", "_dPhi"))
