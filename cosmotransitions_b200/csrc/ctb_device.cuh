@@ -677,8 +677,10 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
         } else {
             sincos(z, &sh, &ch);
         }
-        phi = (sh / z - 1.0) * ratio + phi0;
-        dphi = ((ch - sh / z) / r) * ratio;
+        // (1 / z by the Newton reciprocal, 1 / r = beta / z: no IEEE division sequence on this path)
+        const double inv_z = rcp_fast(z), shz = sh * inv_z;
+        phi = (shz - 1.0) * ratio + phi0;
+        dphi = ((ch - shz) * (beta * inv_z)) * ratio;
     } else if (ALPHA == 1) {
         // nu = 0: I_0(z) - 1 and (I_{-1} + I_1)/2 = I_1 ; J: J_0(z) - 1 and (J_{-1} - J_1)/2 = -J_1
         if (modified) {
@@ -749,6 +751,7 @@ struct Sfi {
     Pot pot;
     double phi_abs, phi_meta, phi_eps, inv_12eps;
     double friction; // used by ALPHA == CTB_ALPHA_WALL only
+    double inv_r_end; // 1 / (t + dt) of the last Cash-Karp attempt
     int n_rkck;
     CTB_DEV void set_phi_eps(double e) { phi_eps = e; inv_12eps = 1.0 / (12. * e); }
 
@@ -793,6 +796,38 @@ struct Sfi {
         return dv;
     }
 
+    // Root of |phi(r) - phi_abs| = ac on [lo, hi] for the monotone (V'' > 0) exact solution.  err as brentq's.
+    CTB_DEV double start_radius_newton(const ExactCoef &ec, double pa, double ac, double lo, double hi, int &err) const
+    {
+        err = 0;
+        const double flo = fabs(exact_solution<ALPHA>(lo, ec).x - pa) - ac;
+        double2 e = exact_solution<ALPHA>(hi, ec);
+        const double fhi = fabs(e.x - pa) - ac;
+        if (isnan(flo) || isnan(fhi)) { err = 2; return nan(""); }
+        if (flo == 0) return lo;
+        if (fhi == 0) return hi;
+        if (signbit(flo) == signbit(fhi)) { err = 1; return 0.; }
+        if (flo > 0) return brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; }, lo, hi, err);
+        const double inv_ac = 1.0 / ac;
+        double x = hi;
+        for (int it = 0; it < 80; it++) {
+            const double d = e.x - pa, ad = fabs(d);
+            double xn = nan("");
+            if (ad < 1.7976931348623157e308 && e.y != 0 && fabs(e.y) < 1.7976931348623157e308) {
+                if (ad == ac) return x;
+                xn = x - log(ad * inv_ac) * d / e.y; // Newton on log(|phi - phi_abs| / ac): d/dr = phi' / (phi - phi_abs)
+            }
+            if (fabs(xn - x) <= 4e-15 * x) return xn; // converged (NaN compares false); may sit a rounding outside [lo, hi]
+            if (ad >= ac) hi = x; else lo = x; // (also taken for an overflowed value at x: the root lies below)
+            if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+            x = xn;
+            if ((hi - lo) <= 4e-16 * hi) break;
+            e = exact_solution<ALPHA>(x, ec);
+            if (isnan(e.x)) { err = 2; return nan(""); }
+        }
+        return x;
+    }
+
     // T1D:377-434, given dV_from_absMin(delta_phi0) and d2V(phi0); returns 0 or a CTB_ST_* error
     CTB_DEV int initial_conditions(double delta_phi0, double dv, double d2v, double rmin, double cutoff, double &r0,
                                    double &phi_r0, double &dphi_r0) const
@@ -812,8 +847,16 @@ struct Sfi {
         }
         int err;
         const double pa = phi_abs, ac = fabs(cutoff);
-        double rr = brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; },
-                           rlast, r, err);
+        double rr;
+        if (d2v > 0) {
+            // V'' > 0 (always the case close to the true vacuum, i.e. for every thin-wall shot): |phi(r) - phi_abs|
+            // grows monotonically like sinh(beta r) / (beta r) or I_nu, so its logarithm is almost linear in r and a
+            // bracketed Newton iteration on log(|phi - phi_abs| / cutoff) -- phi' comes with phi for free -- converges
+            // in 3-5 evaluations where brentq needs ~16.  The end-point tests are brentq's own (same statuses).
+            rr = start_radius_newton(ec, pa, ac, rlast, r, err);
+        } else {
+            rr = brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; }, rlast, r, err);
+        }
         if (err == 2) return CTB_ST_NONFINITE;
         if (err == 1) return CTB_ST_BRENT_SIGN;
         r0 = rr;
@@ -825,9 +868,13 @@ struct Sfi {
     // T1D:436-440
     CTB_DEV void eom(double y0, double y1, double r, double &f0, double &f1) const
     {
+        eom_inv(y0, y1, (ALPHA == CTB_ALPHA_WALL) ? 0.0 : rcp_fast(r), f0, f1);
+    }
+    CTB_DEV void eom_inv(double y0, double y1, double inv_r, double &f0, double &f1) const
+    {
         f0 = y1;
         if constexpr (ALPHA == CTB_ALPHA_WALL) f1 = fma(-friction, y1, dV(y0)); // T1D:912-916
-        else f1 = fma(-CTB_MUL((double)ALPHA, y1), rcp_fast(r), dV(y0));
+        else f1 = fma(-CTB_MUL((double)ALPHA, y1), inv_r, dV(y0));
     }
 
     // HF:204-236 Cash-Karp step
@@ -852,8 +899,11 @@ struct Sfi {
             k30, k31);
         eom(fma(dt, fma(b43, k30, fma(b42, k20, CTB_MUL(b41, d0))), y0),
             fma(dt, fma(b43, k31, fma(b42, k21, CTB_MUL(b41, d1))), y1), fma(a4, dt, t), k40, k41);
-        eom(fma(dt, fma(b54, k40, fma(b53, k30, fma(b52, k20, CTB_MUL(b51, d0)))), y0),
-            fma(dt, fma(b54, k41, fma(b53, k31, fma(b52, k21, CTB_MUL(b51, d1)))), y1), fma(a5, dt, t), k50, k51);
+        // (a5 = 1: this stage sits at t + dt, where the caller evaluates the derivative again after an accepted step;
+        //  its reciprocal radius is kept for that)
+        inv_r_end = (ALPHA == CTB_ALPHA_WALL) ? 0.0 : rcp_fast(fma(a5, dt, t));
+        eom_inv(fma(dt, fma(b54, k40, fma(b53, k30, fma(b52, k20, CTB_MUL(b51, d0)))), y0),
+                fma(dt, fma(b54, k41, fma(b53, k31, fma(b52, k21, CTB_MUL(b51, d1)))), y1), inv_r_end, k50, k51);
         eom(fma(dt, fma(b65, k50, fma(b64, k40, fma(b63, k30, fma(b62, k20, CTB_MUL(b61, d0))))), y0),
             fma(dt, fma(b65, k51, fma(b64, k41, fma(b63, k31, fma(b62, k21, CTB_MUL(b61, d1))))), y1), fma(a6, dt, t),
             k60, k61);
@@ -909,6 +959,34 @@ struct Cubic {
     CTB_DEV double operator()(double t) const { return fma(t, fma(t, fma(t, A3, A2), A1), A0); }
     CTB_DEV double at(double t) const { return (t == 1.0) ? Yend : (*this)(t); } // exact end point (root bracketing)
 };
+
+// Where the dense-output cubic of one step crosses `off` (T1D:521-534: brentq on [0, 1], xtol 2e-12): a bracketed
+// Newton iteration started from the secant through the end points; the cubic is close to linear within a step, so two
+// or three evaluations reach rounding level.  err as brentq's (1: no sign change, 2: NaN).
+CTB_DEV double cubic_crossing(const Cubic &f, double off, int &err)
+{
+    err = 0;
+    const double f0 = f.A0 - off, f1 = f.Yend - off;
+    if (isnan(f0) || isnan(f1)) { err = 2; return nan(""); }
+    if (f0 == 0) return 0.0;
+    if (f1 == 0) return 1.0;
+    if (signbit(f0) == signbit(f1)) { err = 1; return 0.; }
+    double lo = 0.0, hi = 1.0; // f(lo) has the sign of f0
+    double t = f0 / (f0 - f1);
+    for (int it = 0; it < 60; it++) {
+        const double ft = f(t) - off;
+        if (ft == 0) return t;
+        if (isnan(ft)) { err = 2; return nan(""); }
+        if (signbit(ft) == signbit(f0)) lo = t; else hi = t;
+        const double dft = fma(t, fma(t, CTB_MUL(3.0, f.A3), CTB_MUL(2.0, f.A2)), f.A1);
+        double tn = t - ft / dft;
+        if (fabs(tn - t) <= 1e-15) return fmin(fmax(tn, 0.0), 1.0); // converged (NaN compares false)
+        if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+        t = tn;
+        if ((hi - lo) <= 1e-15) break;
+    }
+    return t;
+}
 
 struct InstanceResult {
     double S, phi0, r0, rf, x, phi_bar, rscale;
@@ -1132,16 +1210,18 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 double dy0, dy1, drnext;
                 int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
                 if (e) { fail(e); break; }
-                double r1, na, nb;
+                double r1, na, nb, inv_r1;
                 if (saving && dr < drmin) { // T1D:594-597
                     na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;
                     dr = drnext = drmin;
                     r1 = r_ + dr;
+                    inv_r1 = rcp_fast(r1);
                 } else {
                     r1 = r_ + dr; na = ya + dy0; nb = yb + dy1;
+                    inv_r1 = s.inv_r_end; // the Cash-Karp stage at t + dt already formed 1 / r1
                 }
                 double nda, ndb;
-                s.eom(na, nb, r1, nda, ndb);
+                s.eom_inv(na, nb, inv_r1, nda, ndb);
                 if (!saving) {
                     if (r1 > rmax) { fail(CTB_ST_RMAX); break; }
                     else if (dr < drmin) { fail(CTB_ST_DRMIN); break; }
@@ -1158,7 +1238,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                         const Cubic &fr = under ? f1 : f0;
                         const double off = under ? 0.0 : phi_meta;
                         int berr;
-                        double xx = brentq([&](double t) { return fr.at(t) - off; }, 0.0, 1.0, berr);
+                        double xx = cubic_crossing(fr, off, berr);
                         if (berr == 1 || berr == 2) { fail((berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN); break; }
                         rf = fma(dr, xx, r_);
                         yf0 = f0.at(xx); yf1 = f1.at(xx);

@@ -68,7 +68,7 @@ __device__ int wall_integrate(Sfi<Pot, CTB_ALPHA_WALL> &s, double y00, double y0
                 const Cubic &fr = under ? f1 : f0;
                 const double off = under ? 0.0 : phi_meta;
                 int berr;
-                double xx = brentq([&](double t) { return fr.at(t) - off; }, 0.0, 1.0, berr);
+                double xx = cubic_crossing(fr, off, berr);
                 if (berr == 1 || berr == 2) return (berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN;
                 rf = fma(dr, xx, r_);
                 yf0 = f0.at(xx); yf1 = f1.at(xx);

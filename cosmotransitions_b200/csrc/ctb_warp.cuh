@@ -60,7 +60,7 @@ __device__ void run_shot(Sfi<Pot, ALPHA> &s, const ShootConsts &c, double x, Sho
         if (e) { o.status = e; break; }
         const double r1 = r_ + dr, na = ya + dy0, nb = yb + dy1;
         double nda, ndb;
-        s.eom(na, nb, r1, nda, ndb);
+        s.eom_inv(na, nb, s.inv_r_end, nda, ndb);
         if (r1 > rmax) { o.status = CTB_ST_RMAX; break; }
         else if (dr < c.drmin) { o.status = CTB_ST_DRMIN; break; }
         else if (fabs(na - c.phi_meta) < 3 * c.ea0 && fabs(nb) < 3 * c.ea1) {
@@ -75,7 +75,7 @@ __device__ void run_shot(Sfi<Pot, ALPHA> &s, const ShootConsts &c, double x, Sho
             const Cubic &fr = under ? f1 : f0;
             const double off = under ? 0.0 : c.phi_meta;
             int berr;
-            double xx = brentq([&](double t) { return fr.at(t) - off; }, 0.0, 1.0, berr);
+            double xx = cubic_crossing(fr, off, berr);
             if (berr == 1 || berr == 2) { o.status = (berr == 2) ? CTB_ST_NONFINITE : CTB_ST_BRENT_SIGN; ctype = -1; break; }
             rf = fma(dr, xx, r_);
             yf0 = f0.at(xx); yf1 = f1.at(xx);
