@@ -727,19 +727,14 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
         phi = fm1 * ratio + phi0;
         dphi = (beta * fp) * ratio;
     } else {
-        double hp = 2.0 / z; // (z/2)^-1, Gamma(2) = 1
-        double Inu, Im, Ip, sg;
-        if (modified) {
-            double i0 = cyl_bessel_i0(z), i1 = cyl_bessel_i1(z);
-            Inu = i1; Im = i0; Ip = i0 - 2.0 * i1 / z; sg = 1.0;
-        } else {
-            double j0_ = j0(z), j1_ = j1(z);
-            Inu = j1_; Im = j0_; Ip = 2.0 * j1_ / z - j0_; sg = -1.0;
-        }
-        phi = (hp * Inu - 1) * dv / d2v + phi0;
-        double d = -1.0 * (hp / r) * Inu;
-        d += hp * 0.5 * beta * (Im + sg * Ip);
-        dphi = d * ratio;
+        // nu = 1: f = (z/2)^-1 I_1(z), f' = (z/2)^-1 I_2(z) with I_2 = I_0 - (2/z) I_1 (J: f' = -(z/2)^-1 J_2,
+        // J_2 = (2/z) J_1 - J_0), i.e. the reference's -nu (..) I_nu / r + (..) beta (I_{nu-1} +- I_{nu+1}) / 2 collected
+        const double hp = 2.0 * rcp_fast(z); // (z/2)^-1, Gamma(2) = 1
+        double B0, B1;
+        if (modified) { B0 = cyl_bessel_i0(z); B1 = cyl_bessel_i1(z); }
+        else { B0 = j0(z); B1 = j1(z); }
+        phi = (hp * B1 - 1.0) * ratio + phi0;
+        dphi = ((beta * hp) * (B0 - hp * B1)) * ratio;
     }
     return make_double2(phi, dphi);
 }
