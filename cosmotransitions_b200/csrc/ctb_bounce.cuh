@@ -10,6 +10,9 @@
 #ifndef CTB_MIN_BLOCKS
 #define CTB_MIN_BLOCKS 3
 #endif
+#ifndef CTB_BIG_OCC
+#define CTB_BIG_OCC 4 // 128-thread blocks per SM of the shoot kernel in the throughput regime (128 registers)
+#endif
 
 namespace ctb {
 
@@ -145,13 +148,17 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
                        a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
     if (alpha < 1 || alpha > 4) return CTB_ERR_UNSUPPORTED;
     if (split && (alpha == 2 || alpha == 3)) {
+#ifdef CTB_FORCE_BIG // tuning builds: -DCTB_FORCE_BIG=0|1 pins the occupancy variant of the shoot kernel
+        const bool big = Pot::analytic && CTB_FORCE_BIG;
+#else
         const bool big = Pot::analytic && a.n >= 300000; // throughput regime: trade registers for warps
+#endif
         if (alpha == 2) {
-            if (big) bounce_kernel<Pot, 2, false, MODE_SHOOT, 4><<<grid, block, sm, st>>>(a);
+            if (big) bounce_kernel<Pot, 2, false, MODE_SHOOT, CTB_BIG_OCC><<<grid, block, sm, st>>>(a);
             else bounce_kernel<Pot, 2, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
             bounce_kernel<Pot, 2, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
         } else {
-            if (big) bounce_kernel<Pot, 3, false, MODE_SHOOT, 4><<<grid, block, sm, st>>>(a);
+            if (big) bounce_kernel<Pot, 3, false, MODE_SHOOT, CTB_BIG_OCC><<<grid, block, sm, st>>>(a);
             else bounce_kernel<Pot, 3, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
             bounce_kernel<Pot, 3, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
         }
