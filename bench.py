@@ -33,10 +33,11 @@ WORKLOADS = {
 }
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (the shoot kernel,
-# bounce_kernel<.., MODE_SHOOT>: 0.68 of the 1.0 ms of kernel time per step), from the `ncu --set full`
-# capture committed as profiles/r1_final_c2_split_metrics.csv (8.06 MB read: 5.6 MB parameters/minima +
-# 2.4 MB phi_bar/rscale/order; results and the 2.4 MB hand-over to the save kernel stay in L2)
-NCU_TRAFFIC_BYTES = {"c2": 8.056320e6}
+# bounce_kernel<.., MODE_SHOOT>: 0.64 of the 0.94 ms of kernel time per C2 step), from the `ncu --set full`
+# captures committed as profiles/r1b_c2_newton_metrics.csv (8.06 MB read: 5.6 MB parameters/minima + 2.4 MB
+# phi_bar/rscale/order; results and the 2.4 MB hand-over to the save kernel stay in L2) and
+# profiles/r1b_c3_newton_metrics.csv (80.1 MB read + 48.0 MB written)
+NCU_TRAFFIC_BYTES = {"c2": 8.063488e6, "c3": 128.039168e6}
 
 
 def sweep_c(n, rank=0, world=1):
@@ -329,10 +330,13 @@ def main():
                      "frac": achieved_tf / fp64_peak if fp64_peak else None,
                      "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                      "traffic_note": "bytes per launch of the shoot kernel, ncu dram__bytes_read+write "
-                                     "(profiles/r1_final_c2_split_metrics.csv); algorithmic: 64 B x instances",
+                                     "(profiles/r1b_c2_newton_metrics.csv, r1b_c3_newton_metrics.csv); algorithmic: 64 B x instances",
                      "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run "
                                     "(MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
+                     "scope": "whole step: setup + sort + shoot + save kernels (the flop count per bounce covers "
+                              "shooting, dense output and quadrature); the shoot kernel alone is 0.64 of the step's "
+                              "kernel time (profiles/r1b_c2_launches.csv)",
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "bytes_per_bounce": BYTES_PER_BOUNCE}},
         "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
