@@ -51,9 +51,24 @@ def test_ctypes_structs_follow_header_field_order():
         return out
 
     for cname, cls in (("ctb_jtable", _lib.JTable), ("ctb_opts", _lib.Opts), ("ctb_bounce_in", _lib.BounceIn),
-                       ("ctb_bounce_out", _lib.BounceOut)):
+                       ("ctb_bounce_out", _lib.BounceOut), ("ctb_wall_opts", _lib.WallOpts)):
         assert fields(cname) == [f[0] for f in cls._fields_], cname
     assert "#define CTB_ABI_VERSION %d" % _lib.ABI_VERSION in hdr
+
+
+def test_integration_md_stub_matches_the_abi():
+    """The reference-side ctypes stub printed in INTEGRATION.md declares the same structures as the product."""
+    import ctypes as C
+    from cosmotransitions_b200 import _lib
+    md = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    code = md.split("```python")[1].split("```")[0]
+    assert "ctb_abi_version() == %d" % _lib.ABI_VERSION in code
+    classes = code[code.index("class JTable"):code.index("def bounce_actions_quartic")]
+    ns = {"C": C}
+    exec(classes, ns)
+    for name in ("JTable", "Opts", "BounceIn", "BounceOut"):
+        assert [f[0] for f in ns[name]._fields_] == [f[0] for f in getattr(_lib, name)._fields_], name
+        assert C.sizeof(ns[name]) == C.sizeof(getattr(_lib, name)), name
 
 
 def test_bspline_to_pp_matches_scipy():
