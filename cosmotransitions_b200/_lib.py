@@ -24,7 +24,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
-           "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_potential", "ctb_fp64_peak"]
+           "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_vtot_thermal1f", "ctb_potential", "ctb_fp64_peak"]
 
 
 class JTable(C.Structure):
@@ -104,6 +104,9 @@ def load():
     lib.ctb_vtot_model1_grid.restype = C.c_int
     lib.ctb_vtot_model1_grid.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(JTable), C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.ctb_vtot_thermal1f.restype = C.c_int
+    lib.ctb_vtot_thermal1f.argtypes = [C.POINTER(C.c_double), C.c_double, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     lib.ctb_potential.restype = C.c_int
     lib.ctb_potential.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p]

@@ -319,6 +319,34 @@ __global__ void __launch_bounds__(VG_THREADS) vtot_model1_grid_kernel(Model8 m, 
     }
 }
 
+// generic_potential.Vtot / V1T_from_X (GP:258-337) for the general one-field model (CTB_POT_THERMAL1F layout, one
+// model, per-point temperature): X_i, T_i -> out_i.  `rad` = (num_boson_dof - sum n_b) pi^4/45 + (num_fermion_dof -
+// sum n_f) 7 pi^4/360, the field-independent radiation term of V1T (GP:289-295), 0 without it.
+struct Thermal1FModel { double v[CTB_NPARAM_THERMAL1F]; };
+__global__ void __launch_bounds__(256) vtot_thermal1f_kernel(Thermal1FModel m, double rad, JTab gb, JTab gf,
+                                                             const double *__restrict__ phi, const double *__restrict__ T,
+                                                             double *__restrict__ out, int64_t n, int parts)
+{
+    extern __shared__ double smem[];
+    __shared__ double row[CTB_NPARAM_THERMAL1F];
+    const JTab jb = stage_table_compact(gb, smem);
+    const JTab jf = stage_table_compact(gf, smem + ((CTB_TABLE_DOUBLES_COMPACT(gb.nint) + 1) & ~(size_t)1)); // 16-byte aligned
+    if (threadIdx.x < CTB_NPARAM_THERMAL1F) row[threadIdx.x] = m.v[threadIdx.x];
+    __syncthreads();
+    const double inv_rs = 1.0 / row[5];
+    const int nb = min(max((int)row[7], 0), CTB_THERMAL1F_MAX_BOSONS), nf = min(max((int)row[8], 0), CTB_THERMAL1F_MAX_FERMIONS);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double Ti = T[i], T2 = Ti * Ti;
+        const PotThermal1F::Parts o = PotThermal1F::eval(row, nb, nf, inv_rs, T2, 1.0 / (T2 + 1e-100), 0.0, jb, jf, phi[i]);
+        double v = 0.0;
+        if (parts & CTB_V_TREE) v += o.v0;
+        if (parts & CTB_V_ONELOOP) v += o.v1;
+        if (parts & CTB_V_THERMAL) v += (o.v1t - rad) * ((T2 * T2) / (2 * CTB_PI * CTB_PI));
+        out[i] = v;
+    }
+}
+
 template <class Pot>
 __global__ void potential_kernel(const double *params, JTab jb, JTab jf, const double *__restrict__ phi,
                                  double *__restrict__ out, int64_t n)
@@ -718,6 +746,23 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     vtot_model1_grid_kernel<<<(unsigned)nblk, VG_THREADS, vg_smem,
                               (cudaStream_t)stream>>>(m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns,
                                                       d_T, nT, d_out, chunk);
+    return (int)cudaGetLastError();
+}
+
+CTB_API int ctb_vtot_thermal1f(const double *model64, double rad, const ctb_jtable *jb, const ctb_jtable *jf,
+                               const double *d_phi, const double *d_T, double *d_out, int64_t n, int parts, void *stream)
+{
+    if (!model64 || !jtab_ok(jb) || !jtab_ok(jf) || n < 0 || parts < 1 || parts > CTB_V_TOTAL) return CTB_ERR_BAD_ARG;
+    if (n == 0) return CTB_OK;
+    if (!d_phi || !d_T || !d_out) return CTB_ERR_BAD_ARG;
+    Thermal1FModel m;
+    for (int i = 0; i < CTB_NPARAM_THERMAL1F; i++) m.v[i] = model64[i];
+    const size_t sm = table_bytes_compact(jb) + table_bytes_compact(jf) + 16;
+    cudaFuncSetAttribute(vtot_thermal1f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 2) g = 148 * 2; // persistent: two 80 KB table pairs per SM
+    vtot_thermal1f_kernel<<<(unsigned)g, 256, sm, (cudaStream_t)stream>>>(m, rad, to_jtab(jb), to_jtab(jf), d_phi, d_T, d_out,
+                                                                         n, parts);
     return (int)cudaGetLastError();
 }
 

@@ -322,24 +322,35 @@ struct PotThermal1F {
         jb = *jb_;
         jf = *jf_;
     }
-    __device__ __noinline__ double V(double phi) const
+    // V0 / V1 / V1T pieces (GP:240-296) for one field value; p may live in global or shared memory
+    struct Parts { double v0, v1, v1t; };
+    static CTB_DEV Parts eval(const double *p, int nb, int nf, double inv_rs, double T2, double inv_T2, double T4c,
+                              const JTab &jb, const JTab &jf, double phi)
     {
         const double p2 = phi * phi;
-        double r = __ldg(p) + phi * (__ldg(p + 1) + phi * (__ldg(p + 2) + phi * (__ldg(p + 3) + phi * __ldg(p + 4))));
+        Parts o;
+        o.v0 = p[0] + phi * (p[1] + phi * (p[2] + phi * (p[3] + phi * p[4])));
         double y1 = 0.0, yt = 0.0;
         for (int i = 0; i < nb; i++) { // GP:249-251, 285-286
             const double *q = p + 9 + 5 * i;
-            const double m2 = __ldg(q) + __ldg(q + 1) * p2 + __ldg(q + 2) * T2, dof = __ldg(q + 3);
-            y1 += dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - __ldg(q + 4));
+            const double m2 = q[0] + q[1] * p2 + q[2] * T2, dof = q[3];
+            y1 += dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - q[4]);
             yt += dof * jtab_eval<0>(jb, m2 * inv_T2);
         }
         for (int j = 0; j < nf; j++) { // GP:252-255, 287-288
             const double *q = p + 49 + 3 * j;
-            const double m2 = __ldg(q) + __ldg(q + 1) * p2, dof = __ldg(q + 2);
+            const double m2 = q[0] + q[1] * p2, dof = q[2];
             y1 -= dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - 1.5);
             yt += dof * jtab_eval<0>(jf, m2 * inv_T2);
         }
-        return r + y1 * (1.0 / (64 * CTB_PI * CTB_PI)) + yt * T4c;
+        o.v1 = y1 * (1.0 / (64 * CTB_PI * CTB_PI));
+        o.v1t = yt; // in units of T^4 / (2 pi^2): the caller subtracts the radiation constant before scaling
+        return o;
+    }
+    __device__ __noinline__ double V(double phi) const
+    {
+        const Parts o = eval(p, nb, nf, inv_rs, T2, inv_T2, T4c, jb, jf, phi);
+        return o.v0 + o.v1 + o.v1t * T4c;
     }
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, _tables
-from .potentials import model1_model8, Model1LinePotential
+from .potentials import model1_model8, Model1LinePotential, Thermal1FPotential, thermal1f_params
 
 
 class model1:
@@ -84,3 +84,114 @@ class model1:
         x_abs, x_meta = np.asarray(x_abs, float), np.asarray(x_meta, float)
         L = float(np.linalg.norm(x_meta - x_abs))
         return Model1LinePotential(x_abs, (x_meta - x_abs) / L, T, self.model8), L
+
+
+class one_field_model:
+    """A general ONE-field generic_potential (generic_potential.py:26-345) on the device: quartic tree-level
+    potential V0 = sum_k V0_coefs[k] phi^k, bosons with m^2 = a + b phi^2 + t T^2 (dof, c), fermions with
+    m^2 = a + b phi^2 (dof) -- the data a subclass would return from V0 / boson_massSq / fermion_massSq
+    (generic_potential.py:132-238), given once as tables instead of Python callbacks.
+
+    Same attributes (Ndim, x_eps, T_eps, deriv_order, renormScaleSq, num_boson_dof, num_fermion_dof) and the same
+    methods with the reference's broadcasting contract (X[..., 1] against T[...]): Vtot, V1T_from_X, DVtot, gradV,
+    d2V, dgradV_dT, energyDensity.  `potential(T)` hands the same model to the bounce solver."""
+
+    Ndim = 1
+
+    def __init__(self, V0_coefs, renormScaleSq=1000. ** 2, bosons=(), fermions=(), num_boson_dof=None,
+                 num_fermion_dof=None, x_eps=.001, T_eps=.001, deriv_order=4):
+        self.V0_coefs, self.bosons, self.fermions = list(V0_coefs), [tuple(b) for b in bosons], [tuple(f) for f in fermions]
+        self.renormScaleSq, self.x_eps, self.T_eps, self.deriv_order = renormScaleSq, x_eps, T_eps, deriv_order
+        self.num_boson_dof, self.num_fermion_dof = num_boson_dof, num_fermion_dof
+        if deriv_order not in (2, 4):
+            raise ValueError("deriv_order must be 2 or 4")
+        row = thermal1f_params(self.V0_coefs, renormScaleSq, 0.0, self.bosons, self.fermions)[0]
+        self._row = (C.c_double * len(row))(*row)
+
+    def potential(self, T):
+        """Device functor of Vtot(phi, T) for SingleFieldInstanton / find_bounce_batch."""
+        return Thermal1FPotential(self.V0_coefs, self.renormScaleSq, T, self.bosons, self.fermions)
+
+    def _rad(self, include_radiation):
+        rad = 0.0   # generic_potential.py:289-295
+        if include_radiation and self.num_boson_dof is not None:
+            rad += (self.num_boson_dof - sum(b[3] for b in self.bosons)) * np.pi ** 4 / 45.
+        if include_radiation and self.num_fermion_dof is not None:
+            rad += (self.num_fermion_dof - sum(f[2] for f in self.fermions)) * 7 * np.pi ** 4 / 360.
+        return rad
+
+    def _eval(self, X, T, parts, include_radiation=True, shifts=None):
+        """sum_k w_k V(X + dx_k, T + dT_k) for shifts = [(dx, dT, w), ...] in one launch (finite differences)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        is_tensor = isinstance(X, torch.Tensor)
+        dev = X.device if is_tensor and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        Xd = (X if is_tensor else torch.from_numpy(np.asarray(X, dtype=np.float64))).to(dev, torch.float64)
+        Td = (T if isinstance(T, torch.Tensor) else torch.from_numpy(np.asarray(T, dtype=np.float64))).to(
+            dev, torch.float64)
+        if Xd.dim() == 0 or Xd.shape[-1] != 1:
+            raise ValueError("X must have a last axis of length Ndim = 1")
+        shape = torch.broadcast_shapes(Xd.shape[:-1], Td.shape)
+        phi = Xd[..., 0].expand(shape).reshape(-1)
+        Tf = Td.expand(shape).reshape(-1)
+        shifts = shifts or [(0.0, 0.0, 1.0)]
+        phis = torch.cat([phi + dx for dx, _, _ in shifts]).contiguous()
+        Ts = torch.cat([Tf + dT for _, dT, _ in shifts]).contiguous()
+        out = torch.empty_like(phis)
+        tabs = _tables.device_tables(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ctb_vtot_thermal1f(self._row, self._rad(include_radiation), tabs.jb, tabs.jf, phis.data_ptr(),
+                                              Ts.data_ptr(), out.data_ptr(), phis.numel(), parts,
+                                              torch.cuda.current_stream(dev).cuda_stream), "ctb_vtot_thermal1f")
+        n = phi.numel()
+        res = sum(w * out[k * n:(k + 1) * n] for k, (_, _, w) in enumerate(shifts)).reshape(shape)
+        if is_tensor:
+            return res if X.is_cuda else res.cpu()
+        res = res.cpu().numpy()
+        return float(res) if res.ndim == 0 else res
+
+    def Vtot(self, X, T, include_radiation=True):
+        """The total finite temperature effective potential (generic_potential.py:312-337)."""
+        return self._eval(X, T, _lib.V_TOTAL, include_radiation)
+
+    def V1T_from_X(self, X, T, include_radiation=True):
+        """The one-loop finite-temperature part alone (generic_potential.py:298-310)."""
+        return self._eval(X, T, _lib.V_THERMAL, include_radiation)
+
+    def DVtot(self, X, T):
+        """Vtot offset such that V(0, T) = 0 (generic_potential.py:339-345)."""
+        X0 = np.zeros(self.Ndim)
+        return self.Vtot(X, T, False) - self.Vtot(X0, T, False)
+
+    def _stencil(self, eps, order):
+        # helper_functions.deriv14 / gradientFunction coefficients (helper_functions.py:400-520)
+        if self.deriv_order == 2:
+            return ([(-eps, -.5 / eps), (eps, .5 / eps)] if order == 1 else
+                    [(-eps, 1. / eps ** 2), (0.0, -2. / eps ** 2), (eps, 1. / eps ** 2)])
+        if order == 1:
+            return [(-2 * eps, 1 / (12. * eps)), (-eps, -8 / (12. * eps)), (eps, 8 / (12. * eps)), (2 * eps, -1 / (12. * eps))]
+        return [(-2 * eps, -1 / (12. * eps * eps)), (-eps, 16 / (12. * eps * eps)), (0.0, -30 / (12. * eps * eps)),
+                (eps, 16 / (12. * eps * eps)), (2 * eps, -1 / (12. * eps * eps))]
+
+    def gradV(self, X, T):
+        """Gradient of Vtot (no radiation term) by finite differences in phi; shape X.shape (generic_potential.py:347-367)."""
+        g = self._eval(X, T, _lib.V_TOTAL, False, [(dx, 0.0, w) for dx, w in self._stencil(self.x_eps, 1)])
+        return g[..., None] if hasattr(g, "shape") else np.array([g])
+
+    def d2V(self, X, T):
+        """Second derivative (the 1 x 1 Hessian) of Vtot; shape X.shape[:-1] + (1, 1) (generic_potential.py:390-408)."""
+        h = self._eval(X, T, _lib.V_TOTAL, False, [(dx, 0.0, w) for dx, w in self._stencil(self.x_eps, 2)])
+        return h[..., None, None] if hasattr(h, "shape") else np.array([[h]])
+
+    def dgradV_dT(self, X, T):
+        """d/dT of gradV from V1T alone (generic_potential.py:369-388)."""
+        sx, sT = self._stencil(self.x_eps, 1), self._stencil(self.T_eps, 1)
+        g = self._eval(X, T, _lib.V_THERMAL, False, [(dx, dT, wx * wT) for dx, wx in sx for dT, wT in sT])
+        return g[..., None] if hasattr(g, "shape") else np.array([g])
+
+    def energyDensity(self, X, T, include_radiation=True):
+        """V - T dV/dT, the temperature derivative from V1T by finite differences (generic_potential.py:443-456)."""
+        dVdT = self._eval(X, T, _lib.V_THERMAL, include_radiation,
+                          [(0.0, dT, w) for dT, w in self._stencil(self.T_eps, 1)])
+        Tb = T if hasattr(dVdT, "is_cuda") else np.asarray(T, dtype=np.float64)
+        return self.Vtot(X, T, include_radiation) - Tb * dVdT

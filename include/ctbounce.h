@@ -264,6 +264,13 @@ CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const do
 CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, const ctb_jtable *jb, const double *d_s,
                          int64_t ns, const double *d_T, int64_t nT, double *d_out, void *stream);
 
+/* generic_potential.Vtot / V1T_from_X (generic_potential.py:258-337) for ONE general one-field model
+ * (model64: host pointer, the CTB_POT_THERMAL1F row layout; its T entry is ignored) at n (phi_i, T_i) points.
+ * rad = (num_boson_dof - sum n_b) pi^4/45 + (num_fermion_dof - sum n_f) 7 pi^4/360 is the field-independent radiation
+ * constant of V1T (generic_potential.py:289-295; 0 when include_radiation is off or the totals are None).         */
+CTB_API int ctb_vtot_thermal1f(const double *model64, double rad, const ctb_jtable *jb, const ctb_jtable *jf,
+                               const double *d_phi, const double *d_T, double *d_out, int64_t n, int parts, void *stream);
+
 /* Potential functor evaluation V(phi_j) for one parameter row (debug / parity aid). */
 CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
                   const double *d_phi, double *d_out, int64_t n, void *stream);

@@ -421,6 +421,22 @@ def gen_thermal1f():
         cases.append(r)
         print("thermal1f T=%.3f" % T, {q: r.get(q) for q in ("S", "npts", "n_shots", "n_rkck", "error")})
     out["bounces"] = cases
+    # the generic_potential surface on (phi, T) grids with broadcasting, radiation terms on and off
+    m2 = SMlike()
+    m2.num_boson_dof, m2.num_fermion_dof = 40., 90.
+    gphi, gT = np.linspace(-20, 320, 18), np.array([0.0, 35.0, 90.0, 160.0, 240.0])
+    X = np.broadcast_to(gphi[:, None, None], (18, 5, 1))   # (the reference's in-place `y +=` needs the full shape)
+    gp_ = dict(phi=gphi.tolist(), T=gT.tolist(), num_boson_dof=40., num_fermion_dof=90.)
+    gp_["Vtot"] = m2.Vtot(X, gT[None, :]).tolist()
+    gp_["Vtot_norad"] = m2.Vtot(X, gT[None, :], False).tolist()
+    gp_["V1T"] = m2.V1T_from_X(X, gT[None, :]).tolist()
+    gp_["DVtot"] = m2.DVtot(X, gT[None, :]).tolist()
+    gp_["gradV"] = m2.gradV(X, gT[None, :]).tolist()
+    gp_["d2V"] = m2.d2V(X, gT[None, :]).tolist()
+    gp_["dgradV_dT"] = m2.dgradV_dT(X, gT[None, :]).tolist()
+    gp_["energyDensity"] = m2.energyDensity(X, gT[None, :]).tolist()
+    gp_["Vtot_point"] = float(m2.Vtot(np.array([123.0]), 77.0))
+    out["generic_potential"] = gp_
     with open(os.path.join(GOLD, "thermal1f.json"), "w") as f:
         json.dump(out, f, indent=0)
 

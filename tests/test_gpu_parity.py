@@ -690,6 +690,39 @@ def test_thermal1f_general_model(ctb, oracle, tables, gold_dir):
     assert abs(inst.findAction(inst.findProfile()) - S_ref[1]) < S_RTOL * S_ref[1]
 
 
+def test_one_field_generic_potential_surface(ctb, gold_dir):
+    """generic_potential.one_field_model (ctb_vtot_thermal1f): Vtot / V1T_from_X / DVtot / gradV / d2V / dgradV_dT /
+    energyDensity with the reference's broadcasting contract and radiation terms, against the reference itself."""
+    from cosmotransitions_b200 import generic_potential as gpm
+    g = json.load(open(os.path.join(gold_dir, "thermal1f.json")))
+    gp = g["generic_potential"]
+    m = gpm.one_field_model(g["V0_coefs"], g["renorm"], g["bosons"], g["fermions"], num_boson_dof=gp["num_boson_dof"],
+                            num_fermion_dof=gp["num_fermion_dof"])
+    X = np.array(gp["phi"])[:, None, None]
+    T = np.array(gp["T"])[None, :]
+    scale = np.abs(np.array(gp["Vtot"])).max()
+    np.testing.assert_allclose(m.Vtot(X, T), gp["Vtot"], rtol=1e-11, atol=1e-12 * scale)
+    np.testing.assert_allclose(m.Vtot(X, T, False), gp["Vtot_norad"], rtol=1e-11, atol=1e-12 * scale)
+    np.testing.assert_allclose(m.V1T_from_X(X, T), gp["V1T"], rtol=1e-11, atol=1e-12 * scale)
+    np.testing.assert_allclose(m.DVtot(X, T), gp["DVtot"], rtol=1e-9, atol=1e-11 * scale)
+    # finite differences of a ~1e9-sized potential with steps of 1e-3: rounding noise V eps_mach / h (/ h^2)
+    gV = np.array(gp["gradV"])
+    assert m.gradV(X, T).shape == gV.shape
+    np.testing.assert_allclose(m.gradV(X, T), gV, rtol=1e-7, atol=1e-13 * scale / 1e-3)
+    d2 = np.array(gp["d2V"])
+    assert m.d2V(X, T).shape == d2.shape
+    np.testing.assert_allclose(m.d2V(X, T), d2, rtol=1e-6, atol=1e-13 * scale / 1e-6)
+    np.testing.assert_allclose(m.dgradV_dT(X, T), gp["dgradV_dT"], rtol=1e-5, atol=1e-13 * scale / 1e-6)
+    np.testing.assert_allclose(m.energyDensity(X, T), gp["energyDensity"], rtol=1e-7, atol=1e-10 * scale)
+    assert abs(m.Vtot(np.array([123.0]), 77.0) - gp["Vtot_point"]) <= 1e-11 * abs(gp["Vtot_point"])
+    # the same model feeds the bounce solver
+    from cosmotransitions_b200 import tunneling1D as t1
+    c = g["bounces"][1]
+    inst = t1.SingleFieldInstanton(c["phi_abs"], 0.0, gpm.one_field_model(g["V0_coefs"], g["renorm"], g["bosons"],
+                                                                          g["fermions"]).potential(c["T"]))
+    assert abs(inst.findAction(inst.findProfile()) - c["S"]) < S_RTOL * c["S"]
+
+
 def test_c3_full_size_subsample_vs_oracle(ctb, oracle):
     """BASELINE.json config C3 at full size (1e6 quartic instances, alpha=3) through the production path
     (work-sorted, split solve); every 500th instance is checked against the CPU oracle."""

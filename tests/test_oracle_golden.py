@@ -122,6 +122,21 @@ def test_wall_with_const_friction(oracle, gold_dir):
         assert abs(r["Phi"][-1] - case["Phi_last"]) < 1e-8 and abs(r["dPhi"][-1] - case["dPhi_last"]) < 1e-8
 
 
+def test_thermal1f_generic_potential_grid(oracle, tables, gold_dir):
+    """generic_potential.Vtot on a (phi, T) grid (radiation off) and the radiation constant (generic_potential.py:289-295)."""
+    g = json.load(open(os.path.join(gold_dir, "thermal1f.json")))
+    gp = g["generic_potential"]
+    phi, T = np.array(gp["phi"]), np.array(gp["T"])
+    P, TT = np.meshgrid(phi, T, indexing="ij")
+    cfg = oracle.make_config(kind=oracle.POT_THERMAL1F, tables=tables)
+    V = oracle.potential_rows(cfg, _thermal1f_rows(g, TT.reshape(-1)), P.reshape(-1)).reshape(P.shape)
+    np.testing.assert_allclose(V, np.array(gp["Vtot_norad"]), rtol=1e-12, atol=1e-4)
+    rad = (gp["num_boson_dof"] - sum(b[3] for b in g["bosons"])) * np.pi ** 4 / 45. \
+        + (gp["num_fermion_dof"] - sum(f[2] for f in g["fermions"])) * 7 * np.pi ** 4 / 360.
+    np.testing.assert_allclose(np.array(gp["Vtot"]) - np.array(gp["Vtot_norad"]),
+                               np.broadcast_to(-rad * T ** 4 / (2 * np.pi ** 2), P.shape), rtol=1e-6, atol=1e-3)
+
+
 def _profile_slice(g, case):
     sl = slice(*case["sl"])
     return tuple(g[case["name"] + k][sl] for k in ("_R", "_Phi", "_dPhi"))
