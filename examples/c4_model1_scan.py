@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3]: testModel1 finite-T potential -- batched Vtot with Jb/Jf on a 4096 x 1024
 (phi, T) grid, plus a per-T 1-D bounce scan toward T_nuc along the straight line between the two phases
-(SURVEY.md s.8d C4).  Prints timings, the S3/T = 140 crossing and a spot check against the CPU oracle."""
+(SURVEY.md s.8d C4).  Prints timings and the S3/T = 140 crossing (parity of the same scan against the CPU oracle: tests/test_gpu_parity.py)."""
 import json
 import os
 import sys
@@ -42,16 +42,4 @@ st = r["status"].cpu().numpy()
 out = {"vtot_grid_s": t_grid, "vtot_pts_per_s": 4096 * 1024 / t_grid, "scan_T": len(Ts), "scan_s": t_scan,
        "bounces_per_s": len(Ts) / t_scan, "solved": int((st <= 1).sum()), "Tnuc_line": float(r["Tnuc"])}
 
-if "--check" in sys.argv:   # oracle spot check on every 32nd temperature (test infrastructure)
-    from oracle import oracle as O
-    tab = O.Tables.from_npz(os.path.join(REPO, "cosmotransitions_b200", "data", "finiteT_tables.npz"))
-    cfg = O.make_config(kind=O.POT_MODEL1_LINE, tables=tab)
-    worst = 0.0
-    for i in range(0, len(Ts), 32):
-        if st[i] > 1:
-            continue
-        p = np.concatenate([m.model8, [Ts[i]], x_low, nhat])
-        o = O.bounce_one(cfg, p, float(r["s_abs"][i]), float(r["s_meta"][i]))
-        worst = max(worst, abs(o["S"] - float(r["S"][i])) / abs(o["S"]))
-    out["max_rel_err_S_vs_oracle"] = worst
 print(json.dumps(out))
