@@ -4,10 +4,11 @@ Public surface (mirrors the reference's for this path):
     tunneling1D.SingleFieldInstanton, tunneling1D.PotentialError, helper_functions.IntegrationError
     finiteT.Jb_spline / Jf_spline / Jb / Jf
     generic_potential.model1 (.Vtot, .Vtot_grid, .line_potential)
-    batch.find_bounce_batch (the batched entry point), multigpu.find_bounce_batch_multi
+    batch.find_bounce_batch (the batched entry point), batch.BouncePipeline (streamed host batches),
+    batch.find_wall_batch, batch.find_action_batch, multigpu.find_bounce_batch_multi
     potentials.* (device functors)
 The CUDA library is loaded lazily; there is no CPU fallback."""
 from . import _lib  # noqa: F401
-from .batch import find_bounce_batch  # noqa: F401
+from .batch import find_bounce_batch, BouncePipeline  # noqa: F401
 
 __version__ = "0.1.0"

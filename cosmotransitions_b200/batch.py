@@ -273,3 +273,70 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
     if on_host:
         out = {k: v.cpu() for k, v in out.items()}
     return out
+
+
+class BouncePipeline:
+    """Streaming front end for many same-sized batches coming from HOST memory (parameter scans that are generated
+    or read on the CPU): `depth` slots, each with its own CUDA stream, device buffers and pinned result buffers, so
+    that the host->device copy of batch k+1 and the device->host copy of batch k-1 run on the copy engines while the
+    kernels of batch k occupy the SMs.  Results are identical to find_bounce_batch (instances are independent).
+
+        pipe = BouncePipeline(_lib.POT_POLY4, n, alpha=2)
+        for k, (params, phi_abs, phi_meta) in enumerate(batches):     # pinned CPU tensors for truly async copies
+            if k >= pipe.depth:
+                consume(pipe.collect(k - pipe.depth))                 # dict of pinned CPU tensors (valid until reuse)
+            pipe.submit(params, phi_abs, phi_meta)
+        ... collect the last `depth` tickets
+    """
+
+    def __init__(self, potential_kind, n, depth=2, device=None, outputs=("S", "status"), alpha=2, phi_eps=1e-3,
+                 schedule="auto", split="auto", block_threads=0, kernel="auto", **findProfile_knobs):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self.kind = getattr(potential_kind, "kind", potential_kind)
+        self.n, self.depth = int(n), int(depth)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.opts = make_opts(alpha=alpha, phi_eps=phi_eps, block_threads=block_threads, kernel=kernel, **findProfile_knobs)
+        self.schedule, self.split, self.outputs = schedule, split, tuple(outputs)
+        K = _lib.NPARAM[self.kind]
+        self._slots = []
+        for _ in range(self.depth):
+            slot = dict(stream=torch.cuda.Stream(self.device), done=torch.cuda.Event(),
+                        params=torch.empty((self.n, K), dtype=torch.float64, device=self.device),
+                        phi_abs=torch.empty(self.n, dtype=torch.float64, device=self.device),
+                        phi_meta=torch.empty(self.n, dtype=torch.float64, device=self.device),
+                        out=alloc_out(torch, self.n, self.device))
+            slot["host"] = {k: torch.empty(self.n, dtype=slot["out"][k].dtype).pin_memory() for k in self.outputs}
+            self._slots.append(slot)
+        self._submitted = 0
+
+    def submit(self, params, phi_absMin, phi_metaMin):
+        """Queue one batch (CPU tensors / arrays of n rows); returns its ticket.  Does not block on the GPU, except
+        that a slot is reused only after its previous results have been copied out."""
+        torch = self._torch
+        k = self._submitted
+        slot = self._slots[k % self.depth]
+        slot["done"].synchronize()          # previous occupant of the slot (no-op for a fresh event)
+        as_t = lambda x: x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+        with torch.cuda.device(self.device), torch.cuda.stream(slot["stream"]):
+            slot["params"].copy_(as_t(params).reshape(self.n, -1), non_blocking=True)
+            slot["phi_abs"].copy_(as_t(phi_absMin).expand(self.n) if as_t(phi_absMin).dim() == 0 else as_t(phi_absMin),
+                                  non_blocking=True)
+            slot["phi_meta"].copy_(as_t(phi_metaMin).expand(self.n) if as_t(phi_metaMin).dim() == 0
+                                   else as_t(phi_metaMin), non_blocking=True)
+            launch_bounce(self.kind, slot["params"], slot["phi_abs"], slot["phi_meta"], self.opts, slot["out"],
+                          schedule=self.schedule, split=self.split)
+            for name in self.outputs:
+                slot["host"][name].copy_(slot["out"][name], non_blocking=True)
+            slot["done"].record(slot["stream"])
+        self._submitted += 1
+        return k
+
+    def collect(self, ticket):
+        """Wait for batch `ticket` and return its results (pinned CPU tensors owned by the pipeline: copy them if
+        they must outlive the next `depth` submissions)."""
+        if not (self._submitted - self.depth <= ticket < self._submitted):
+            raise ValueError("ticket %d is not in flight" % ticket)
+        slot = self._slots[ticket % self.depth]
+        slot["done"].synchronize()
+        return slot["host"]

@@ -337,6 +337,31 @@ def test_scalar_api_overrides(ctb):
     assert inst.phi_bar == 0.8
 
 
+def test_bounce_pipeline_streams(ctb):
+    """BouncePipeline (two slots / streams, host batches in, pinned host results out) returns exactly what
+    find_bounce_batch returns, batch after batch, including when slots are reused."""
+    import torch
+    from cosmotransitions_b200 import _lib, batch, potentials
+    n = 5000
+    rng = np.random.default_rng(4)
+    batches = [potentials.quartic_family_params(0.02 + 0.475 * rng.random(n)) for _ in range(5)]
+    ref = [_np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, alpha=3)) for p in batches]
+    pipe = batch.BouncePipeline(_lib.POT_POLY4, n, depth=2, outputs=("S", "status", "n_rkck"), alpha=3)
+    ones, zeros = torch.ones(n, dtype=torch.float64).pin_memory(), torch.zeros(n, dtype=torch.float64).pin_memory()
+    got = []
+    for k, p in enumerate(batches):
+        if k >= pipe.depth:
+            got.append({q: v.clone().numpy() for q, v in pipe.collect(k - pipe.depth).items()})
+        pipe.submit(torch.from_numpy(p).pin_memory(), ones, zeros)
+    for k in range(len(batches) - pipe.depth, len(batches)):
+        got.append({q: v.clone().numpy() for q, v in pipe.collect(k).items()})
+    for r, g in zip(ref, got):
+        for q in ("S", "status", "n_rkck"):
+            assert np.array_equal(r[q], g[q], equal_nan=True), q
+    with pytest.raises(ValueError):
+        pipe.collect(0)          # long since overwritten
+
+
 def test_multigpu_driver(ctb):
     """Single-process multi-device driver: strided shards, gather in the original order.  With one
     visible device it degenerates to one shard; with several the result must not change."""
