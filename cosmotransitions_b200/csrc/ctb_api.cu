@@ -456,16 +456,28 @@ int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, cons
 // scipy.integrate.simpson on the non-uniform R is linear in the integrand, S = sum_j w_j y_j: lane-strided
 // points, each lane forms its point's weight from the five neighbouring abscissae (coalesced reads) and
 // evaluates the integrand once; warp-shuffle reduction; lane 0 adds the bulk term of the bubble interior.
-CTB_DEV void simpson_pair_w(double x0, double x1, double x2, double &w0, double &w1, double &w2)
+// one Simpson pair of scipy.integrate.simpson on unequal spacing (_quadrature.py:_basic_simpson)
+CTB_DEV double simpson_pair_sum(double x0, double x1, double x2, double y0, double y1, double y2)
 {
     const double h0 = x1 - x0, h1 = x2 - x1, hsum = h0 + h1, hprod = h0 * h1;
-    const double h0divh1 = (h1 != 0) ? h0 / h1 : 0.0; // scipy's guarded divisions
+    if (hprod > 0 && hprod < 1e300) { // regular spacing: h0/h1, h1/h0 and hsum/hprod from one Newton reciprocal
+        const double rp = rcp_fast(hprod);
+        return (hsum * (1.0 / 6.0)) * (y0 * (2.0 - h1 * h1 * rp) + y1 * (hsum * (hsum * rp)) + y2 * (2.0 - h0 * h0 * rp));
+    }
+    const double h0divh1 = (h1 != 0) ? h0 / h1 : 0.0; // scipy's guarded divisions (repeated abscissae)
     const double inv = (h0divh1 != 0) ? 1.0 / h0divh1 : 0.0;
     const double q = (hprod != 0) ? hsum / hprod : 0.0;
-    const double c = hsum / 6.0;
-    w0 = c * (2.0 - inv); w1 = c * (hsum * q); w2 = c * (2.0 - h0divh1);
+    return (hsum / 6.0) * (y0 * (2.0 - inv) + y1 * (hsum * q) + y2 * (2.0 - h0divh1));
 }
 
+#define FA_U 4                     // points per lane and chunk
+#define FA_PTS (FA_U * 32)         // a chunk = 64 Simpson pairs = 129 points (the last one is shared with the next chunk)
+#define FA_ROW (FA_PTS + 8)
+// findAction for given profiles (tunneling1D.py:763-791): one WARP per profile, HBM-streaming (24 B per point in).
+// Per chunk of 128 points: phase A -- every lane turns its four points (r, phi, phi') into the integrand and stages
+// (r, y) in shared memory; the loads of the NEXT chunk are issued before the arithmetic of this one (double
+// buffering in registers); phase B -- every lane sums two Simpson pairs from the staged values (one reciprocal per
+// pair, no divergence between odd and even points).
 template <class Pot>
 __global__ void __launch_bounds__(128) find_action_kernel(const double *__restrict__ params, JTab jb, JTab jf,
                                                           const double *__restrict__ phi_meta,
@@ -475,6 +487,7 @@ __global__ void __launch_bounds__(128) find_action_kernel(const double *__restri
                                                           double afac, double vfac, double *__restrict__ S)
 {
     extern __shared__ double smem[];
+    __shared__ double fa_r[4 * FA_ROW], fa_y[4 * FA_ROW];
     if (!Pot::analytic) {
         jb = stage_table_compact(jb, smem);
         __syncthreads();
@@ -490,35 +503,52 @@ __global__ void __launch_bounds__(128) find_action_kernel(const double *__restri
     const double Vm = pot.V_quad(phi_meta[i]);
     const int nb = (N & 1) ? N : N - 1; // composite rule on the first nb points
     const int ialpha = (alpha == (double)(int)alpha) ? (int)alpha : -1;
-    double acc = 0.0;
-    for (int j = lane; j < N; j += 32) {
-        double w = 0.0, w0, w1, w2;
-        if (N == 2) {
-            w = 0.5 * (r[1] - r[0]);
-        } else {
-            if (j & 1) {
-                if (j <= nb - 2) { simpson_pair_w(r[j - 1], r[j], r[j + 1], w0, w1, w2); w = w1; }
-            } else {
-                if (j >= 2 && j <= nb - 1) { simpson_pair_w(r[j - 2], r[j - 1], r[j], w0, w1, w2); w = w2; }
-                if (j <= nb - 3) { simpson_pair_w(r[j], r[j + 1], r[j + 2], w0, w1, w2); w += w0; }
-            }
-            if (!(N & 1) && j >= N - 3) { // even N: Cartwright's correction for the last interval
-                const double h0 = r[N - 2] - r[N - 3], h1 = r[N - 1] - r[N - 2];
-                double num, den;
-                if (j == N - 1) { num = 2 * h1 * h1 + 3 * h0 * h1; den = 6 * (h1 + h0); w += (den != 0) ? num / den : 0.0; }
-                else if (j == N - 2) { num = h1 * h1 + 3.0 * h0 * h1; den = 6 * h0; w += (den != 0) ? num / den : 0.0; }
-                else { num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1); w -= (den != 0) ? num / den : 0.0; }
-            }
-        }
-        const double rj = r[j], d = dp[j];
+    auto integrand = [&](double rj, double phj, double dpj) {
         const double ra = (ialpha == 2) ? rj * rj : (ialpha == 3) ? rj * rj * rj : (ialpha == 0) ? 1.0 : pow(rj, alpha);
-        acc += w * ((0.5 * (d * d) + pot.V_quad(ph[j]) - Vm) * (ra * afac));
+        return (0.5 * (dpj * dpj) + pot.V_quad(phj) - Vm) * ra;
+    };
+    double *sr = fa_r + (threadIdx.x >> 5) * FA_ROW, *sy = fa_y + (threadIdx.x >> 5) * FA_ROW;
+    double rn[FA_U + 1], pn[FA_U + 1], dn[FA_U + 1]; // slot FA_U: the chunk's 129th point (lane 0 only)
+    auto fetch = [&](int base) {
+#pragma unroll
+        for (int u = 0; u <= FA_U; u++) {
+            const int j = base + 32 * u + lane;
+            const bool on = j < N && (u < FA_U || lane == 0);
+            rn[u] = on ? __ldcs(r + j) : 0.0; pn[u] = on ? __ldcs(ph + j) : 0.0; dn[u] = on ? __ldcs(dp + j) : 0.0;
+        }
+    };
+    double acc = 0.0;
+    fetch(0);
+    for (int base = 0; base < nb - 1; base += FA_PTS) {
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u <= FA_U; u++) {
+            if (u < FA_U || lane == 0) { sr[32 * u + lane] = rn[u]; sy[32 * u + lane] = integrand(rn[u], pn[u], dn[u]); }
+        }
+        if (base + FA_PTS < nb - 1) fetch(base + FA_PTS); // in flight while the pairs of this chunk are summed
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < FA_U / 2; v++) {
+            const int a = 2 * (lane + 32 * v);            // local index of the pair's first point
+            if (base + a + 2 <= nb - 1)
+                acc += simpson_pair_sum(sr[a], sr[a + 1], sr[a + 2], sy[a], sy[a + 1], sy[a + 2]);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
+        if (N == 2) acc = 0.5 * (r[1] - r[0]) * (integrand(r[1], ph[1], dp[1]) + integrand(r[0], ph[0], dp[0]));
+        else if (!(N & 1)) { // even N: Cartwright's correction for the last interval (scipy.integrate.simpson)
+            const double h0 = r[N - 2] - r[N - 3], h1 = r[N - 1] - r[N - 2];
+            double num, den, al, be, et;
+            num = 2 * h1 * h1 + 3 * h0 * h1; den = 6 * (h1 + h0); al = (den != 0) ? num / den : 0.0;
+            num = h1 * h1 + 3.0 * h0 * h1; den = 6 * h0; be = (den != 0) ? num / den : 0.0;
+            num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1); et = (den != 0) ? num / den : 0.0;
+            acc += al * integrand(r[N - 1], ph[N - 1], dp[N - 1]) + be * integrand(r[N - 2], ph[N - 2], dp[N - 2])
+                   - et * integrand(r[N - 3], ph[N - 3], dp[N - 3]);
+        }
         const double r0 = r[0];
         const double rd = (ialpha == 2) ? r0 * r0 * r0 : (ialpha == 3) ? (r0 * r0) * (r0 * r0) : pow(r0, alpha + 1.0);
-        S[i] = acc + (rd * vfac) * (pot.V_quad(ph[0]) - Vm);
+        S[i] = acc * afac + (rd * vfac) * (pot.V_quad(ph[0]) - Vm);
     }
 }
 
