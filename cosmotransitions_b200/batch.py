@@ -312,7 +312,8 @@ class BouncePipeline:
 
     def submit(self, params, phi_absMin, phi_metaMin):
         """Queue one batch (CPU tensors / arrays of n rows); returns its ticket.  Does not block on the GPU, except
-        that a slot is reused only after its previous results have been copied out."""
+        that a slot is reused only after its previous results have been copied out.  Pinned input tensors are
+        copied asynchronously: leave them unchanged until collect(ticket) has returned."""
         torch = self._torch
         k = self._submitted
         slot = self._slots[k % self.depth]
