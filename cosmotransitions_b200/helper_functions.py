@@ -9,19 +9,17 @@ class IntegrationError(Exception):
 
 
 def monotonicIndices(x):
-    """
-    Returns the indices of `x` such that `x[i]` is purely increasing
-    (helper_functions.py:57-75; host-side helper of evenlySpacedPhi).
-    """
+    """Indices of `x` that leave a strictly increasing subsequence between the first and the last entry (what
+    helper_functions.py:57-75 computes point by point; host-side helper of evenlySpacedPhi).  Vectorised: an interior
+    point survives iff it lies below the last value and above every earlier survivor, i.e. it is a record high of the
+    candidates below x[-1], the first entry being the initial record."""
     import numpy as np
-    x = np.array(x)
-    is_reversed = x[0] > x[-1]
-    if is_reversed:
-        x = x[::-1]
-    keep = [0]
-    for i in range(1, len(x) - 1):
-        if x[i] > x[keep[-1]] and x[i] < x[-1]:
-            keep.append(i)
-    keep.append(len(x) - 1)
-    keep = np.array(keep)
-    return len(x) - 1 - keep if is_reversed else keep
+    x = np.asarray(x)
+    flipped = x[0] > x[-1]
+    y = x[::-1] if flipped else x
+    last = len(y) - 1
+    inner = y[1:last]
+    below_end = inner < y[last]
+    record = np.maximum.accumulate(np.concatenate(([y[0]], np.where(below_end, inner, -np.inf))))[:-1]
+    idx = np.concatenate(([0], np.nonzero(below_end & (inner > record))[0] + 1, [last]))
+    return last - idx if flipped else idx

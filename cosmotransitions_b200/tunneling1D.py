@@ -116,23 +116,19 @@ class SingleFieldInstanton:
         one ~750-point profile for the multi-field caller, pathDeformation.py:967-968).  k=1 (the only
         value the reference passes) is plain linear interpolation.
         """
-        phi, dphi = np.asarray(phi, dtype=float), np.asarray(dphi, dtype=float)
-        if fixAbs is True:
-            phi = np.append(self.phi_absMin, np.append(phi, self.phi_metaMin))
-            dphi = np.append(0.0, np.append(dphi, 0.0))
-        else:
-            phi = np.append(phi, self.phi_metaMin)
-            dphi = np.append(dphi, 0.0)
-        i = monotonicIndices(phi)
-        if fixAbs:
-            p = np.linspace(self.phi_absMin, self.phi_metaMin, npoints)
-        else:
-            p = np.linspace(phi[i][0], self.phi_metaMin, npoints)
+        # pad with the end points the profile is known to reach (phi' = 0 there), drop whatever is not monotonic
+        pad_phi, pad_dphi = ([self.phi_absMin], [0.0]) if fixAbs is True else ([], [])
+        grid = np.concatenate([pad_phi, np.asarray(phi, dtype=float), [self.phi_metaMin]])
+        vals = np.concatenate([pad_dphi, np.asarray(dphi, dtype=float), [0.0]])
+        keep = monotonicIndices(grid)
+        grid, vals = grid[keep], vals[keep]
+        p = np.linspace(self.phi_absMin if fixAbs else grid[0], self.phi_metaMin, npoints)
         if k == 1:
-            dp = np.interp(p, phi[i], dphi[i])
+            # a degree-1 interpolating spline is the piecewise-linear interpolant (np.interp wants ascending abscissae)
+            dp = np.interp(p, grid, vals) if grid[0] <= grid[-1] else np.interp(p, grid[::-1], vals[::-1])
         else:
             from scipy import interpolate
-            dp = interpolate.splev(p, interpolate.splrep(phi[i], dphi[i], k=k))
+            dp = interpolate.splev(p, interpolate.splrep(grid, vals, k=k))
         return p, dp
 
 

@@ -203,3 +203,26 @@ def test_bench_reference_arm_contract():
     assert j["value"] > 1e3 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert j["config"]["workload"].startswith("C2") and j["solved_fraction"] == 1.0
+
+
+def test_monotonic_indices_matches_the_sequential_definition():
+    """helper_functions.monotonicIndices (vectorised) against the point-by-point rule of helper_functions.py:57-75."""
+    from cosmotransitions_b200.helper_functions import monotonicIndices
+
+    def sequential(x):
+        x = np.array(x)
+        flipped = x[0] > x[-1]
+        if flipped:
+            x = x[::-1]
+        kept = [0]
+        for i in range(1, len(x) - 1):
+            if x[kept[-1]] < x[i] < x[-1]:
+                kept.append(i)
+        kept = np.array(kept + [len(x) - 1])
+        return len(x) - 1 - kept if flipped else kept
+
+    rng = np.random.default_rng(0)
+    for t in range(500):
+        n = int(rng.integers(2, 40))
+        x = np.cumsum(rng.normal(0.2 * rng.choice([-1, 1]), 1, n)) if t % 2 else rng.integers(0, 6, n).astype(float)
+        assert np.array_equal(monotonicIndices(x), sequential(x))
