@@ -9,7 +9,83 @@ from . import _lib, _tables
 from .potentials import model1_model8, Model1LinePotential, Thermal1FPotential, thermal1f_params
 
 
-class model1:
+def _stencil1(eps, order, deriv):
+    """(offset, weight) pairs of helper_functions.gradientFunction / hessianFunction for one direction
+    (helper_functions.py:446-461, 522-528): first or second derivative, order 2 or 4."""
+    if order == 2:
+        return ([(-eps, -.5 / eps), (eps, .5 / eps)] if deriv == 1 else
+                [(-eps, 1. / (eps * eps)), (0.0, -2. / (eps * eps)), (eps, 1. / (eps * eps))])
+    if deriv == 1:
+        return [(k * eps, w / (12. * eps)) for k, w in ((-2, 1.), (-1, -8.), (1, 8.), (2, -1.))]
+    return [(k * eps, w / (12. * eps * eps)) for k, w in ((-2, -1.), (-1, 16.), (0, -30.), (1, 16.), (2, -1.))]
+
+
+class _FiniteDifferences:
+    """gradV, d2V, dgradV_dT, energyDensity, massSqMatrix of generic_potential (generic_potential.py:347-456) as finite
+    differences of the device Vtot / V1T: every stencil point of every input point goes into ONE kernel launch
+    (`self._combo`), the weighted sum is formed on the device.  Needs Ndim, x_eps, T_eps, deriv_order, _combo."""
+
+    x_eps, T_eps, deriv_order = .001, .001, 4
+
+    def _unit(self, i, h):
+        e = np.zeros(self.Ndim)
+        e[i] = h
+        return e
+
+    def gradV(self, X, T):
+        """Gradient of Vtot (radiation terms off); same shape as X (generic_potential.py:347-367)."""
+        comps = [self._combo(X, T, _lib.V_TOTAL, False, [(self._unit(i, h), 0.0, w)
+                                                        for h, w in _stencil1(self.x_eps, self.deriv_order, 1)])
+                 for i in range(self.Ndim)]
+        return _stack(comps, -1)
+
+    def d2V(self, X, T, parts=None):
+        """Hessian of Vtot (radiation terms off); shape X.shape + (Ndim,) (generic_potential.py:419-442)."""
+        parts = _lib.V_TOTAL if parts is None else parts
+        s1, s2 = _stencil1(self.x_eps, self.deriv_order, 1), _stencil1(self.x_eps, self.deriv_order, 2)
+        rows = []
+        for i in range(self.Ndim):
+            row = []
+            for j in range(self.Ndim):
+                if i == j:
+                    sh = [(self._unit(i, h), 0.0, w) for h, w in s2]
+                else:   # product of two first-derivative stencils (helper_functions.py:505-519)
+                    sh = [(self._unit(i, hi) + self._unit(j, hj), 0.0, wi * wj) for hi, wi in s1 for hj, wj in s1]
+                row.append(self._combo(X, T, parts, False, sh) if j >= i else None)
+            rows.append(row)
+        for i in range(self.Ndim):
+            for j in range(i):
+                rows[i][j] = rows[j][i]
+        return _stack([_stack(r, -1) for r in rows], -2)
+
+    def massSqMatrix(self, X):
+        """Hessian of the tree-level potential V0 (generic_potential.py:390-417)."""
+        return self.d2V(X, 0.0, parts=_lib.V_TREE)
+
+    def dgradV_dT(self, X, T):
+        """d/dT of the gradient, from V1T alone (generic_potential.py:369-388)."""
+        sx, sT = _stencil1(self.x_eps, self.deriv_order, 1), _stencil1(self.T_eps, self.deriv_order, 1)
+        comps = [self._combo(X, T, _lib.V_THERMAL, False, [(self._unit(i, hx), hT, wx * wT) for hx, wx in sx for hT, wT in sT])
+                 for i in range(self.Ndim)]
+        return _stack(comps, -1)
+
+    def energyDensity(self, X, T, include_radiation=True):
+        """V - T dV/dT with the temperature derivative taken from V1T (generic_potential.py:443-456)."""
+        dVdT = self._combo(X, T, _lib.V_THERMAL, include_radiation,
+                           [(np.zeros(self.Ndim), hT, w) for hT, w in _stencil1(self.T_eps, self.deriv_order, 1)])
+        V = self._combo(X, T, _lib.V_TOTAL, include_radiation, [(np.zeros(self.Ndim), 0.0, 1.0)])
+        Tb = T if hasattr(dVdT, "is_cuda") else np.asarray(T, dtype=np.float64)
+        return V - Tb * dVdT
+
+
+def _stack(parts, axis):
+    if hasattr(parts[0], "is_cuda"):
+        import torch
+        return torch.stack(list(parts), dim=axis)
+    return np.stack([np.asarray(p) for p in parts], axis=axis)
+
+
+class model1(_FiniteDifferences):
     """Same constructor parameters as examples/testModel1.py:model1.init."""
 
     Ndim = 2
@@ -36,6 +112,11 @@ class model1:
         return self._eval(X, T, _lib.V_TOTAL) - self._eval(X0, T, _lib.V_TOTAL)
 
     def _eval(self, X, T, parts):
+        return self._combo(X, T, parts, True, None)
+
+    def _combo(self, X, T, parts, include_radiation, shifts):
+        """sum_k w_k V(X + dx_k, T + dT_k) over shifts = [(dx[2], dT, w), ...] in one launch (None: plain evaluation).
+        model1 sets no num_boson_dof / num_fermion_dof, so include_radiation changes nothing."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         is_tensor = isinstance(X, torch.Tensor)
@@ -46,11 +127,17 @@ class model1:
         shape = torch.broadcast_shapes(Xd.shape[:-1], Td.shape)
         Xf = Xd.expand(shape + (2,)).contiguous().reshape(-1, 2)
         Tf = Td.expand(shape).contiguous().reshape(-1)
+        n = Tf.numel()
+        if shifts is not None:
+            Xf = torch.cat([Xf + torch.as_tensor(dx, dtype=torch.float64, device=dev) for dx, _, _ in shifts]).contiguous()
+            Tf = torch.cat([Tf + dT for _, dT, _ in shifts]).contiguous()
         out = torch.empty(Tf.shape, dtype=torch.float64, device=dev)
         tabs = _tables.device_tables(dev)
         with torch.cuda.device(dev):
             _lib.check(lib.ctb_vtot_model1(self._m8, tabs.jb, Xf.data_ptr(), Tf.data_ptr(), out.data_ptr(), Tf.numel(),
                                            parts, torch.cuda.current_stream(dev).cuda_stream), "ctb_vtot_model1")
+        if shifts is not None:
+            out = sum(w * out[k * n:(k + 1) * n] for k, (_, _, w) in enumerate(shifts))
         out = out.reshape(shape)
         if is_tensor:
             return out if X.is_cuda else out.cpu()
@@ -86,7 +173,7 @@ class model1:
         return Model1LinePotential(x_abs, (x_meta - x_abs) / L, T, self.model8), L
 
 
-class one_field_model:
+class one_field_model(_FiniteDifferences):
     """A general ONE-field generic_potential (generic_potential.py:26-345) on the device: quartic tree-level
     potential V0 = sum_k V0_coefs[k] phi^k, bosons with m^2 = a + b phi^2 + t T^2 (dof, c), fermions with
     m^2 = a + b phi^2 (dof) -- the data a subclass would return from V0 / boson_massSq / fermion_massSq
@@ -120,8 +207,8 @@ class one_field_model:
             rad += (self.num_fermion_dof - sum(f[2] for f in self.fermions)) * 7 * np.pi ** 4 / 360.
         return rad
 
-    def _eval(self, X, T, parts, include_radiation=True, shifts=None):
-        """sum_k w_k V(X + dx_k, T + dT_k) for shifts = [(dx, dT, w), ...] in one launch (finite differences)."""
+    def _combo(self, X, T, parts, include_radiation=True, shifts=None):
+        """sum_k w_k V(X + dx_k, T + dT_k) for shifts = [(dx[1], dT, w), ...] in one launch (finite differences)."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         is_tensor = isinstance(X, torch.Tensor)
@@ -134,8 +221,8 @@ class one_field_model:
         shape = torch.broadcast_shapes(Xd.shape[:-1], Td.shape)
         phi = Xd[..., 0].expand(shape).reshape(-1)
         Tf = Td.expand(shape).reshape(-1)
-        shifts = shifts or [(0.0, 0.0, 1.0)]
-        phis = torch.cat([phi + dx for dx, _, _ in shifts]).contiguous()
+        shifts = shifts or [(np.zeros(1), 0.0, 1.0)]
+        phis = torch.cat([phi + float(np.asarray(dx).reshape(-1)[0]) for dx, _, _ in shifts]).contiguous()
         Ts = torch.cat([Tf + dT for _, dT, _ in shifts]).contiguous()
         out = torch.empty_like(phis)
         tabs = _tables.device_tables(dev)
@@ -152,46 +239,13 @@ class one_field_model:
 
     def Vtot(self, X, T, include_radiation=True):
         """The total finite temperature effective potential (generic_potential.py:312-337)."""
-        return self._eval(X, T, _lib.V_TOTAL, include_radiation)
+        return self._combo(X, T, _lib.V_TOTAL, include_radiation)
 
     def V1T_from_X(self, X, T, include_radiation=True):
         """The one-loop finite-temperature part alone (generic_potential.py:298-310)."""
-        return self._eval(X, T, _lib.V_THERMAL, include_radiation)
+        return self._combo(X, T, _lib.V_THERMAL, include_radiation)
 
     def DVtot(self, X, T):
         """Vtot offset such that V(0, T) = 0 (generic_potential.py:339-345)."""
         X0 = np.zeros(self.Ndim)
         return self.Vtot(X, T, False) - self.Vtot(X0, T, False)
-
-    def _stencil(self, eps, order):
-        # helper_functions.deriv14 / gradientFunction coefficients (helper_functions.py:400-520)
-        if self.deriv_order == 2:
-            return ([(-eps, -.5 / eps), (eps, .5 / eps)] if order == 1 else
-                    [(-eps, 1. / eps ** 2), (0.0, -2. / eps ** 2), (eps, 1. / eps ** 2)])
-        if order == 1:
-            return [(-2 * eps, 1 / (12. * eps)), (-eps, -8 / (12. * eps)), (eps, 8 / (12. * eps)), (2 * eps, -1 / (12. * eps))]
-        return [(-2 * eps, -1 / (12. * eps * eps)), (-eps, 16 / (12. * eps * eps)), (0.0, -30 / (12. * eps * eps)),
-                (eps, 16 / (12. * eps * eps)), (2 * eps, -1 / (12. * eps * eps))]
-
-    def gradV(self, X, T):
-        """Gradient of Vtot (no radiation term) by finite differences in phi; shape X.shape (generic_potential.py:347-367)."""
-        g = self._eval(X, T, _lib.V_TOTAL, False, [(dx, 0.0, w) for dx, w in self._stencil(self.x_eps, 1)])
-        return g[..., None] if hasattr(g, "shape") else np.array([g])
-
-    def d2V(self, X, T):
-        """Second derivative (the 1 x 1 Hessian) of Vtot; shape X.shape[:-1] + (1, 1) (generic_potential.py:390-408)."""
-        h = self._eval(X, T, _lib.V_TOTAL, False, [(dx, 0.0, w) for dx, w in self._stencil(self.x_eps, 2)])
-        return h[..., None, None] if hasattr(h, "shape") else np.array([[h]])
-
-    def dgradV_dT(self, X, T):
-        """d/dT of gradV from V1T alone (generic_potential.py:369-388)."""
-        sx, sT = self._stencil(self.x_eps, 1), self._stencil(self.T_eps, 1)
-        g = self._eval(X, T, _lib.V_THERMAL, False, [(dx, dT, wx * wT) for dx, wx in sx for dT, wT in sT])
-        return g[..., None] if hasattr(g, "shape") else np.array([g])
-
-    def energyDensity(self, X, T, include_radiation=True):
-        """V - T dV/dT, the temperature derivative from V1T by finite differences (generic_potential.py:443-456)."""
-        dVdT = self._eval(X, T, _lib.V_THERMAL, include_radiation,
-                          [(0.0, dT, w) for dT, w in self._stencil(self.T_eps, 1)])
-        Tb = T if hasattr(dVdT, "is_cuda") else np.asarray(T, dtype=np.float64)
-        return self.Vtot(X, T, include_radiation) - Tb * dVdT

@@ -23,6 +23,7 @@ It does not travel to the GPU box, so everything the tests need is frozen into s
   tests/golden/findaction.json  findAction on given (truncated / strided) profiles, alpha in {1, 2, 2.5, 3, 4}
   tests/golden/jexact.npz       Jb / Jf with approx='exact' (deriv 0, 1), Jb_exact2 / Jf_exact2 incl. theta < 0, + mpmath values
   tests/golden/wall.json        WallWithConstFriction.findProfile on the quartic family (F, rf, sampled profile, errors)
+  tests/golden/model1_derivs.npz gradV / d2V / dgradV_dT / energyDensity / massSqMatrix of examples/testModel1.py
   tests/golden/VERSIONS.json    numpy / scipy versions (scipy is part of the oracle)
 """
 import json
@@ -686,6 +687,25 @@ def gen_wall():
         json.dump(cases, f, indent=0)
 
 
+def gen_model1_derivs():
+    """generic_potential.gradV / d2V / dgradV_dT / energyDensity / massSqMatrix for examples/testModel1.py
+    (finite differences of Vtot, generic_potential.py:347-456) -> tests/golden/model1_derivs.npz"""
+    import testModel1
+    m = testModel1.model1()
+    rng = np.random.default_rng(55)
+    X = rng.uniform(-350, 350, (48, 2))
+    T = rng.uniform(5, 250, 48)
+    out = dict(X=X, T=T, gradV=m.gradV(X, T), d2V=m.d2V(X, T), dgradV_dT=m.dgradV_dT(X, T),
+               energyDensity=m.energyDensity(X, T), massSqMatrix=m.massSqMatrix(X),
+               gradV_point=m.gradV(np.array([200., 150.]), 90.0), d2V_point=m.d2V(np.array([200., 150.]), 90.0))
+    # broadcasting: 6 field points against 4 temperatures
+    Xg = np.broadcast_to(X[:6, None, :], (6, 4, 2))
+    out["grid_T"] = T[:4]
+    out["grid_gradV"] = m.gradV(Xg, T[None, :4])
+    np.savez(os.path.join(GOLD, "model1_derivs.npz"), **out)
+    print({k: np.asarray(v).shape for k, v in out.items()})
+
+
 def gen_alpha14():
     """alpha = 1 and 4 (d = 2 and 5 dimensions, Bessel order nu = 0 and 3/2): quartic family, a few knob sets,
     and exactSolution unit vectors -> tests/golden/alpha14.json"""
@@ -727,7 +747,7 @@ def gen_alpha14():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall"]
+                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

@@ -508,6 +508,31 @@ def test_model1_vtot_golden(ctb, gold_dir):
     np.testing.assert_allclose(Vb, ref, rtol=1e-11, atol=1e-13 * scale)
 
 
+def test_model1_finite_difference_surface(ctb, gold_dir):
+    """generic_potential.gradV / d2V / dgradV_dT / energyDensity / massSqMatrix for model1: finite differences of the
+    device Vtot (all stencil points of all inputs in one launch) against the reference's own finite differences."""
+    from cosmotransitions_b200 import generic_potential as gp
+    g = np.load(os.path.join(gold_dir, "model1_derivs.npz"))
+    m = gp.model1()
+    X, T = g["X"], g["T"]
+    Vs = np.abs(m.Vtot(X, T)).max()
+    # rounding noise of differencing a ~1e9-sized potential with steps of 1e-3: ~1e-16 Vs / h, / h^2, / h^2
+    got = m.gradV(X, T)
+    assert got.shape == g["gradV"].shape
+    np.testing.assert_allclose(got, g["gradV"], rtol=1e-7, atol=2e-13 * Vs / 1e-3)
+    got = m.d2V(X, T)
+    assert got.shape == g["d2V"].shape and np.array_equal(got[..., 0, 1], got[..., 1, 0])
+    np.testing.assert_allclose(got, g["d2V"], rtol=1e-6, atol=2e-13 * Vs / 1e-6)
+    np.testing.assert_allclose(m.dgradV_dT(X, T), g["dgradV_dT"], rtol=1e-5, atol=2e-13 * Vs / 1e-6)
+    np.testing.assert_allclose(m.energyDensity(X, T), g["energyDensity"], rtol=1e-7, atol=1e-9 * Vs)
+    np.testing.assert_allclose(m.massSqMatrix(X), g["massSqMatrix"], rtol=1e-6, atol=2e-13 * Vs / 1e-6)
+    np.testing.assert_allclose(m.gradV(np.array([200., 150.]), 90.0), g["gradV_point"], rtol=1e-7, atol=2e-13 * Vs / 1e-3)
+    np.testing.assert_allclose(m.d2V(np.array([200., 150.]), 90.0), g["d2V_point"], rtol=1e-6, atol=2e-13 * Vs / 1e-6)
+    got = m.gradV(X[:6, None, :], g["grid_T"][None, :])
+    assert got.shape == g["grid_gradV"].shape
+    np.testing.assert_allclose(got, g["grid_gradV"], rtol=1e-7, atol=2e-13 * Vs / 1e-3)
+
+
 def test_model1_line_bounces_golden(ctb, gold_dir):
     from cosmotransitions_b200 import generic_potential as gp, tunneling1D as t1
     g = np.load(os.path.join(gold_dir, "model1.npz"))
