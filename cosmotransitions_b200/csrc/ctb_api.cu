@@ -470,6 +470,9 @@ CTB_DEV double simpson_pair_sum(double x0, double x1, double x2, double y0, doub
     return (hsum / 6.0) * (y0 * (2.0 - inv) + y1 * (hsum * q) + y2 * (2.0 - h0divh1));
 }
 
+#ifndef FA_MIN_BLOCKS
+#define FA_MIN_BLOCKS 6
+#endif
 #define FA_U 4                     // points per lane and chunk
 #define FA_PTS (FA_U * 32)         // a chunk = 64 Simpson pairs = 129 points (the last one is shared with the next chunk)
 #define FA_ROW (FA_PTS + 8)
@@ -479,7 +482,7 @@ CTB_DEV double simpson_pair_sum(double x0, double x1, double x2, double y0, doub
 // buffering in registers); phase B -- every lane sums two Simpson pairs from the staged values (one reciprocal per
 // pair, no divergence between odd and even points).
 template <class Pot>
-__global__ void __launch_bounds__(128) find_action_kernel(const double *__restrict__ params, JTab jb, JTab jf,
+__global__ void __launch_bounds__(128, FA_MIN_BLOCKS) find_action_kernel(const double *__restrict__ params, JTab jb, JTab jf,
                                                           const double *__restrict__ phi_meta,
                                                           const double *__restrict__ R, const double *__restrict__ Phi,
                                                           const double *__restrict__ dPhi, int64_t stride,
