@@ -78,6 +78,40 @@ class _FiniteDifferences:
         return V - Tb * dVdT
 
 
+    def findMinimum(self, X=None, T=0.0, max_iter=60, xtol=1e-9):
+        """The minimum of Vtot(., T) nearest to `X` (generic_potential.py:477-484, where it is one
+        scipy.optimize.fmin call per point).  Batched: X [..., Ndim] against T [...], every point iterates a damped
+        Newton step X <- X - (H + lam I)^-1 grad V with the device gradV / d2V (lam lifts a non-positive Hessian,
+        steps are capped at a tenth of |X| + 1 and halved while they do not lower V) until all points move by less
+        than xtol (|X| + 1).  Returns an array of the broadcast shape + (Ndim,)."""
+        if X is None:
+            X = self.approxZeroTMin()[0]
+        X = np.array(np.broadcast_to(np.asarray(X, dtype=np.float64),
+                                     np.broadcast_shapes(np.shape(X)[:-1], np.shape(T)) + (self.Ndim,)))
+        T = np.array(np.broadcast_to(np.asarray(T, dtype=np.float64), X.shape[:-1]))
+        eye = np.eye(self.Ndim)
+        V = np.asarray(self._combo(X, T, _lib.V_TOTAL, False, None))
+        for _ in range(max_iter):
+            g, H = np.asarray(self.gradV(X, T)), np.asarray(self.d2V(X, T))
+            lo = np.linalg.eigvalsh(H)[..., 0]
+            lam = np.where(lo > 0, 0.0, 1e-3 * np.abs(lo) - lo + 1e-12)
+            step = -np.linalg.solve(H + lam[..., None, None] * eye, g[..., None])[..., 0]
+            cap = 0.1 * (np.linalg.norm(X, axis=-1) + 1.0)
+            norm = np.linalg.norm(step, axis=-1)
+            step *= np.minimum(1.0, cap / np.maximum(norm, 1e-300))[..., None]
+            for _half in range(30):      # backtrack where the step does not lower V (beyond rounding noise)
+                Vn = np.asarray(self._combo(X + step, T, _lib.V_TOTAL, False, None))
+                worse = Vn > V + 1e-13 * np.abs(V)
+                if not worse.any():
+                    break
+                step = np.where(worse[..., None], 0.5 * step, step)
+            X = X + step
+            V = np.asarray(self._combo(X, T, _lib.V_TOTAL, False, None))
+            if np.all(np.linalg.norm(step, axis=-1) <= xtol * (np.linalg.norm(X, axis=-1) + 1.0)):
+                break
+        return X
+
+
 def _stack(parts, axis):
     if hasattr(parts[0], "is_cuda"):
         import torch
@@ -165,6 +199,11 @@ class model1(_FiniteDifferences):
         if is_tensor and s.is_cuda:
             return out
         return out.cpu() if is_tensor else out.cpu().numpy()
+
+    def approxZeroTMin(self):
+        """The two tree-level minima (examples/testModel1.py:118-122)."""
+        v = float(self.v2) ** .5
+        return [np.array([v, v]), np.array([v, -v])]
 
     def line_potential(self, x_abs, x_meta, T):
         """Device functor of Vtot along the straight line from x_abs (phi = 0) to x_meta (phi = L)."""

@@ -533,6 +533,27 @@ def test_model1_finite_difference_surface(ctb, gold_dir):
     np.testing.assert_allclose(got, g["grid_gradV"], rtol=1e-7, atol=2e-13 * Vs / 1e-3)
 
 
+def test_model1_find_minimum_batched(ctb, gold_dir):
+    """generic_potential.findMinimum as a batched damped Newton iteration on the device gradV / d2V: both phases of
+    model1 at the seven temperatures of the golden file (found there by scipy.optimize.fmin, xtol 1e-8), started
+    from displaced points, all 14 minimisations in one batch; plus the T = 0 default start."""
+    from cosmotransitions_b200 import generic_potential as gp
+    g = np.load(os.path.join(gold_dir, "model1.npz"))
+    m = gp.model1()
+    T = np.concatenate([g["b_T"], g["b_T"]])
+    ref = np.concatenate([g["b_xlow"], g["b_xhigh"]])
+    rng = np.random.default_rng(3)
+    X0 = ref + rng.uniform(-12, 12, ref.shape)
+    X = m.findMinimum(X0, T)
+    assert X.shape == ref.shape
+    np.testing.assert_allclose(X, ref, rtol=0, atol=2e-5)
+    grad = m.gradV(X, T)
+    assert np.abs(grad).max() < 1e-2 * np.abs(m.gradV(X0, T)).max()
+    X00 = m.findMinimum()                          # X = approxZeroTMin()[0], T = 0
+    assert X00.shape == (2,) and np.abs(m.gradV(X00, 0.0)).max() < 1.0
+    assert m.Vtot(X00, 0.0) < m.Vtot(m.approxZeroTMin()[0], 0.0)
+
+
 def test_model1_line_bounces_golden(ctb, gold_dir):
     from cosmotransitions_b200 import generic_potential as gp, tunneling1D as t1
     g = np.load(os.path.join(gold_dir, "model1.npz"))
