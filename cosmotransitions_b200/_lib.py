@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 9
+ABI_VERSION = 10
 V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 EXACT_X, EXACT_DX, EXACT_THETA = 0, 1, 2
@@ -20,7 +20,7 @@ SPLINE_MAX_PIECES = 255
 THERMAL_KINDS = (POT_MODEL1_LINE, POT_MODEL1F, POT_THERMAL1F)   # need the Jb / Jf tables
 NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, POT_THERMAL1F: 64}
 (ST_CONVERGED, ST_XTOL, ST_STABLE, ST_NO_BARRIER, ST_RMAX, ST_DRMIN, ST_STEP_UNDERFLOW, ST_NONFINITE,
- ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN) = range(11)
+ ST_BRENT_SIGN, ST_FIRST_SHOT, ST_NOT_RUN, ST_MAXSTEPS) = range(12)
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",

@@ -597,8 +597,9 @@ CTB_API const char *ctb_status_string(int status)
     static const char *names[] = {"converged", "xtol reached", "stable, not metastable", "no barrier", "r > rmax",
                                   "dr < drmin", "Stepsize rounds down to zero.",
                                   "non-finite value in initialConditions root find", "brentq: same sign at both ends",
-                                  "non-finite initial conditions on the first shot", "not run"};
-    if (status < 0 || status > 10) return "unknown status";
+                                  "non-finite initial conditions on the first shot", "not run",
+                                  "more than CTB_MAX_STEPS integration steps"};
+    if (status < 0 || status > 11) return "unknown status";
     return names[status];
 }
 

@@ -845,7 +845,7 @@ struct Sfi {
         if (fabs(phi_r0 - phi_abs) > fabs(cutoff)) return 0;
         if (isnan(dphi_r0) || isnan(delta_phi0) || sgn(dphi_r0) != sgn(delta_phi0)) return 0;
         double r = rmin, rlast = rmin;
-        while (isfinite(r)) {
+        while (isfinite(r) && r > 0) { // (r > 0: a zero start radius would never leave this loop)
             rlast = r;
             r *= 10;
             double p = exact_solution<ALPHA>(r, ec).x;
@@ -1098,6 +1098,8 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     else x = -log(fabs((phi_bar - phi_abs) / (phi_meta - phi_abs)));
     const double rmin = k.rmin * rscale;
     const double dr0 = rmin, drmin = 0.01 * rmin, rmax_rel = k.rmax * rscale;
+    // guard (not in the reference, where this case never returns): zero or non-finite radial scale
+    if (phase != PH_DONE && !(rmin > 0.0 && rmin < INFINITY)) { res.status = CTB_ST_NONFINITE; phase = PH_DONE; }
     const double delta_phi = phi_meta - phi_abs;
     const double ea0 = fabs(delta_phi * phitol), ea1 = fabs(delta_phi / rscale * phitol);
     const double epsfrac = phitol;
@@ -1216,6 +1218,9 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 double dy0, dy1, drnext;
                 int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
                 if (e) { fail(e); break; }
+#ifndef CTB_NO_STEP_GUARD
+                if (s.n_rkck >= CTB_MAX_STEPS) { fail(CTB_ST_MAXSTEPS); break; } // guard, see ctbounce.h
+#endif
                 double r1, na, nb, inv_r1;
                 if (saving && dr < drmin) { // T1D:594-597
                     na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;

@@ -43,6 +43,7 @@ __device__ int wall_integrate(Sfi<Pot, CTB_ALPHA_WALL> &s, double y00, double y0
         double dy0, dy1, drnext;
         int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
         if (e) return e;
+        if (s.n_rkck >= 8 * CTB_MAX_STEPS) return CTB_ST_MAXSTEPS; // guard, see ctbounce.h (walls: ~1e5 steps to reach rmax)
         double r1, na, nb;
         if (SAVE && dr < drmin) { // T1D:594-597
             na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(128) wall_kernel(const WallArgs a)
         s.set_phi_eps(k.phi_eps * fabs(phi_abs - phi_meta));
         // findProfile (T1D:918-999)
         const double rmin = k.rmin * rscale, dr0 = rmin, drmin = 0.01 * rmin, rmax = k.rmax * rscale;
+        if (!(rmin > 0.0 && rmin < INFINITY)) { status = CTB_ST_NONFINITE; break; } // guard, see ctbounce.h
         const double delta_phi = phi_meta - phi_abs;
         const double ea0 = fabs(delta_phi * k.phitol), ea1 = fabs(delta_phi / rscale * k.phitol);
         double Fmin = 0.0, Fmax = INFINITY;

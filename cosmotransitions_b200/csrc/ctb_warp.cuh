@@ -58,6 +58,7 @@ __device__ void run_shot(Sfi<Pot, ALPHA> &s, const ShootConsts &c, double x, Sho
         double dy0, dy1, drnext;
         e = s.rkqs(ya, yb, da, db, r_, dr, c.epsfrac, c.inv_ea0, c.inv_ea1, dy0, dy1, drnext);
         if (e) { o.status = e; break; }
+        if (s.n_rkck - nrk0 >= CTB_MAX_STEPS) { o.status = CTB_ST_MAXSTEPS; break; } // guard, see ctbounce.h
         const double r1 = r_ + dr, na = ya + dy0, nb = yb + dy1;
         double nda, ndb;
         s.eom_inv(na, nb, s.inv_r_end, nda, ndb);
@@ -130,6 +131,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
     ShootConsts c;
     c.phi_abs = phi_abs; c.phi_meta = phi_meta; c.delta_phi = phi_meta - phi_abs;
     c.rmin = k.rmin * rscale; c.dr0 = c.rmin; c.drmin = 0.01 * c.rmin; c.rmax_rel = k.rmax * rscale;
+    if (!(c.rmin > 0.0 && c.rmin < INFINITY)) { res.status = CTB_ST_NONFINITE; return; } // guard, see ctbounce.h
     c.ea0 = fabs(c.delta_phi * phitol); c.ea1 = fabs(c.delta_phi / rscale * phitol);
     c.inv_ea0 = 1.0 / c.ea0; c.inv_ea1 = 1.0 / c.ea1; c.epsfrac = phitol;
     c.cutoff = k.thinCutoff * c.delta_phi;
@@ -237,7 +239,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
         int err = 0;
         int guard = 0;
         while (i_pt < npoints) {
-            if (++guard > (1 << 20)) { err = CTB_ST_RMAX; break; }
+            if (++guard > CTB_MAX_STEPS) { err = CTB_ST_MAXSTEPS; break; }
             double dy0, dy1, drnext;
             err = s.rkqs(ya, yb, da, db, r_, dr, c.epsfrac, c.inv_ea0, c.inv_ea1, dy0, dy1, drnext);
             if (err) break;

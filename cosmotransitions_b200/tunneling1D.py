@@ -39,6 +39,7 @@ _ERRORS = {
     _lib.ST_RMAX: lambda: IntegrationError("r > rmax"),
     _lib.ST_DRMIN: lambda: IntegrationError("dr < drmin"),
     _lib.ST_STEP_UNDERFLOW: lambda: IntegrationError("Stepsize rounds down to zero."),
+    _lib.ST_MAXSTEPS: lambda: IntegrationError("more than 2**20 integration steps (guard of the GPU solver)"),
     _lib.ST_NONFINITE: lambda: ValueError("The function value in the initialConditions root find is NaN; "
                                           "solver cannot continue."),
     _lib.ST_BRENT_SIGN: lambda: ValueError("f(a) and f(b) must have different signs"),

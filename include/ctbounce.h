@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 9
+#define CTB_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -53,6 +53,13 @@ extern "C" {
 #define CTB_ST_BRENT_SIGN 8      /* ValueError from brentq: same signs     tunneling1D.py:432,519,523 */
 #define CTB_ST_FIRST_SHOT 9      /* AssertionError                         tunneling1D.py:710   */
 #define CTB_ST_NOT_RUN 10
+/* Guard that the reference does not have: an instance may take at most CTB_MAX_STEPS Cash-Karp attempts in total
+ * (valid bounces need 1e2..1e4; the wall solver, whose legitimate "r > rmax" runs take ~1e5 steps, allows 8x as
+ * many); beyond that it is abandoned instead of occupying the GPU for hours (the reference would keep stepping until
+ * r > rmax, up to rmax/drmin = 1e10 steps per shot).  Likewise a set-up whose radial scale is zero or not finite
+ * (where the reference's start-radius search never returns) ends with CTB_ST_NONFINITE.                       */
+#define CTB_ST_MAXSTEPS 11
+#define CTB_MAX_STEPS (1 << 20)
 
 /* ---- potential functors (device-side V(phi); parameters are rows of d_params) --------------- */
 /* V = c0 + c1 phi + c2 phi^2 + c3 phi^3 + c4 phi^4 ; analytic dV, d2V.  params[5] = c0..c4        */

@@ -337,6 +337,42 @@ def test_scalar_api_overrides(ctb):
     assert inst.phi_bar == 0.8
 
 
+@pytest.mark.timeout(120)
+def test_garbage_inputs_terminate(ctb):
+    """NaN / inf / degenerate parameters must end in a status code, not in a hang: every loop of the kernels is
+    bounded (bisection by its tolerance, fminbound by 500 evaluations, the integration by rmax / drmin / underflow)."""
+    from cosmotransitions_b200 import _lib, batch, potentials
+    good = potentials.quartic_family_params([0.3])[0]
+    rows = [good, [np.nan] * 5, [0, 0, 0, 0, 0], [0, 0, np.inf, -1, 1], [0, 0, 1e300, -1e300, 1e300], [0, 0, 0.15, -0.433, np.nan],
+            [1e-300, 0, 1e-300, -1e-300, 1e-300], good]
+    pa = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0])
+    pm = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])      # last row: phi_abs == phi_meta
+    for kern in ("thread", "warp"):
+        for alpha in (1, 2, 3, 4):
+            r = _np(batch.find_bounce_batch(_lib.POT_POLY4, np.array(rows, dtype=float), pa, pm, alpha=alpha, kernel=kern))
+            assert r["status"][0] in (0, 1) and np.isfinite(r["S"][0])
+            assert (r["status"][1:] >= 2).all(), (kern, alpha, r["status"])
+    w = _np(batch.find_wall_batch(_lib.POT_POLY4, np.array(rows, dtype=float), pa, pm))
+    assert w["status"][0] in (0, 1) and np.isfinite(w["F"][0])   # (statuses of garbage rows are unspecified: it must return)
+    # thermal functor: T = 0, negative / NaN couplings, phi_abs on the wrong side
+    from cosmotransitions_b200 import finiteT, scan
+    good_t = [0.12, 246. ** 2, 0.35, 30., 246. ** 2, 95.0]
+    trow = np.array([good_t, [0.12, 246. ** 2, 0.35, 30., 246. ** 2, 0.0], [np.nan] * 6, [-0.12, 246. ** 2, -0.35, 30., 246. ** 2, 95.0],
+                     [0.12, 0.0, 0.35, 30., 0.0, 95.0], [0.12, 246. ** 2, 0.35, 30., 246. ** 2, 1e300]])
+    for kern in ("thread", "warp"):
+        r = _np(batch.find_bounce_batch(_lib.POT_MODEL1F, trow, 230.0, 0.0, kernel=kern))
+        assert r["status"].shape == (6,)
+    x, v = scan.minimize_1d(_lib.POT_MODEL1F, trow, np.full(6, np.nan), np.full(6, 500.0))
+    assert x.shape == (6,)
+    # thermal integrals and the quadrature kernel on hostile arguments
+    bad = np.array([np.nan, np.inf, -np.inf, -1e300, 1e300, -1e6, 0.0, -0.0])
+    assert finiteT.Jb_exact2(bad).shape == bad.shape and finiteT.dJf_exact(bad).shape == bad.shape
+    assert finiteT.Jb(bad, approx="high").shape == bad.shape and finiteT.Jf_spline(bad).shape == bad.shape
+    R = np.array([[0.0, np.nan, 1.0, 2.0], [0.0, 0.0, 0.0, 0.0], [3.0, 2.0, 1.0, 0.0]])
+    S = batch.find_action_batch(_lib.POT_POLY4, np.array(rows[:3], dtype=float), 0.0, R, R, R, alpha=2)
+    assert S.shape == (3,)
+
+
 def test_bounce_pipeline_streams(ctb):
     """BouncePipeline (two slots / streams, host batches in, pinned host results out) returns exactly what
     find_bounce_batch returns, batch after batch, including when slots are reused."""
