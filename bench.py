@@ -36,8 +36,8 @@ BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
 # bounce_kernel<.., MODE_SHOOT>: 0.64 of the 0.94 ms of kernel time per C2 step), from the `ncu --set full`
 # captures committed as profiles/r1b_c2_newton_metrics.csv (8.06 MB read: 5.6 MB parameters/minima + 2.4 MB
 # phi_bar/rscale/order; results and the 2.4 MB hand-over to the save kernel stay in L2) and
-# profiles/r1b_c3_newton_metrics.csv (80.1 MB read + 48.0 MB written)
-NCU_TRAFFIC_BYTES = {"c2": 8.063488e6, "c3": 128.039168e6}
+# profiles/r1b_c3_newton_metrics.csv (80.3 MB read + 47.4 MB written)
+NCU_TRAFFIC_BYTES = {"c2": 8.064000e6, "c3": 127.660544e6}
 
 
 def sweep_c(n, rank=0, world=1):
