@@ -1218,9 +1218,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 double dy0, dy1, drnext;
                 int e = s.rkqs(ya, yb, da, db, r_, dr, epsfrac, inv_ea0, inv_ea1, dy0, dy1, drnext);
                 if (e) { fail(e); break; }
-#ifndef CTB_NO_STEP_GUARD
                 if (s.n_rkck >= CTB_MAX_STEPS) { fail(CTB_ST_MAXSTEPS); break; } // guard, see ctbounce.h
-#endif
                 double r1, na, nb, inv_r1;
                 if (saving && dr < drmin) { // T1D:594-597
                     na = ya + dy0 * drmin / dr; nb = yb + dy1 * drmin / dr;

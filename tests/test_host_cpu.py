@@ -226,3 +226,20 @@ def test_monotonic_indices_matches_the_sequential_definition():
         n = int(rng.integers(2, 40))
         x = np.cumsum(rng.normal(0.2 * rng.choice([-1, 1]), 1, n)) if t % 2 else rng.integers(0, 6, n).astype(float)
         assert np.array_equal(monotonicIndices(x), sequential(x))
+
+
+def test_finite_difference_stencils_are_exact_on_polynomials():
+    """generic_potential._stencil1 (the gradientFunction / hessianFunction weights, helper_functions.py:446-528):
+    order 4 differentiates quartics exactly, order 2 quadratics; the radiation constant of V1T (generic_potential.py:289-295)."""
+    from cosmotransitions_b200 import generic_potential as gpm
+    p = np.poly1d([0.7, -1.3, 0.4, 2.0, -5.0])
+    x0, eps = 0.83, 1e-2
+    for order, poly in ((4, p), (2, np.poly1d([0.4, 2.0, -5.0]))):
+        d1 = sum(w * poly(x0 + h) for h, w in gpm._stencil1(eps, order, 1))
+        d2 = sum(w * poly(x0 + h) for h, w in gpm._stencil1(eps, order, 2))
+        assert abs(d1 - poly.deriv(1)(x0)) < 1e-10 and abs(d2 - poly.deriv(2)(x0)) < 1e-8
+    m = gpm.one_field_model.__new__(gpm.one_field_model)
+    m.bosons, m.fermions, m.num_boson_dof, m.num_fermion_dof = [(0, 1, 0, 3., 1.5), (0, 1, 0, 1., 1.5)], [(0, 1, 12.)], 10., None
+    assert m._rad(False) == 0.0 and abs(m._rad(True) - 6. * np.pi ** 4 / 45.) < 1e-12
+    m.num_fermion_dof = 90.
+    assert abs(m._rad(True) - (6. * np.pi ** 4 / 45. + 78. * 7 * np.pi ** 4 / 360.)) < 1e-10
