@@ -667,7 +667,8 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
                                                                                                      : 6.0 * 52.34277778455352;
         const double g = (ALPHA == 1) ? 1.0 : (ALPHA == 2) ? 0.88622692545275801 : (ALPHA == 3) ? 1.0 : 1.3293403881791370;
         double h2 = (0.5 * z) * (0.5 * z);
-        double t1 = s / G1, t2 = h2 / G2, t3 = h2 * h2 * s / G3;
+        // (reciprocals of the constants are folded at compile time: no IEEE division sequence on this path)
+        double t1 = s * (1.0 / G1), t2 = h2 * (1.0 / G2), t3 = h2 * h2 * s * (1.0 / G3);
         double p = t1 + t2 + t3;
         double dp = t1 * 2 + t2 * 4 + t3 * 6;
         phi = p * (0.25 * g * (r * r) * dv * s) + phi0;
@@ -821,7 +822,7 @@ struct Sfi {
             double xn = nan("");
             if (ad < 1.7976931348623157e308 && e.y != 0 && fabs(e.y) < 1.7976931348623157e308) {
                 if (ad == ac) return x;
-                xn = x - log(ad * inv_ac) * d / e.y; // Newton on log(|phi - phi_abs| / ac): d/dr = phi' / (phi - phi_abs)
+                xn = x - log(ad * inv_ac) * d * rcp_fast(e.y); // Newton on log(|phi - phi_abs| / ac): d/dr = phi' / (phi - phi_abs)
             }
             if (fabs(xn - x) <= 4e-15 * x) return xn; // converged (NaN compares false); may sit a rounding outside [lo, hi]
             if (ad >= ac) hi = x; else lo = x; // (also taken for an overflowed value at x: the root lies below)
@@ -985,7 +986,7 @@ CTB_DEV double cubic_crossing(const Cubic &f, double off, int &err)
         if (isnan(ft)) { err = 2; return nan(""); }
         if (signbit(ft) == signbit(f0)) lo = t; else hi = t;
         const double dft = fma(t, fma(t, CTB_MUL(3.0, f.A3), CTB_MUL(2.0, f.A2)), f.A1);
-        double tn = t - ft / dft;
+        double tn = t - ft * rcp_fast(dft); // (a zero / non-finite slope gives NaN or a point outside the bracket: bisection)
         if (fabs(tn - t) <= 1e-15) return fmin(fmax(tn, 0.0), 1.0); // converged (NaN compares false)
         if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
         t = tn;
