@@ -803,6 +803,13 @@ struct Sfi {
         return dv;
     }
 
+    // The reference's own root find (T1D:428-434), one out-of-line copy for its two (rare) callers
+    __device__ __noinline__ double start_radius_brentq(const ExactCoef ec, double pa, double ac, double lo, double hi,
+                                                      int &err) const
+    {
+        return brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; }, lo, hi, err);
+    }
+
     // Root of |phi(r) - phi_abs| = ac on [lo, hi] for the monotone (V'' > 0) exact solution.  err as brentq's.
     CTB_DEV double start_radius_newton(const ExactCoef &ec, double pa, double ac, double lo, double hi, int &err) const
     {
@@ -814,7 +821,7 @@ struct Sfi {
         if (flo == 0) return lo;
         if (fhi == 0) return hi;
         if (signbit(flo) == signbit(fhi)) { err = 1; return 0.; }
-        if (flo > 0) return brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; }, lo, hi, err);
+        if (flo > 0) return start_radius_brentq(ec, pa, ac, lo, hi, err);
         const double inv_ac = 1.0 / ac;
         double x = hi;
         for (int it = 0; it < 80; it++) {
@@ -911,7 +918,7 @@ struct Sfi {
             // in 3-5 evaluations where brentq needs ~16.  The end-point tests are brentq's own (same statuses).
             rr = start_radius_newton(ec, pa, ac, rlast, r, err);
         } else {
-            rr = brentq([&](double r_) { return fabs(exact_solution<ALPHA>(r_, ec).x - pa) - ac; }, rlast, r, err);
+            rr = start_radius_brentq(ec, pa, ac, rlast, r, err);
         }
         if (err == 2) return CTB_ST_NONFINITE;
         if (err == 1) return CTB_ST_BRENT_SIGN;
