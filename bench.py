@@ -33,11 +33,11 @@ WORKLOADS = {
 }
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (the shoot kernel,
-# bounce_kernel<.., MODE_SHOOT>: 0.64 of the 0.94 ms of kernel time per C2 step), from the `ncu --set full`
+# bounce_kernel<.., MODE_SHOOT>: 0.63 of the 0.90 ms of kernel time per C2 step), from the `ncu --set full`
 # captures committed as profiles/r1b_c2_newton_metrics.csv (8.06 MB read: 5.6 MB parameters/minima + 2.4 MB
 # phi_bar/rscale/order; results and the 2.4 MB hand-over to the save kernel stay in L2) and
-# profiles/r1b_c3_newton_metrics.csv (80.3 MB read + 47.4 MB written)
-NCU_TRAFFIC_BYTES = {"c2": 8.064000e6, "c3": 127.660544e6}
+# profiles/r1b_c3_newton_metrics.csv (80.1 MB read + 51.4 MB written)
+NCU_TRAFFIC_BYTES = {"c2": 8.056576e6, "c3": 131.504128e6}
 
 
 def sweep_c(n, rank=0, world=1):
@@ -339,7 +339,7 @@ def main():
                                     "(MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
                      "scope": "whole step: setup + sort + shoot + save kernels (the flop count per bounce covers "
-                              "shooting, dense output and quadrature); the shoot kernel alone is 0.64 of the step's "
+                              "shooting, dense output and quadrature); the shoot kernel alone is 0.63 of the step's "
                               "kernel time (profiles/r1b_c2_launches.csv)",
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "bytes_per_bounce": BYTES_PER_BOUNCE}},
