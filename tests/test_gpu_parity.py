@@ -373,6 +373,33 @@ def test_garbage_inputs_terminate(ctb):
     assert S.shape == (3,)
 
 
+def test_npoints_limits(ctb, oracle):
+    """The npoints knob at its ends: 2 (smallest), 2048 (the oracle's largest) against the oracle, 4096 (the library's
+    largest; the warp kernel's staging does not fit, AUTO takes the thread kernel) against the 2048-point answer, and
+    the rejected values."""
+    from cosmotransitions_b200 import _lib, batch, potentials
+    c = np.array([0.1, 0.3, 0.45, 0.49])
+    p = potentials.quartic_family_params(c)
+    for npts in (2, 3, 2048):
+        g = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, npoints=npts, return_profiles=True))
+        o = oracle.bounce_batch(oracle.make_config(npoints=npts), p, 1.0, 0.0)
+        assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["n_points"], o["n_points"])
+        np.testing.assert_allclose(g["S"], o["S"], rtol=1e-9)
+        assert g["R"].shape[1] == npts + npts // 2
+    big = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, npoints=4096, return_profiles=True))
+    ref = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, npoints=2048))
+    assert (big["status"] <= 1).all() and (big["n_points"] >= 4097).all() and (big["n_points"] <= 6144).all()
+    np.testing.assert_allclose(big["S"], ref["S"], rtol=1e-7)      # Simpson on 2048 vs 4096 points of a smooth profile
+    for i in range(4):
+        n = int(big["n_points"][i])
+        assert np.all(np.diff(big["R"][i, :n]) > 0) and np.isnan(big["R"][i, n:]).all()
+    for bad in (1, 0, 4097):
+        with pytest.raises(_lib.CtbError):
+            batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, npoints=bad)
+    with pytest.raises(_lib.CtbError):
+        batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, npoints=4096, kernel="warp")
+
+
 def test_bounce_pipeline_streams(ctb):
     """BouncePipeline (two slots / streams, host batches in, pinned host results out) returns exactly what
     find_bounce_batch returns, batch after batch, including when slots are reused."""
