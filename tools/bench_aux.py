@@ -71,4 +71,15 @@ pm = torch.from_numpy(potentials.quartic_family_params(c)).to(dev)
 lo, hi = torch.full((n,), 0.6, dtype=torch.float64, device=dev), torch.full((n,), 1.5, dtype=torch.float64, device=dev)
 ms = timeit(lambda: scan.minimize_1d(_lib.POT_POLY4, pm, lo, hi))
 out["minimize_1d_quartic"] = {"n": n, "ms": ms, "minima_per_s": n / ms * 1e3}
+# --- generic_potential.one_field_model.Vtot on a 4096 x 1024 (phi, T) grid (5 bosons incl. a thermal mass, 1 fermion)
+from cosmotransitions_b200 import generic_potential as gpm  # noqa: E402
+v2 = 246. ** 2
+mdl = gpm.one_field_model([0.0, 0.0, -.5 * 0.13 * v2, 0.0, .25 * 0.13], v2,
+                          bosons=[(-0.13 * v2, 0.39, 0.0, 1., 1.5), (-0.13 * v2, 0.13, 0.0, 3., 1.5), (0.0, 0.105, 0.0, 6., 5. / 6),
+                                  (0.0, 0.1375, 0.0, 3., 5. / 6), (0.0, 0.9, 0.15, 12., 1.5)], fermions=[(0.0, 0.49, 12.)])
+Xg = torch.linspace(-20.0, 320.0, 4096, dtype=torch.float64, device=dev)[:, None, None]
+Tg = torch.linspace(1.0, 250.0, 1024, dtype=torch.float64, device=dev)[None, :]
+ms = timeit(lambda: mdl.Vtot(Xg, Tg))
+out["vtot_one_field_grid"] = {"points": 4096 * 1024, "ms": ms, "pts_per_s": 4096 * 1024 / ms * 1e3,
+                              "note": "includes the broadcast / concat of the (phi, T) pairs in torch (24 B per point in and out)"}
 print(json.dumps(out))
