@@ -127,12 +127,13 @@ def model1f_bounce_scan(lam, Y, n, nT=256, v2=246. ** 2, window=None, phi_box=(5
 
 
 def model1f_tnuc(lam, Y, n, v2=246. ** 2, target=140.0, nT_coarse=24, rounds=10, T_tol=1e-7, phi_box=(50.0, 500.0),
-                 window=None, **knobs):
+                 window=None, beta_step=0.0, **knobs):
     """Nucleation temperature per parameter point: the root of S3(T)/T - 140 (the reference's default
     nuclCriterion, transitionFinder.py:773, found there by a sequential brentq over T, :836-837).
     Batched form: a coarse sweep brackets the crossing, then every round solves ONE bounce per point at
     an Illinois (regula-falsi) abscissa, all points in one launch.  Returns device tensors
-    dict(Tnuc, S, T0, Tc, bracket_lo, bracket_hi, rounds)."""
+    dict(Tnuc, S, T0, Tc, bracket_lo, bracket_hi, rounds) and, with beta_step > 0 (e.g. 2e-3),
+    beta_over_H = T d(S3/T)/dT at T_nuc by a central difference over T_nuc (1 +- beta_step)."""
     torch = _lib.require_cuda()
     lam, Y, n = (torch.as_tensor(x, dtype=torch.float64).cuda().reshape(-1) for x in (lam, Y, n))
     P = lam.numel()
@@ -170,7 +171,23 @@ def model1f_tnuc(lam, Y, n, v2=246. ** 2, target=140.0, nT_coarse=24, rounds=10,
         a, fa = torch.where(left, Tm, a), torch.where(left, fm, fa)
         b, fb = torch.where(left, b, Tm), torch.where(left, fb, fm)
     Tn = torch.where(has, torch.where(fa.abs() < fb.abs(), a, b), torch.full_like(a, float("nan")))
-    return dict(Tnuc=Tn, S=S_last, T0=sweep["T0"], Tc=sweep["Tc"], bracket_lo=a, bracket_hi=b, rounds=done_rounds)
+    out = dict(Tnuc=Tn, S=S_last, T0=sweep["T0"], Tc=sweep["Tc"], bracket_lo=a, bracket_hi=b, rounds=done_rounds)
+    if beta_step:
+        # beta / H = T d(S3/T)/dT at T_nuc -- the quantity generic_potential.py:608-609 lists as "NOT IMPLEMENTED YET":
+        # central difference over T_nuc (1 +- beta_step), two more bounces per point in one launch
+        Tq = torch.where(has, Tn, 0.5 * (sweep["T0"] + sweep["Tc"]))
+        Tpm = torch.cat([Tq * (1.0 - beta_step), Tq * (1.0 + beta_step)])
+        rep = lambda v: torch.cat([v, v])
+        params = model1f_params(rep(lam), rep(Y), rep(n), Tpm, v2)
+        phi_abs, _ = minimize_1d(_lib.POT_MODEL1F, params, rep(lo), rep(hi))
+        # S(T) at the default tolerances carries ~1e-4 of bisection noise, which a derivative amplifies: these two
+        # bounces are solved two orders of magnitude tighter
+        tight = dict(knobs)
+        tight["xtol"], tight["phitol"] = min(knobs.get("xtol", 1e-4), 1e-6), min(knobs.get("phitol", 1e-4), 1e-6)
+        r = batch.find_bounce_batch(_lib.POT_MODEL1F, params, phi_abs, torch.zeros_like(phi_abs), **tight)
+        soT = torch.where(r["status"] <= 1, r["S"] / Tpm, torch.full_like(Tpm, float("nan")))
+        out["beta_over_H"] = torch.where(has, (soT[P:] - soT[:P]) / (2.0 * beta_step), torch.full_like(Tn, float("nan")))
+    return out
 
 
 # ---- model1 along a fixed straight line (BASELINE.json configs[3]) -------------------

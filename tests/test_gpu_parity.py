@@ -757,6 +757,25 @@ def test_find_action_random_profiles_vs_oracle(ctb, oracle):
     assert finiteT.Jb_exact(np.zeros(0)).size == 0
 
 
+def test_beta_over_H_from_tnuc(ctb):
+    """beta / H = T d(S3/T)/dT at T_nuc (not implemented in the reference, generic_potential.py:608-609): the central
+    difference of model1f_tnuc against the slope of an independent dense scan fitted around T_nuc."""
+    from cosmotransitions_b200 import scan
+    lam, Y, n = np.array([0.12, 0.13]), np.array([0.35, 0.33]), np.array([30.0, 31.0])
+    r = scan.model1f_tnuc(lam, Y, n, beta_step=2e-3)
+    Tn, bH = r["Tnuc"].cpu().numpy(), r["beta_over_H"].cpu().numpy()
+    assert np.isfinite(Tn).all() and (bH > 0).all()
+    dense = scan.model1f_bounce_scan(lam, Y, n, nT=1024, xtol=1e-6, phitol=1e-6)
+    T, soT = dense["T"].cpu().numpy(), dense["S_over_T"].cpu().numpy()
+    for i in range(2):
+        sel = (np.abs(T[i] / Tn[i] - 1.0) < 8e-3) & np.isfinite(soT[i])
+        assert sel.sum() > 10
+        slope = np.polyfit(T[i][sel], soT[i][sel], 3)
+        ref = Tn[i] * np.polyval(np.polyder(slope), Tn[i])
+        print("beta/H", bH[i], "dense-scan fit", ref)
+        assert abs(bH[i] - ref) < 0.01 * ref, (bH[i], ref)
+
+
 @pytest.mark.parametrize("alpha", [1, 2, 3, 4])
 def test_random_affine_quartics_vs_oracle(ctb, oracle, alpha):
     """20 000 quartics with random minima positions (either order), scales over four decades and random wall
