@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the batched bounce solver (BASELINE.json metric: bounce actions / second).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--mode auto|global|replicas]
+                  [--impl ours|reference]
 
-A "step" is one pass of the hot path (SingleFieldInstanton.__init__ + findProfile + findAction for
-every instance) over one batch.  Workload c2 = BASELINE.json configs[1]: 1e5 quartic instances
-V = phi^4/4 - (1+c)/3 phi^3 + c/2 phi^2, c_i = 0.02 + 0.475 (i + 1/2)/N, alpha = 2, all findProfile
-defaults.  c3 = configs[2]: 1e6 instances, alpha = 3.
+A "step" is one pass of the hot path (SingleFieldInstanton.__init__ + findProfile + findAction for every
+instance) over one batch.  Workloads (BASELINE.json configs):
+  c2  configs[1]: 1e5 quartic instances V = phi^4/4 - (1+c)/3 phi^3 + c/2 phi^2, c_i = 0.02 + 0.475 (i + 1/2)/N,
+      alpha = 2, all findProfile defaults.  The default at N = 1 (the configuration the metric is quoted on).
+  c3  configs[2]: the same family, 1e6 instances, alpha = 3.  The default at N > 1.
+  c5  configs[4] (one GPU's worth): 1000 parameter points x 256 temperatures of the one-field thermal model --
+      phi_absMin(T) by the batched bounded minimiser, then one finite-T bounce (finite-difference dV, d2V) each.
+  c4  configs[3]: model1 Vtot on the 4096 x 1024 (phi, T) grid (metric: grid points/s) + the 512-temperature bounce
+      scan along the line between the phases.
 
-Under torchrun (N > 1) every rank owns one GPU and one full batch (weak scaling; the path has no
-exchange step, so torch.distributed is used only for the barrier and the max-over-ranks of the time).
+N > 1 (torchrun, one rank per GPU), --mode global (default): ONE global batch, partitioned block-cyclically over
+the ranks (cosmotransitions_b200.multigpu), every rank's results landing by DMA in a shared page-locked host
+segment that rank 0 reads: strong scaling, no collective on the data path (torch.distributed: segment name,
+barriers, max-over-ranks of the times).  --mode replicas: every rank owns one full batch (weak scaling).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -27,21 +35,25 @@ sys.path.insert(0, REPO)
 
 WORKLOADS = {
     "c2": dict(n=100000, alpha=2, name="C2: 1e5 quartic thin->thick sweep, alpha=2, findProfile defaults",
-               flop_per_bounce=7.3e4),
+               flop_per_bounce=7.3e4, ref_stride=16),
     "c3": dict(n=1000000, alpha=3, name="C3: 1e6 quartic thin->thick sweep, alpha=3, findProfile defaults",
-               flop_per_bounce=9.0e4),
+               flop_per_bounce=9.0e4, ref_stride=160),
+    "c5": dict(n=256000, alpha=2, name="C5 (one GPU's share): 1000 parameter points x 256 temperatures of the one-field "
+                                       "thermal model, bounded minimiser + finite-T bounce per (point, T)",
+               flop_per_bounce=1.8e6),
+    "c4": dict(n=4096 * 1024, alpha=2, name="C4: model1 Vtot on a 4096 x 1024 (phi, T) grid + 512-temperature bounce "
+                                            "scan along the line between the phases"),
 }
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (the shoot kernel,
-# bounce_kernel<.., MODE_SHOOT>: 0.63 of the 0.90 ms of kernel time per C2 step), from the `ncu --set full`
-# captures committed as profiles/r1b_c2_newton_metrics.csv (8.06 MB read: 5.6 MB parameters/minima + 2.4 MB
-# phi_bar/rscale/order; results and the 2.4 MB hand-over to the save kernel stay in L2) and
-# profiles/r1b_c3_newton_metrics.csv (80.1 MB read + 51.4 MB written)
-NCU_TRAFFIC_BYTES = {"c2": 8.056576e6, "c3": 131.504128e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per STEP (every kernel of the step: setup + sort + shoot + save), from the
+# `ncu --set full` captures under profiles/ (see profiles/README.md); None until captured for a workload
+NCU_TRAFFIC_BYTES = {"c2": 25.7e6, "c3": None}
+NCU_TRAFFIC_NOTE = ("whole step (setup + sort + shoot + save kernels), ncu dram__bytes_read+write summed over the "
+                    "step's launches; algorithmic: 64 B x instances")
 
 
 def sweep_c(n, rank=0, world=1):
-    # every rank gets its own sweep over the same range (offset by a fraction of a grid step)
+    # replicas mode: every rank gets its own sweep over the same range (offset by a fraction of a grid step)
     return 0.02 + 0.475 * (np.arange(n) + (rank + 0.5) / world) / n
 
 
@@ -51,6 +63,15 @@ def quartic_params(c):
     p[:, 3] = -(1 + c) / 3
     p[:, 4] = 0.25
     return p
+
+
+def make_config(args, wl, world, mode):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm of the same command."""
+    cfg = {"workload": wl["name"], "instances": wl["n"], "alpha": wl["alpha"], "order": args.order}
+    if world > 1:
+        cfg["partition"] = ("one global batch, block-cyclic over %d ranks" % world) if mode == "global" else \
+                           ("%d independent replicas of the batch" % world)
+    return cfg
 
 
 class ClockSampler:
@@ -89,6 +110,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.t.join(timeout=2)
+
         def summarise(rows):
             sm, mx, reasons = [], [], set()
             for _, r in rows:
@@ -103,7 +125,6 @@ class ClockSampler:
             return sm, mx, reasons
         # prefer samples taken inside the timed region; a region shorter than a few sampling periods
         # falls back to every sample taken while the same kernel loop kept the GPU busy
-        # (warm-up + timed region + end-to-end loop)
         window = "timed region"
         t0, t1 = self.windows.get("timed", (0, 0))
         sm, mx, reasons = summarise([x for x in self.rows if t0 <= x[0] <= t1])
@@ -115,9 +136,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def cpu_oracle_rate(wl, threads, sample_stride, c=None):
-    """Times the CPU oracle (C port of the reference algorithm, oracle/ctb_oracle.c) on a strided
-    sample of the workload with `threads` host threads.  Returns (bounces/s, results dict, idx)."""
+# ------------------------------------------------------------------------------------------------------------
+# CPU side: the reference itself (oracle/_ref, pure Python, multiprocessing.Pool) and the C port of it
+
+def cpu_port_rate(wl, threads, sample_stride, c=None):
+    """The C restatement (oracle/ctb_oracle.c, pthreads) on a strided sample.  (bounces/s, results, idx)"""
     from oracle import oracle as O
     O.build()
     if c is None:
@@ -132,79 +155,253 @@ def cpu_oracle_rate(wl, threads, sample_stride, c=None):
     return idx.size / dt, res, idx
 
 
-def run_reference(args, wl):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference
-    itself is pure Python and is not on the GPU box) on all host threads, same config/metric."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def reference_subprocess(wl, stride, procs):
+    """The unmodified Python reference under multiprocessing.Pool(procs), chunksize 25, in a
+    subprocess (this process has CUDA initialised; the pool forks).  Returns the runner's dict or None."""
+    runner = os.path.join(REPO, "oracle", "ref_runner.py")
+    if not os.path.exists(os.path.join(REPO, "oracle", "_ref", "cosmoTransitions", "tunneling1D.py")):
+        return None
+    out = os.path.join(REPO, "gpurun_out", "ref_runner_%d.json" % os.getpid())
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [sys.executable, runner, "--n", str(wl["n"]), "--alpha", str(wl["alpha"]), "--stride", str(stride),
+           "--procs", str(procs), "--out", out]
+    try:
+        subprocess.run(cmd, check=True, timeout=900, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        with open(out) as f:
+            return json.load(f)
+    except Exception:
+        return None
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
+
+
+def run_reference(args, wl, world, mode):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, same config / metric.
+    oracle/_ref present (the unmodified Python reference, installed by oracle/make_ref.py): multiprocessing.Pool over
+    a strided sample per step, analytic V / dV / d2V lambdas, chunksize 25 (kind "reference").  Otherwise the C port
+    (kind "port").  Under torchrun rank 0 alone runs it."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import oracle as O
-    O.build()
+    if args.workload not in ("c2", "c3"):
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm covers the quartic workloads c2 / c3"}))
+        return
+    from oracle import ref_runner
     threads = len(os.sched_getaffinity(0))
-    c = sweep_c(wl["n"])
-    # bounded sample per step: ~2 s of wall time at ~9e3 bounces/s/thread
-    n_step = int(min(wl["n"], max(2000, 9000 * threads * 2)))
-    stride = max(1, wl["n"] // n_step)
-    idx = np.arange(0, wl["n"], stride)
-    cfg = O.make_config(alpha=wl["alpha"])
-    p = quartic_params(c[idx])
-    for _ in range(args.warmup):
-        O.bounce_batch(cfg, p, 1.0, 0.0, nthreads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = O.bounce_batch(cfg, p, 1.0, 0.0, nthreads=threads)
-    dt = time.perf_counter() - t0
-    value = idx.size * args.steps / dt
-    sample = "every %d-th instance of the %d-instance sweep (%d per step)" % (stride, wl["n"], idx.size)
+    n, alpha = wl["n"], wl["alpha"]
+    total_steps = args.steps + args.warmup
+    line_extra = {}
+    if ref_runner.available() and not args.port:
+        # ~27 bounces/s per core (SURVEY.md s.6.2); whole run <= ~150 s
+        per_step_s = args.ref_seconds if args.ref_seconds > 0 else min(6.0, 150.0 / total_steps)
+        n_step = int(min(n // 16, max(4 * threads, 27.0 * threads * per_step_s)))
+        stride = max(1, n // n_step)
+        pool = ref_runner.make_pool(alpha, threads)
+        try:
+            S = None
+            for k in range(args.warmup):
+                idx = np.arange(k % stride, n, stride)
+                ref_runner.quartic_pool(0.02 + 0.475 * (idx + 0.5) / n, alpha, threads, 25, pool=pool)
+            t0 = time.perf_counter()
+            count, solved = 0, 0
+            for k in range(args.steps):
+                idx = np.arange((args.warmup + k) % stride, n, stride)
+                S, status, _ = ref_runner.quartic_pool(0.02 + 0.475 * (idx + 0.5) / n, alpha, threads, 25, pool=pool)
+                count += idx.size
+                solved += sum(s == "ok" for s in status)
+            dt = time.perf_counter() - t0
+        finally:
+            pool.close()
+            pool.join()
+        kind = "reference"
+        sample = ("every %d-th instance of the %d-instance sweep (%d per step, rotating offset), unmodified "
+                  "cosmoTransitions.tunneling1D under multiprocessing.Pool(%d), chunksize 25" % (stride, n, count // args.steps, threads))
+        value, solved_fraction = count / dt, solved / count
+        import scipy
+        line_extra["versions"] = {"numpy": np.__version__, "scipy": scipy.__version__, "python": sys.version.split()[0]}
+    else:
+        from oracle import oracle as O
+        O.build()
+        c = sweep_c(n)
+        n_step = int(min(n, max(2000, 9000 * threads * 2)))     # ~2 s per step at ~9e3 bounces/s/thread
+        stride = max(1, n // n_step)
+        idx = np.arange(0, n, stride)
+        cfg = O.make_config(alpha=alpha)
+        p = quartic_params(c[idx])
+        for _ in range(args.warmup):
+            O.bounce_batch(cfg, p, 1.0, 0.0, nthreads=threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = O.bounce_batch(cfg, p, 1.0, 0.0, nthreads=threads)
+        dt = time.perf_counter() - t0
+        kind = "port"
+        value, solved_fraction = idx.size * args.steps / dt, float((res["status"] <= 1).mean())
+        sample = "every %d-th instance of the %d-instance sweep (%d per step), C port with pthreads" % (stride, n, idx.size)
     line = {
         "impl": "reference", "metric": "bounce actions/sec", "value": value, "unit": "bounces/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "instances_per_step": int(idx.size)},
-        "cpu_baseline": {"value": value, "unit": "bounces/s", "cores": threads, "kind": "port", "sample": sample},
+        "scaling": "strong" if (world > 1 and mode == "global") else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": make_config(args, wl, world, mode),
+        "cpu_baseline": {"value": value, "unit": "bounces/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "bounces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "solved_fraction": float((res["status"] <= 1).mean()),
+        "solved_fraction": solved_fraction,
     }
+    line.update(line_extra)
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--block", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "sorted", "natural"],
-                    help="instance scheduling inside the library (see batch.launch_bounce)")
-    ap.add_argument("--order", default="natural", choices=["natural", "reversed", "shuffled"],
-                    help="instance order inside the batch (SURVEY.md s.8d: shuffled exposes divergence sensitivity)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        run_reference(args, wl)
-        return
+# ------------------------------------------------------------------------------------------------------------
 
+def fp64_peak_tflops(_lib, torch, dev):
+    """FP64 roofline denominator, measured here: register-resident DFMA loop (MEASURED_PEAKS.json has no FP64 entry)."""
+    import ctypes as C
+    lib = _lib.load()
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    ms = C.c_float(0)
+    iters = 1 << 16
+    blocks = max(1, lib.ctb_sm_count()) * 8
+    best = 0.0
+    for _ in range(3):
+        _lib.check(lib.ctb_fp64_peak(iters, blocks, 256, sink.data_ptr(), C.byref(ms), None), "fp64_peak")
+        best = max(best, blocks * 256 * iters * 16 * 2 / (ms.value * 1e-3) / 1e12)
+    return best
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
+
+
+class Env:
+    pass
+
+
+def setup_env(args):
     import torch
     import torch.distributed as dist
-    from cosmotransitions_b200 import _lib, batch
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from cosmotransitions_b200 import _lib
+    e = Env()
+    e.torch, e.dist, e._lib = torch, dist, _lib
+    e.rank = int(os.environ.get("RANK", "0"))
+    e.world = int(os.environ.get("WORLD_SIZE", "1"))
+    e.local = int(os.environ.get("LOCAL_RANK", "0"))
     _lib.require_cuda()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    torch.cuda.set_device(e.local)
+    e.dev = torch.device("cuda", e.local)
+    if e.world > 1:
+        dist.init_process_group("nccl", device_id=e.dev)
     assert _lib.load().ctb_device_ok() == 0, "not an sm_100 device"
+    e.flush = torch.empty(256 << 20, dtype=torch.uint8, device=e.dev)  # > 126 MB L2
 
+    def barrier():
+        if e.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=e.dev)
+        if e.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e.barrier, e.max_over_ranks = barrier, max_over_ranks
+    return e
+
+
+def timed_device_loop(e, args, step, sampler, t_load0, settle_s=0.6):
+    """W warm-up steps, then exactly K steps, each bracketed by CUDA events on the launching (current) stream, an L2
+    flush before each; barrier + synchronize on both sides.  Returns (per-step ms list, wall seconds)."""
+    torch = e.torch
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    while time.perf_counter() - t_load0 < settle_s:      # clocks settled, sampler reporting
+        step()
+        torch.cuda.synchronize()
+    e.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e.barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e.flush.zero_()                 # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    e.barrier()
+    wall = time.perf_counter() - t0
+    sampler.mark("timed", t0, t0 + wall)
+    return [a.elapsed_time(b) for a, b in ev], wall
+
+
+def quartic_roofline(e, args, wl, kern_avg_ms, n_in_step, scope):
+    fp64_peak = fp64_peak_tflops(e._lib, e.torch, e.dev)
+    achieved_tf = wl["flop_per_bounce"] * n_in_step / (kern_avg_ms * 1e-3) / 1e12
+    peaks, peak_src = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_achieved = BYTES_PER_BOUNCE * n_in_step / (kern_avg_ms * 1e-3) / 1e9
+    return {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp64_peak if fp64_peak else None,
+            "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "traffic_note": NCU_TRAFFIC_NOTE,
+            "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run "
+                           "(MEASURED_PEAKS.json has no FP64 entry)",
+            "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms, "scope": scope,
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "bytes_per_bounce": BYTES_PER_BOUNCE, "peak_source": peak_src}}
+
+
+def cpu_baseline_and_parity(args, wl, c, out_np, want_reference=True):
+    """Rank 0, after the timed regions: the reference (Python, Pool) on the strided sample of BASELINE.md s.4 and the C
+    port on a larger one; S of the GPU run is checked against both on exactly those instances."""
+    n = wl["n"]
+    threads = len(os.sched_getaffinity(0))
+    status, S_gpu = out_np["status"], out_np["S"]
+    res = {}
+    pstride = max(1, n // 100000)
+    rate, pres, idx = cpu_port_rate(wl, threads, pstride, c)
+    ok = (pres["status"] <= 1) & (status[idx] <= 1)
+    rel = np.abs(S_gpu[idx][ok] - pres["S"][ok]) / np.abs(pres["S"][ok])
+    port = {"value": rate, "unit": "bounces/s", "cores": threads, "kind": "port",
+            "sample": "every %d-th instance of the workload (%d instances), one pass, C port (oracle/ctb_oracle.c) with "
+                      "pthreads" % (pstride, idx.size)}
+    parity = {"max_rel_err_S_vs_oracle": float(rel.max()) if rel.size else None,
+              "status_equal": bool(np.array_equal(pres["status"], status[idx])), "checked": int(idx.size),
+              "n_rkck_mismatches": int((out_np["n_rkck"][idx] != pres["n_rkck"]).sum()),
+              "n_shots_mismatches": int((out_np["n_shots"][idx] != pres["n_shots"]).sum())}
+    ref = reference_subprocess(wl, wl["ref_stride"], threads) if (want_reference and args.order == "natural") else None
+    if ref is not None:
+        ridx = np.arange(ref["offset"], n, ref["stride"])
+        Sr = np.array(ref["S"])
+        okr = np.array([s == "ok" for s in ref["status"]]) & (status[ridx] <= 1)
+        relr = np.abs(S_gpu[ridx][okr] - Sr[okr]) / np.abs(Sr[okr])
+        res["cpu_baseline"] = {
+            "value": ref["rate"], "unit": "bounces/s", "cores": ref["procs"], "kind": "reference",
+            "sample": "every %d-th instance of the workload (%d instances, %.1f s wall), the unmodified "
+                      "cosmoTransitions.tunneling1D.SingleFieldInstanton (oracle/_ref) under multiprocessing.Pool(%d), "
+                      "chunksize %d, analytic V / dV / d2V lambdas" % (ref["stride"], ref["count"], ref["wall_s"],
+                                                                       ref["procs"], ref["chunksize"]),
+            "versions": {"numpy": ref["numpy"], "scipy": ref["scipy"], "python": ref["python"]},
+            "port": port}
+        parity["live_reference"] = {"max_rel_err_S": float(relr.max()) if relr.size else None, "checked": int(okr.sum()),
+                                    "reference_failures": int(len(ref["status"]) - sum(s == "ok" for s in ref["status"])),
+                                    "gpu_failures_on_sample": int((status[ridx] > 1).sum())}
+    else:
+        res["cpu_baseline"] = port
+    res["parity"] = parity
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workloads c2 / c3 on one GPU, or as N replicas (weak)
+
+def run_quartic_single(args, wl, e, mode):
+    torch, _lib = e.torch, e._lib
+    from cosmotransitions_b200 import batch
     n = wl["n"]
     sorted_sched = args.schedule == "sorted" or (args.schedule == "auto" and n >= batch.SORT_THRESHOLD)
-    c = sweep_c(n, rank, world)
+    c = sweep_c(n, e.rank, e.world)
     if args.order == "reversed":
         c = c[::-1].copy()
     elif args.order == "shuffled":
@@ -212,56 +409,25 @@ def main():
     params_h = torch.from_numpy(quartic_params(c)).pin_memory()
     abs_h = torch.ones(n, dtype=torch.float64).pin_memory()
     meta_h = torch.zeros(n, dtype=torch.float64).pin_memory()
-    d_params, d_abs, d_meta = params_h.to(dev), abs_h.to(dev), meta_h.to(dev)
+    d_params, d_abs, d_meta = params_h.to(e.dev), abs_h.to(e.dev), meta_h.to(e.dev)
     opts = batch.make_opts(alpha=wl["alpha"], block_threads=args.block)
-    out = batch.alloc_out(torch, n, dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    out = batch.alloc_out(torch, n, e.dev)
 
     def step():
         batch.launch_bounce(_lib.POT_POLY4, d_params, d_abs, d_meta, opts, out, schedule=args.schedule)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(e.local)
     sampler.start()
     t_load0 = time.perf_counter()
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    # keep the same step running (untimed) until the clocks have settled and the sampler is reporting
-    while time.perf_counter() - t_load0 < 0.6:
-        step()
-        torch.cuda.synchronize()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                 # L2 flush between timed iterations (outside the event pair)
-        ev[k][0].record()
-        step()
-        ev[k][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    sampler.mark("timed", t_wall0, t_wall0 + t_wall)
-    kern_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(kern_ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = world * n * args.steps / (total_ms * 1e-3)
-    status = out["status"].cpu().numpy()
-    S_gpu = out["S"].cpu().numpy()
+    kern_ms, t_wall = timed_device_loop(e, args, step, sampler, t_load0)
+    total_ms = e.max_over_ranks(sum(kern_ms))
+    value = e.world * n * args.steps / (total_ms * 1e-3)
+    out_np = {k: v.cpu().numpy() for k, v in out.items()}
 
     # ---- end to end through the public API: host buffers in, host results out, every step ----
-
     # BouncePipeline: two slots, each with its own stream -- the H2D copy of step k+1 and the D2H copy of step k-1
     # overlap the kernels of step k; every step's copies happen inside the timed region
-    pipe = batch.BouncePipeline(_lib.POT_POLY4, n, depth=2, device=dev, outputs=("S", "status"), alpha=wl["alpha"],
+    pipe = batch.BouncePipeline(_lib.POT_POLY4, n, depth=2, device=e.dev, outputs=("S", "status"), alpha=wl["alpha"],
                                 block_threads=args.block, schedule=args.schedule)
 
     def e2e_run(steps):
@@ -277,72 +443,36 @@ def main():
         return checksum
 
     e2e_run(3)
-    barrier()
+    e.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
     e2e_run(args.steps)
     e1.record()
-    barrier()
+    e.barrier()
     e2e_wall = time.perf_counter() - t0
     sampler.mark("load", t_load0, time.perf_counter())
     clocks = sampler.stop()
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / (float(t.item()) * 1e-3)
+    e2e_ms = e.max_over_ranks(max(e0.elapsed_time(e1), e2e_wall * 1e3))
+    e2e_value = e.world * n * args.steps / (e2e_ms * 1e-3)
     h2d = params_h.numel() * 8 + abs_h.numel() * 8 + meta_h.numel() * 8
     d2h = n * 8 + n * 4
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- FP64 roofline denominator, measured here: register-resident FMA loop ----
-    sink = torch.zeros(8, dtype=torch.float64, device=dev)
-    import ctypes as C
-    ms = C.c_float(0)
-    iters = 1 << 16
-    best = 0.0
-    for _ in range(3):
-        _lib.check(_lib.load().ctb_fp64_peak(iters, 148 * 8, 256, sink.data_ptr(), C.byref(ms), None), "fp64_peak")
-        best = max(best, 148 * 8 * 256 * iters * 16 * 2 / (ms.value * 1e-3) / 1e12)
-    fp64_peak = best
+    if e.rank != 0:
+        return None
     kern_avg_ms = float(np.mean(kern_ms))
-    achieved_tf = wl["flop_per_bounce"] * n / (kern_avg_ms * 1e-3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_achieved = BYTES_PER_BOUNCE * n / (kern_avg_ms * 1e-3) / 1e9
-
     line = {
-        "metric": "bounce actions/sec", "value": value, "unit": "bounces/s", "n_gpus": world, "steps": args.steps,
+        "metric": "bounce actions/sec", "value": value, "unit": "bounces/s", "n_gpus": e.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "instances_per_gpu": n, "alpha": wl["alpha"], "order": args.order,
-                   "schedule": "work-sorted (setup kernel + device argsort + shoot kernel + save kernel, all inside "
-                               "the timed step)" if sorted_sched else "natural",
-                   "timing": "CUDA events around each step's kernel on torch's current stream; 256 MiB L2 flush "
-                             "between timed iterations", "wall_s_timed_region": t_wall},
-        "solved_fraction": float((status <= 1).mean()),
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                     "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
-                     "traffic_note": "bytes per launch of the shoot kernel, ncu dram__bytes_read+write "
-                                     "(profiles/r1b_c2_newton_metrics.csv, r1b_c3_newton_metrics.csv); algorithmic: 64 B x instances",
-                     "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run "
-                                    "(MEASURED_PEAKS.json has no FP64 entry)",
-                     "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
-                     "scope": "whole step: setup + sort + shoot + save kernels (the flop count per bounce covers "
-                              "shooting, dense output and quadrature); the shoot kernel alone is 0.63 of the step's "
-                              "kernel time (profiles/r1b_c2_launches.csv)",
-                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": hbm_achieved / hbm_peak, "bytes_per_bounce": BYTES_PER_BOUNCE}},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(args, wl, e.world, mode),
+        "schedule": "work-sorted (setup kernel + device argsort + shoot kernel + save kernel, all inside the timed "
+                    "step)" if sorted_sched else "natural",
+        "timing": "CUDA events around each step's kernels on torch's current stream (the launching stream); 256 MiB L2 "
+                  "flush between timed iterations; max over ranks",
+        "wall_s_timed_region": t_wall,
+        "solved_fraction": float((out_np["status"] <= 1).mean()),
+        "roofline": quartic_roofline(e, args, wl, kern_avg_ms, n,
+                                     "whole step: setup + sort + shoot + save kernels (the flop count per bounce covers "
+                                     "shooting, dense output and quadrature)"),
         "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "batch.BouncePipeline (public API), pinned host buffers in / pinned host results out every step, two "
                        "slots on two CUDA streams so the copies of neighbouring steps overlap the kernels; wall clock "
@@ -352,25 +482,355 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
-        threads = len(os.sched_getaffinity(0))
-        stride = max(1, n // 100000)
-        rate, res, idx = cpu_oracle_rate(wl, threads, stride, c)
-        ok = (res["status"] <= 1) & (status[idx] <= 1)
-        rel = np.abs(S_gpu[idx][ok] - res["S"][ok]) / np.abs(res["S"][ok])
-        line["cpu_baseline"] = {"value": rate, "unit": "bounces/s", "cores": threads, "kind": "port",
-                                "reference_python_note": "the reference itself is pure Python and does not travel to "
-                                                         "the GPU box; measured in the build container (SURVEY.md "
-                                                         "s.6.2): 28.2 bounces/s on 1 core, 221 bounces/s with "
-                                                         "multiprocessing.Pool(8), same quartic family, alpha=2",
-                                "sample": "every %d-th instance of the workload (%d instances), one pass, C oracle "
-                                          "with pthreads" % (stride, idx.size)}
-        line["parity"] = {"max_rel_err_S_vs_oracle": float(rel.max()) if rel.size else None,
-                          "status_equal": bool(np.array_equal(res["status"], status[idx])), "checked": int(idx.size),
-                          "n_rkck_mismatches": int((out["n_rkck"].cpu().numpy()[idx] != res["n_rkck"]).sum()),
-                          "n_shots_mismatches": int((out["n_shots"].cpu().numpy()[idx] != res["n_shots"]).sum())}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        line.update(cpu_baseline_and_parity(args, wl, c, out_np))
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workloads c2 / c3 as ONE global batch partitioned over the ranks (strong scaling)
+
+def run_quartic_global(args, wl, e, mode):
+    torch, _lib = e.torch, e._lib
+    from cosmotransitions_b200 import batch, multigpu
+    n = wl["n"]
+    c = sweep_c(n)
+    if args.order == "reversed":
+        c = c[::-1].copy()
+    elif args.order == "shuffled":
+        c = c[np.random.default_rng(1234).permutation(n)]
+    # every rank holds the same global input arrays in page-locked host memory (in production: one shared input)
+    params_h = torch.from_numpy(quartic_params(c)).pin_memory()
+    abs_h = torch.ones(n, dtype=torch.float64).pin_memory()
+    meta_h = torch.zeros(n, dtype=torch.float64).pin_memory()
+    outs = ("S", "status")
+    db = multigpu.DistributedBounce(_lib.POT_POLY4, n, block=args.partition_block, depth=2, outputs=outs, device=e.dev,
+                                    alpha=wl["alpha"], block_threads=args.block, schedule=args.schedule)
+    lay = db.layout
+    n_local = lay.n_local
+    sorted_sched = args.schedule == "sorted" or (args.schedule == "auto" and n_local >= batch.SORT_THRESHOLD)
+
+    # ---- `value`: this rank's shard resident in HBM, kernels only, CUDA events; max over ranks ----
+    t0 = db.submit(params_h, abs_h, meta_h)
+    first = db.collect(t0)
+    S_first = first["S"].copy() if e.rank == 0 else None
+    st_first = first["status"].copy() if e.rank == 0 else None
+    slot = db._sharded._slots[0]          # the shard's device-resident inputs (filled by the submit above)
+    opts = db._sharded.opts
+    out = batch.alloc_out(torch, n_local, e.dev)
+
+    def step():
+        batch.launch_bounce(_lib.POT_POLY4, slot["params"], slot["phi_abs"], slot["phi_meta"], opts, out,
+                            schedule=args.schedule)
+
+    sampler = ClockSampler(e.local)
+    sampler.start()
+    t_load0 = time.perf_counter()
+    kern_ms, t_wall = timed_device_loop(e, args, step, sampler, t_load0)
+    total_ms = e.max_over_ranks(sum(kern_ms))
+    value = n * args.steps / (total_ms * 1e-3)
+
+    # ---- `e2e`: the public multi-GPU API, global host arrays in, gathered global host result on rank 0, every step ----
+    def e2e_run(steps):
+        checksum = 0.0
+        tickets = []
+        for k in range(steps):
+            if len(tickets) >= db.depth:
+                res = db.collect(tickets.pop(0))
+                if res is not None:
+                    checksum += float(res["S"][0]) + float(res["S"][-1]) + int(res["status"][n // 2])
+            tickets.append(db.submit(params_h, abs_h, meta_h))
+        for t_ in tickets:
+            res = db.collect(t_)
+            if res is not None:
+                checksum += float(res["S"][0]) + float(res["S"][-1]) + int(res["status"][n // 2])
+        return checksum
+
+    e2e_run(3)
+    e.barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps)
+    torch.cuda.synchronize()
+    e2e_wall_local = time.perf_counter() - t0
+    e.barrier()
+    sampler.mark("load", t_load0, time.perf_counter())
+    clocks = sampler.stop()
+    e2e_ms = e.max_over_ranks(e2e_wall_local * 1e3)
+    e2e_value = n * args.steps / (e2e_ms * 1e-3)
+    h2d = n_local * (5 * 8 + 8 + 8)  # the shard's rows of params, phi_absMin, phi_metaMin
+    d2h = n_local * 12
+
+    # ---- the same global batch on ONE GPU (rank 0), same run: the denominator of the strong-scaling efficiency ----
+    single = None
+    if e.rank == 0 and not args.no_single:
+        d_params, d_abs, d_meta = params_h.to(e.dev), abs_h.to(e.dev), meta_h.to(e.dev)
+        out1 = batch.alloc_out(torch, n, e.dev)
+        opts1 = batch.make_opts(alpha=wl["alpha"], block_threads=args.block)
+        ks = max(3, min(args.steps, 10))
+        for _ in range(2):
+            batch.launch_bounce(_lib.POT_POLY4, d_params, d_abs, d_meta, opts1, out1, schedule=args.schedule)
+        torch.cuda.synchronize()
+        ms1 = []
+        for _ in range(ks):
+            e.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            batch.launch_bounce(_lib.POT_POLY4, d_params, d_abs, d_meta, opts1, out1, schedule=args.schedule)
+            b.record()
+            torch.cuda.synchronize()
+            ms1.append(a.elapsed_time(b))
+        sb = multigpu.ShardedBounce(_lib.POT_POLY4, n, 1, 0, device=e.dev, depth=2, outputs=outs, alpha=wl["alpha"],
+                                    block_threads=args.block, schedule=args.schedule)
+        res1 = {"S": torch.empty(n, dtype=torch.float64).pin_memory(), "status": torch.empty(n, dtype=torch.int32).pin_memory()}
+        for _ in range(2):
+            sb.submit(params_h, 1.0, 0.0, res1)
+        sb.wait()
+        tw = time.perf_counter()
+        tk = []
+        for k in range(ks):
+            if len(tk) >= 2:
+                sb.wait(tk.pop(0))
+            tk.append(sb.submit(params_h, 1.0, 0.0, res1))
+        for t_ in tk:
+            sb.wait(t_)
+        e2e1 = n * ks / (time.perf_counter() - tw)
+        v1 = n / (float(np.mean(ms1)) * 1e-3)
+        single = {"value": v1, "e2e": e2e1, "unit": "bounces/s", "steps": ks,
+                  "strong_scaling_efficiency": {"value": value / (e.world * v1), "e2e": e2e_value / (e.world * e2e1)},
+                  "bit_identical_to_partitioned": bool(np.array_equal(out1["S"].cpu().numpy(), S_first, equal_nan=True)
+                                                       and np.array_equal(out1["status"].cpu().numpy(), st_first)),
+                  "note": "the same 1-GPU code path as --gpus 1 --workload %s, run by rank 0 after the timed regions" % args.workload}
+        out_np = {k: v.cpu().numpy() for k, v in out1.items()}
+    e.barrier()
+    db.close()
+    if e.rank != 0:
+        return None
+    kern_avg_ms = total_ms / args.steps
+    line = {
+        "metric": "bounce actions/sec", "value": value, "unit": "bounces/s", "n_gpus": e.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(args, wl, e.world, mode),
+        "partition": {"block": lay.block, "instances_per_rank": n_local, "how": "block-cyclic (multigpu.ShardLayout); "
+                      "results gathered by each GPU's DMA engine into one shared page-locked host segment, no collective"},
+        "schedule": "work-sorted (setup kernel + device argsort + shoot kernel + save kernel, all inside the timed "
+                    "step)" if sorted_sched else "natural",
+        "timing": "value: CUDA events around each step's kernels on the launching stream, shard resident in HBM, L2 flush "
+                  "between iterations, MAX over ranks of the summed times; e2e: wall clock between barriers, max over ranks",
+        "wall_s_timed_region": t_wall,
+        "solved_fraction": float((st_first <= 1).mean()),
+        "roofline": quartic_roofline(e, args, wl, kern_avg_ms, n_local,
+                                     "one rank's shard per step (setup + sort + shoot + save kernels), slowest rank"),
+        "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d * e.world, "d2h_bytes_per_step": d2h * e.world,
+                "how": "multigpu.DistributedBounce (public API): every rank DMAs its block-cyclic shard out of the pinned "
+                       "GLOBAL input array, solves it, and DMAs S / status into the shared pinned GLOBAL result segment; "
+                       "rank 0 reads every step's gathered result; two result slots rotate so consecutive steps overlap; "
+                       "wall clock over all steps, max over ranks"},
+        "gpu_launches": args.steps * (3 if sorted_sched else 1) * e.world,
+        "clocks": clocks,
+    }
+    if single is not None:
+        line["single_gpu_same_workload"] = single
+        if not args.no_cpu_baseline:
+            line.update(cpu_baseline_and_parity(args, wl, c, out_np, want_reference=False))
+    return line
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload c5: finite-T bounces of the one-field thermal model (minimiser + bounce per (point, T))
+
+def run_c5(args, wl, e, mode):
+    torch, _lib = e.torch, e._lib
+    from cosmotransitions_b200 import batch, scan
+    P, nT = 1000, 256
+    rng = np.random.default_rng(20260101)
+    lam, Y, nb = 0.12 * rng.uniform(.8, 1.2, 10000), 0.35 * rng.uniform(.8, 1.2, 10000), 30. * rng.uniform(.8, 1.2, 10000)
+    sel = np.arange(e.rank, 10000, max(1, 10000 // P))[:P] if e.world == 1 else np.arange(e.rank, 10000, e.world)[:P]
+    lam, Y, nb = (torch.as_tensor(x[sel], dtype=torch.float64, device=e.dev) for x in (lam, Y, nb))
+    T0, Tc = scan.model1f_temperature_window(lam, Y, nb)       # input preparation (not in the timed step)
+    frac = (torch.arange(nT, dtype=torch.float64, device=e.dev) + 0.5) / nT
+    T = T0[:, None] + frac[None, :] * (Tc - T0)[:, None]
+    params = scan.model1f_params(lam[:, None], Y[:, None], nb[:, None], T).reshape(-1, 6).contiguous()
+    n = params.shape[0]
+    lo = torch.full((n,), 50.0, dtype=torch.float64, device=e.dev)
+    hi = torch.full((n,), 500.0, dtype=torch.float64, device=e.dev)
+    zero = torch.zeros(n, dtype=torch.float64, device=e.dev)
+    opts = batch.make_opts(alpha=2, block_threads=args.block)
+    out = batch.alloc_out(torch, n, e.dev)
+
+    def step():
+        phi_abs, _ = scan.minimize_1d(_lib.POT_MODEL1F, params, lo, hi)
+        batch.launch_bounce(_lib.POT_MODEL1F, params, phi_abs, zero, opts, out, schedule=args.schedule)
+
+    sampler = ClockSampler(e.local)
+    sampler.start()
+    t_load0 = time.perf_counter()
+    kern_ms, t_wall = timed_device_loop(e, args, step, sampler, t_load0)
+    total_ms = e.max_over_ranks(sum(kern_ms))
+    value = e.world * n * args.steps / (total_ms * 1e-3)
+    status = out["status"].cpu().numpy()
+    # e2e: pinned host parameter rows in, S / status out, through the public functions
+    params_h = params.cpu().pin_memory()
+    S_h, st_h = torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        p = params_h.to(e.dev, non_blocking=True)
+        phi_abs, _ = scan.minimize_1d(_lib.POT_MODEL1F, p, lo, hi)
+        r = batch.find_bounce_batch(_lib.POT_MODEL1F, p, phi_abs, zero)
+        S_h.copy_(r["S"], non_blocking=True)
+        st_h.copy_(r["status"], non_blocking=True)
+        torch.cuda.synchronize()
+        return float(S_h[0]) + int(st_h[-1])
+
+    e2e_step()
+    e.barrier()
+    t0 = time.perf_counter()
+    ks = max(1, min(args.steps, 5))
+    for _ in range(ks):
+        e2e_step()
+    e.barrier()
+    e2e_ms = e.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sampler.mark("load", t_load0, time.perf_counter())
+    clocks = sampler.stop()
+    if e.rank != 0:
+        return None
+    kern_avg_ms = float(np.mean(kern_ms))
+    fp64_peak = fp64_peak_tflops(_lib, torch, e.dev)
+    achieved = wl["flop_per_bounce"] * n / (kern_avg_ms * 1e-3) / 1e12
+    return {
+        "metric": "bounce actions/sec", "value": value, "unit": "bounces/s", "n_gpus": e.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(args, wl, e.world, mode),
+        "timing": "CUDA events around each step (bounded minimiser + setup + sort + shoot + save kernels) on the launching "
+                  "stream; 256 MiB L2 flush between iterations",
+        "wall_s_timed_region": t_wall, "solved_fraction": float((status <= 1).mean()),
+        "status_hist": np.bincount(status, minlength=12).tolist(),
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                     "traffic": None, "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
+                     "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run",
+                     "scope": "whole step; SURVEY.md s.8d: ~6e3 Vtot evaluations x 300 flop per finite-T bounce"},
+        "e2e": {"value": e.world * n * ks / (e2e_ms * 1e-3), "unit": "bounces/s", "h2d_bytes_per_step": n * 48,
+                "d2h_bytes_per_step": n * 12, "steps": ks,
+                "how": "pinned host parameter rows -> scan.minimize_1d -> batch.find_bounce_batch -> pinned host S / status"},
+        "gpu_launches": args.steps * 4, "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload c4: model1 Vtot on the 4096 x 1024 grid (+ the line bounce scan as a second figure)
+
+def run_c4(args, wl, e, mode):
+    torch, _lib = e.torch, e._lib
+    from cosmotransitions_b200 import generic_potential as gp, scan
+    m = gp.model1()
+    x_low = np.array([286.39824989, 382.19727238])
+    x_high = np.array([231.10296383, -136.82260069])
+    L = np.linalg.norm(x_high - x_low)
+    nhat = (x_high - x_low) / L
+    s = torch.linspace(-0.2 * L, 1.2 * L, 4096, dtype=torch.float64, device=e.dev)
+    T = torch.linspace(1, 250, 1024, dtype=torch.float64, device=e.dev)
+    buf = torch.empty((4096, 1024), dtype=torch.float64, device=e.dev)
+
+    def step():
+        m.Vtot_grid(x_low, nhat, s, T, out=buf)
+
+    sampler = ClockSampler(e.local)
+    sampler.start()
+    t_load0 = time.perf_counter()
+    kern_ms, t_wall = timed_device_loop(e, args, step, sampler, t_load0)
+    total_ms = e.max_over_ranks(sum(kern_ms))
+    npts = 4096 * 1024
+    value = e.world * npts * args.steps / (total_ms * 1e-3)
+    # e2e: host axes in, host grid out
+    s_h, T_h = s.cpu().numpy(), T.cpu().numpy()
+    m.Vtot_grid(x_low, nhat, s_h, T_h)
+    t0 = time.perf_counter()
+    ks = max(1, min(args.steps, 5))
+    for _ in range(ks):
+        g = m.Vtot_grid(x_low, nhat, s_h, T_h)
+    e2e_s = (time.perf_counter() - t0) / ks
+    Ts = np.linspace(77.8, 109.2, 512)
+    scan.model1_line_bounce_scan(m.model8, x_low, x_high, Ts)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = scan.model1_line_bounce_scan(m.model8, x_low, x_high, Ts)
+    torch.cuda.synchronize()
+    t_scan = time.perf_counter() - t0
+    sampler.mark("load", t_load0, time.perf_counter())
+    clocks = sampler.stop()
+    if e.rank != 0:
+        return None
+    peaks, peak_src = load_peaks()
+    kern_avg_ms = float(np.mean(kern_ms))
+    hbm = 8.0 * npts / (kern_avg_ms * 1e-3) / 1e9
+    fp64_peak = fp64_peak_tflops(_lib, torch, e.dev)
+    flop_pt = 120.0
+    return {
+        "metric": "Vtot grid points/sec", "value": value, "unit": "points/s", "n_gpus": e.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(args, wl, e.world, mode),
+        "timing": "CUDA events around each ctb_vtot_model1_grid launch; 256 MiB L2 flush between iterations",
+        "wall_s_timed_region": t_wall,
+        "roofline": {"bound": "hbm", "achieved": hbm, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                     "frac": hbm / peaks.get("hbm_gbs", 6650.0), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_point": 8.0, "kernel_ms": kern_avg_ms,
+                     "fp64": {"achieved": flop_pt * npts / (kern_avg_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "flop_per_point_executed": flop_pt,
+                              "note": "3 table look-ups + cubics, 1/T^2, T^4 per point; the three logs + sqrt of the "
+                                      "field-dependent part are per ROW (hoisted), not per point"}},
+        "e2e": {"value": npts / e2e_s, "unit": "points/s", "h2d_bytes_per_step": (4096 + 1024) * 8, "d2h_bytes_per_step": npts * 8,
+                "how": "generic_potential.model1.Vtot_grid with numpy axes in, numpy grid out"},
+        "line_bounce_scan": {"temperatures": len(Ts), "seconds": t_scan, "bounces_per_s": len(Ts) / t_scan,
+                             "solved": int((r["status"].cpu().numpy() <= 1).sum()), "Tnuc_line": float(r["Tnuc"])},
+        "gpu_launches": args.steps, "clocks": clocks,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="auto", choices=["auto", "global", "replicas"],
+                    help="N > 1: one global batch partitioned over the ranks (default) or one full batch per rank")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--port", action="store_true", help="--impl reference: time the C port even if oracle/_ref exists")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: wall-time budget per step for the Python reference (default: <= 6 s, whole run <= ~150 s)")
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--partition-block", type=int, default=256, help="instances per block of the block-cyclic partition")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="global mode: skip the 1-GPU run of the same batch on rank 0")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "sorted", "natural"],
+                    help="instance scheduling inside the library (see batch.launch_bounce)")
+    ap.add_argument("--order", default="natural", choices=["natural", "reversed", "shuffled"],
+                    help="instance order inside the batch (SURVEY.md s.8d: shuffled exposes divergence sensitivity)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "c2" if world == 1 else "c3"
+    wl = WORKLOADS[args.workload]
+    mode = args.mode
+    if mode == "auto":
+        mode = "global" if (world > 1 and args.workload in ("c2", "c3")) else "replicas"
+    if world == 1:
+        mode = "single"
+    if args.impl == "reference":
+        run_reference(args, wl, world, mode)
+        return
+    e = setup_env(args)
+    if args.workload == "c5":
+        line = run_c5(args, wl, e, mode)
+    elif args.workload == "c4":
+        line = run_c4(args, wl, e, mode)
+    elif mode == "global":
+        line = run_quartic_global(args, wl, e, mode)
+    else:
+        line = run_quartic_single(args, wl, e, mode)
+    if e.rank == 0:
+        print(json.dumps(line), flush=True)
+    if e.world > 1:
+        e.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 10
+ABI_VERSION = 11
 V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 EXACT_X, EXACT_DX, EXACT_THETA = 0, 1, 2
@@ -24,7 +24,8 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
 
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
-           "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_vtot_thermal1f", "ctb_potential", "ctb_fp64_peak"]
+           "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_vtot_thermal1f", "ctb_potential", "ctb_fp64_peak", "ctb_sm_count",
+           "ctb_copy_blocks", "ctb_host_register", "ctb_host_unregister"]
 
 
 class JTable(C.Structure):
@@ -85,6 +86,7 @@ def load():
     lib.ctb_status_string.restype = C.c_char_p
     lib.ctb_status_string.argtypes = [C.c_int]
     lib.ctb_device_ok.restype = C.c_int
+    lib.ctb_sm_count.restype = C.c_int
     lib.ctb_bounce_batch.restype = C.c_int
     lib.ctb_bounce_batch.argtypes = [C.c_int, C.POINTER(BounceIn), C.POINTER(Opts), C.POINTER(JTable),
                                      C.POINTER(JTable), C.POINTER(BounceOut), C.c_void_p]
@@ -123,6 +125,12 @@ def load():
     lib.ctb_find_action.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
                                     C.c_void_p]
+    lib.ctb_copy_blocks.restype = C.c_int
+    lib.ctb_copy_blocks.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    lib.ctb_host_register.restype = C.c_int
+    lib.ctb_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.ctb_host_unregister.restype = C.c_int
+    lib.ctb_host_unregister.argtypes = [C.c_void_p]
     lib.ctb_fp64_peak.restype = C.c_int
     lib.ctb_fp64_peak.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
     if lib.ctb_abi_version() != ABI_VERSION:

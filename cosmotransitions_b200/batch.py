@@ -77,10 +77,13 @@ def _bounce_out(out, profiles=None):
 SORT_THRESHOLD = 4096
 
 
-def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=None, stream=None, schedule="auto",
+def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=None, schedule="auto",
                   phi_bar=None, rscale=None, split="auto"):
     """Lowest-level call: device tensors in, device tensors (pre-allocated dict `out`) filled.
-    Asynchronous on `stream` (default: torch's current stream).
+    Asynchronous on torch's CURRENT stream of the tensors' device: the temporaries (sort keys, permutation,
+    hand-over scratch) are allocated and the sort runs on that stream too, so everything is ordered on one
+    stream.  To use another stream, wrap the call in `with torch.cuda.stream(s):` (a foreign cudaStream_t:
+    torch.cuda.ExternalStream).
 
     schedule: "natural" = thread t solves instance t;  "sorted" = a setup kernel computes phi_bar,
     rscale and a work predictor per instance, the instances are sorted heavy-first (so that lanes of a
@@ -96,7 +99,7 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
     tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
     jb, jf = (tabs.jb, tabs.jf) if tabs else (None, None)
     bo = _bounce_out(out, profiles)
-    st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    st = torch.cuda.current_stream(dev).cuda_stream
     if schedule == "auto":
         schedule = "sorted" if n >= SORT_THRESHOLD else "natural"
     with torch.cuda.device(dev):

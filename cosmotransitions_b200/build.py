@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libctbounce.so")
 SOURCES = ["ctb_api.cu", "ctb_bounce_poly4.cu", "ctb_bounce_spline.cu", "ctb_bounce_model1_line.cu",
            "ctb_bounce_model1f.cu", "ctb_bounce_thermal1f.cu"]
-HEADERS = ["ctb_device.cuh", "ctb_bounce.cuh", os.path.join("..", "..", "include", "ctbounce.h")]
+HEADER = os.path.join(PKG, "..", "include", "ctbounce.h")
 OBJDIR = os.path.join(PKG, "build")
 
 NVCC_FLAGS = [
@@ -32,8 +32,10 @@ def find_nvcc():
 def needs_build():
     if not os.path.exists(LIB):
         return True
+    # every kernel source / header in csrc/ plus the public header: a stale .so must never be loaded silently
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [HEADER]
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
 def _compile_one(args):

@@ -417,7 +417,10 @@ JTab to_jtab(const ctb_jtable *t)
 size_t table_bytes(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES(t->nint) * sizeof(double) : 0; }
 size_t table_bytes_compact(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES_COMPACT(t->nint) * sizeof(double) : 0; }
 
-bool jtab_ok(const ctb_jtable *t) { return t && t->d_brk && t->d_coef && t->nint >= 1 && t->nint <= 5000; }
+// every kernel that stages a table keeps it in at most 48 KB of dynamic shared memory (no opt-in needed):
+// 48-byte records -> nint <= 1000 incl. the 8.5 KB of static staging in find_action_kernel (the shipped tables have 997 intervals)
+#define CTB_JTAB_MAX_NINT 1000
+bool jtab_ok(const ctb_jtable *t) { return t && t->d_brk && t->d_coef && t->nint >= 1 && t->nint <= CTB_JTAB_MAX_NINT; }
 
 template <bool MINIMIZE>
 int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf, const double *a,
@@ -568,10 +571,24 @@ int launch_find_action(const double *params, const ctb_jtable *jb, const ctb_jta
     return (int)cudaGetLastError();
 }
 
+// number of SMs of the current device (148 on B200), queried once per device
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 int grid_for(int64_t n, int block)
 {
     int64_t g = (n + block - 1) / block;
-    const int64_t cap = 148LL * 5; // persistent grid-stride blocks (5 x 40 KB table copies per SM)
+    const int64_t cap = (int64_t)sm_count() * 5; // persistent grid-stride blocks (5 x 40 KB table copies per SM)
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
@@ -610,6 +627,13 @@ CTB_API int ctb_device_ok(void)
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return CTB_ERR_NO_DEVICE;
     return (p.major == 10) ? CTB_OK : CTB_ERR_NO_DEVICE;
+}
+
+CTB_API int ctb_sm_count(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    return sm_count();
 }
 
 static int fill_args(BounceArgs &a, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
@@ -706,7 +730,8 @@ CTB_API int ctb_jspline(const ctb_jtable *tab, int deriv, const double *d_theta,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = table_bytes(tab);
     int64_t gneed = (n + 256 * 4 - 1) / (256 * 4);
-    int g = (int)(gneed < 148 * 4 ? (gneed < 1 ? 1 : gneed) : 148 * 4); // persistent: 4 blocks x 48 KB per SM
+    const int64_t gcap = (int64_t)sm_count() * 4; // persistent: 4 blocks x 48 KB per SM
+    int g = (int)(gneed < gcap ? (gneed < 1 ? 1 : gneed) : gcap);
     switch (deriv) {
     case 0: jspline_kernel<0><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
     case 1: jspline_kernel<1><<<g, 256, sm, st>>>(t, d_theta, d_out, n); break;
@@ -756,6 +781,7 @@ CTB_API int ctb_vtot_model1(const double *model8, const ctb_jtable *jb, const do
     if (!model8 || !jtab_ok(jb) || n < 0 || parts < 1 || parts > CTB_V_TOTAL) return CTB_ERR_BAD_ARG;
     if (n == 0) return CTB_OK;
     if (!d_X || !d_T || !d_out) return CTB_ERR_BAD_ARG;
+    if ((uintptr_t)d_X & 15) return CTB_ERR_BAD_ARG; // X is read as one 16-byte (phi1, phi2) pair per point
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
     vtot_model1_kernel<<<grid_for(n, 256), 256, table_bytes(jb), (cudaStream_t)stream>>>(m, to_jtab(jb), d_X, d_T, d_out, n, parts);
     return (int)cudaGetLastError();
@@ -770,10 +796,12 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
     // persistent grid: 4 blocks per SM unless that would make a block span more than VG_ROWCAP field points
     const int64_t total = ns * nT;
-    int64_t nblk = 148 * 4;
+    int64_t nblk = (int64_t)sm_count() * 4;
     const int64_t min_blocks = (total + (VG_ROWCAP - 2) * nT - 1) / ((VG_ROWCAP - 2) * nT);
-    if (nblk < min_blocks) nblk = min_blocks;
     if (nblk > (total + VG_THREADS - 1) / VG_THREADS) nblk = (total + VG_THREADS - 1) / VG_THREADS;
+    // last word: a block never spans more than VG_ROWCAP field points (chunk <= (VG_ROWCAP - 2) nT points touch at
+    // most VG_ROWCAP - 1 rows), also for nT < 4 where 256 points per block would be 64+ rows
+    if (nblk < min_blocks) nblk = min_blocks;
     const int64_t chunk = (total + nblk - 1) / nblk;
     const size_t vg_smem = table_bytes(jb) + VG_ROWCAP * 6 * sizeof(double);
     cudaFuncSetAttribute(vtot_model1_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vg_smem);
@@ -794,7 +822,7 @@ CTB_API int ctb_vtot_thermal1f(const double *model64, double rad, const ctb_jtab
     const size_t sm = table_bytes_compact(jb) + table_bytes_compact(jf) + 16;
     cudaFuncSetAttribute(vtot_thermal1f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     int64_t g = (n + 255) / 256;
-    if (g > 148 * 2) g = 148 * 2; // persistent: two 80 KB table pairs per SM
+    if (g > (int64_t)sm_count() * 2) g = (int64_t)sm_count() * 2; // persistent: two 80 KB table pairs per SM
     vtot_thermal1f_kernel<<<(unsigned)g, 256, sm, (cudaStream_t)stream>>>(m, rad, to_jtab(jb), to_jtab(jf), d_phi, d_T, d_out,
                                                                          n, parts);
     return (int)cudaGetLastError();
@@ -901,6 +929,26 @@ CTB_API int ctb_find_action(int pot_kind, const double *d_params, const ctb_jtab
         return launch_find_action<PotModel1F>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
     }
     return CTB_ERR_UNSUPPORTED;
+}
+
+CTB_API int ctb_copy_blocks(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                            void *stream)
+{
+    if (width == 0 || height == 0) return CTB_OK;
+    if (!dst || !src || dpitch < width || spitch < width) return CTB_ERR_BAD_ARG;
+    return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, (cudaStream_t)stream);
+}
+
+CTB_API int ctb_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return CTB_ERR_BAD_ARG;
+    return (int)cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+}
+
+CTB_API int ctb_host_unregister(void *p)
+{
+    if (!p) return CTB_ERR_BAD_ARG;
+    return (int)cudaHostUnregister(p);
 }
 
 CTB_API int ctb_fp64_peak(int64_t iters, int blocks, int threads, double *d_sink, float *ms_out, void *stream)

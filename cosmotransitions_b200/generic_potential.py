@@ -165,6 +165,8 @@ class model1(_FiniteDifferences):
         if shifts is not None:
             Xf = torch.cat([Xf + torch.as_tensor(dx, dtype=torch.float64, device=dev) for dx, _, _ in shifts]).contiguous()
             Tf = torch.cat([Tf + dT for _, dT, _ in shifts]).contiguous()
+        if Xf.data_ptr() % 16:      # the kernel reads one 16-byte (phi1, phi2) pair per point
+            Xf = Xf.clone()
         out = torch.empty(Tf.shape, dtype=torch.float64, device=dev)
         tabs = _tables.device_tables(dev)
         with torch.cuda.device(dev):
@@ -190,6 +192,9 @@ class model1(_FiniteDifferences):
             dev, torch.float64).contiguous()
         if out is None:
             out = torch.empty((sd.numel(), Td.numel()), dtype=torch.float64, device=dev)
+        elif not (isinstance(out, torch.Tensor) and out.device == dev and out.dtype == torch.float64
+                  and out.is_contiguous() and tuple(out.shape) == (sd.numel(), Td.numel())):
+            raise ValueError("out must be a contiguous float64 tensor of shape (len(s), len(T)) on %s" % (dev,))
         line = (C.c_double * 4)(float(x0[0]), float(x0[1]), float(nhat[0]), float(nhat[1]))
         tabs = _tables.device_tables(dev)
         with torch.cuda.device(dev):

@@ -21,13 +21,14 @@
 #ifndef CTBOUNCE_H
 #define CTBOUNCE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 10
+#define CTB_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -185,6 +186,10 @@ CTB_API const char *ctb_status_string(int status);
 /* Device check: returns CTB_OK if the current device can run the sm_100a kernels. */
 CTB_API int ctb_device_ok(void);
 
+/* Number of SMs of the current device (148 on B200): the persistent kernels size their grids from it;
+ * exported so that callers (bench, tools) can size theirs the same way.  <= 0: no device. */
+CTB_API int ctb_sm_count(void);
+
 /* SingleFieldInstanton(phi_absMin, phi_metaMin, V, dV, d2V, phi_eps, alpha).findProfile(**knobs)
  * followed by .findAction(profile), for n independent instances (tunneling1D.py:128-791).
  * jb/jf may be NULL for POLY4. */
@@ -293,6 +298,18 @@ CTB_API int ctb_potential_batch(int pot_kind, const double *d_params, const ctb_
 CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
                             const double *d_lo, const double *d_hi, double xtol_rel, int64_t n, double *d_xmin,
                             double *d_vmin, void *stream);
+
+/* ---- host-side gather plumbing of the multi-GPU partition (no collective on the data path) ----
+ * Block-cyclic partition: with blocks of B instances, device r of G owns global blocks r, r + G, r + 2G, ...
+ * ctb_copy_blocks moves `height` rows of `width` bytes between two pitched layouts on `stream` (one DMA descriptor:
+ * cudaMemcpy2DAsync, direction inferred from the pointers), which is exactly the scatter of a shard out of / the
+ * gather of a shard into the GLOBAL host array: host pitch = G * B * elem, device pitch = B * elem, width = B * elem.
+ * The host side should be page-locked (ctb_host_register pins an existing allocation, e.g. a shared-memory
+ * segment that the other ranks of the box map too; every process that issues copies registers it itself).  */
+CTB_API int ctb_copy_blocks(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                            void *stream);
+CTB_API int ctb_host_register(void *p, size_t bytes);
+CTB_API int ctb_host_unregister(void *p);
 
 /* Register-resident FP64 FMA loop used to measure the FP64 roofline denominator.
  * Runs iters * 16 dependent-chain-free FMAs per thread; returns elapsed ms via *ms_out (synchronous). */

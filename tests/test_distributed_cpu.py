@@ -1,6 +1,7 @@
-"""World-size-2 gloo test of the N > 1 host path (sharding by `partition`, per-rank solve, gather to
-rank 0).  No GPU here, so each rank's solve is the CPU oracle standing in for find_bounce_batch; the
-GPU box runs the same driver with the real kernel (bench.py under torchrun)."""
+"""World-size-2 gloo test of the N > 1 host path: block-cyclic partition (`ShardLayout`), per-rank solve, gather
+into the shared-memory result segment that rank 0 reads (`DistributedBounce`).  No GPU here, so each rank's solve
+is the CPU oracle standing in for the kernels; the GPU box runs the same driver with the real kernels and DMA
+copies (bench.py under torchrun, tests/test_gpu_parity.py::test_multigpu_driver)."""
 import os
 import socket
 import sys
@@ -38,11 +39,22 @@ def _worker(rank, world, port, q):
     c = 0.02 + 0.475 * (np.arange(n) + 0.5) / n
     p = potentials.quartic_family_params(c)
     p[7] = [0, 0, -0.1, -0.8 / 3, 0.25]          # no barrier
-    res = multigpu.find_bounce_batch_distributed(_lib.POT_POLY4, p, 1.0, 0.0, solve=_oracle_solve, alpha=2)
+    outs = ("S", "phi0", "rf", "status", "n_shots")
+    res = multigpu.find_bounce_batch_distributed(_lib.POT_POLY4, p, 1.0, 0.0, solve=_oracle_solve, alpha=2,
+                                                 block=8, outputs=outs)
+    # the reusable form: two batches in flight in rotating shared segments, results read by rank 0 only
+    db = multigpu.DistributedBounce(_lib.POT_POLY4, n, block=1, depth=2, outputs=("S", "status"), solve=_oracle_solve,
+                                    alpha=2)
+    t0 = db.submit(p, 1.0, 0.0)
+    t1 = db.submit(p[::-1].copy(), 1.0, 0.0)
+    r0, r1 = db.collect(t0), db.collect(t1)
     if rank == 0:
-        q.put({k: v.numpy() for k, v in res.items()})
+        got = {k: v.numpy() for k, v in res.items()}
+        got["S_pipe0"], got["S_pipe1_reversed"] = r0["S"].copy(), r1["S"].copy()
+        q.put(got)
     else:
-        assert res is None
+        assert res is None and r0 is None and r1 is None
+    db.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -72,3 +84,6 @@ def test_two_rank_partition_and_gather():
     for k in ("S", "phi0", "rf"):
         assert np.array_equal(got[k], ref[k], equal_nan=True), k
     assert np.array_equal(got["status"], ref["status"]) and got["status"][7] == 3
+    assert np.array_equal(got["S_pipe0"], ref["S"], equal_nan=True)
+    assert np.array_equal(got["S_pipe1_reversed"], ref["S"][::-1], equal_nan=True)
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("ctb_")]      # segments unlinked

@@ -1,0 +1,106 @@
+"""The CUDA path beside the UNMODIFIED reference, live (oracle/_ref: installed by oracle/make_ref.py in the build
+container, travels to the GPU box with the snapshot; the product never imports it).
+
+* the GPU class plugged into the reference's own multi-field driver, pathDeformation.fullTunneling(...,
+  tunneling_class=...) (pathDeformation.py:845-1001), on examples/fullTunneling.py (BASELINE.json configs[0]);
+* S of the batched GPU solve against the reference's SingleFieldInstanton on samples of C2 and C3;
+* Jb / Jf spline and model1.Vtot against the reference's finiteT / generic_potential on fresh random inputs.
+Needs a B200: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref is not in this snapshot (python oracle/make_ref.py in the build container)")
+    return ref_runner.import_reference()
+
+
+@pytest.mark.parametrize("fy,S_expected", [(2.0, 1766.937676), (80.0, 4.503666131)])
+def test_full_tunneling_with_gpu_tunneling_class(ref, fy, S_expected):
+    """examples/fullTunneling.py:67-69,81-83 with tunneling_class = the GPU SingleFieldInstanton: every 1-D solve of
+    the path deformation (SplinePath potentials) runs on the device; the final action must be the reference's."""
+    from cosmoTransitions.examples import fullTunneling as ft
+    from cosmotransitions_b200.tunneling1D import SingleFieldInstanton as GpuSFI
+    pd = ref["pd"]
+    m = ft.Potential(c=5., fx=0., fy=fy)
+    calls = []
+
+    class Counting(GpuSFI):
+        def findProfile(self, **kw):
+            calls.append(1)
+            return GpuSFI.findProfile(self, **kw)
+
+    Y = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV, tunneling_class=Counting)
+    Yref = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV)
+    assert len(calls) >= 2
+    assert abs(Yref.action - S_expected) < 5e-7 * S_expected
+    assert abs(Y.action - Yref.action) < 1e-6 * abs(Yref.action), (Y.action, Yref.action)
+    assert len(Y.profile1D.R) == len(Yref.profile1D.R)
+    np.testing.assert_allclose(Y.profile1D.Phi, Yref.profile1D.Phi, rtol=0, atol=1e-6 * abs(Yref.profile1D.Phi).max())
+    np.testing.assert_allclose(Y.Phi, Yref.Phi, rtol=0, atol=1e-6)      # the multi-field profile, [npoints, 2]
+
+
+@pytest.mark.parametrize("alpha,n", [(2, 100000), (3, 1000000)])
+def test_batched_solve_vs_live_reference(ref, alpha, n):
+    """~300 instances of C2 / C3 spread over the thin -> thick range: S rel. 1e-6 (BASELINE.json), live."""
+    from oracle import ref_runner
+    from cosmotransitions_b200 import _lib, batch, potentials
+    idx = np.arange(11, n, n // 300)
+    c = 0.02 + 0.475 * (idx + 0.5) / n
+    S_ref, status, _ = ref_runner.quartic_pool(c, alpha, chunksize=5)
+    assert set(status) == {"ok"}
+    g = batch.find_bounce_batch(_lib.POT_POLY4, potentials.quartic_family_params(c), 1.0, 0.0, alpha=alpha)
+    assert (g["status"].numpy() <= 1).all()
+    rel = np.abs(g["S"].numpy() - S_ref) / np.abs(S_ref)
+    print("alpha=%d: max rel err in S vs the live reference: %.2e" % (alpha, rel.max()))
+    assert rel.max() < 1e-6
+    # and through the thread-per-instance kernels the big batches use
+    g2 = batch.find_bounce_batch(_lib.POT_POLY4, potentials.quartic_family_params(c), 1.0, 0.0, alpha=alpha,
+                                 kernel="thread", schedule="sorted", split=True)
+    assert np.max(np.abs(g2["S"].numpy() - S_ref) / np.abs(S_ref)) < 1e-6
+
+
+def test_docstring_example_of_the_reference(ref):
+    """tunneling1D.py:112-122: the thin- and thick-walled quartics, scalar API on both sides."""
+    from cosmotransitions_b200 import potentials, tunneling1D as g1
+    t1 = ref["t1"]
+    for c in (0.47, 0.2):       # V = phi^4/4 - (1+c)/3 phi^3 + c/2 phi^2: .49 / .235 and .4 / .1
+        a, b = (1 + c) / 3, c / 2
+        inst = t1.SingleFieldInstanton(1.0, 0.0, lambda p: .25 * p ** 4 - a * p ** 3 + b * p ** 2,
+                                       lambda p: p * (p - c) * (p - 1.0))
+        prof = inst.findProfile()
+        S_ref = inst.findAction(prof)
+        ginst = g1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(c))
+        gprof = ginst.findProfile()
+        assert abs(ginst.findAction(gprof) - S_ref) < 1e-9 * S_ref
+        assert len(gprof.R) == len(prof.R)
+        np.testing.assert_allclose(gprof.R, prof.R, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(gprof.Phi, prof.Phi, rtol=0, atol=1e-9)
+
+
+def test_thermal_functions_vs_live_reference(ref):
+    """finiteT.Jb_spline / Jf_spline (derivatives 0..3) and model1.Vtot on fresh random inputs (not the goldens)."""
+    from cosmotransitions_b200 import finiteT as gfT, generic_potential as ggp
+    fT = ref["fT"]
+    rng = np.random.default_rng(77)
+    th = np.concatenate([rng.uniform(-8, 1500, 20000), rng.normal(0, 2, 5000)])
+    for n in range(4):
+        assert np.abs(gfT.Jb_spline(th, n=n) - fT.Jb_spline(th, n=n)).max() < 1e-10
+        assert np.abs(gfT.Jf_spline(th, n=n) - fT.Jf_spline(th, n=n)).max() < 1e-10
+    from cosmoTransitions.examples import testModel1 as tm
+    m_ref, m_gpu = tm.model1(), ggp.model1()
+    X = rng.uniform(-350, 350, (3000, 2))
+    T = rng.uniform(0, 250, 3000)
+    v_ref, v_gpu = m_ref.Vtot(X, T), m_gpu.Vtot(X, T)
+    assert np.max(np.abs(v_gpu - v_ref) / np.maximum(1.0, np.abs(v_ref))) < 1e-11

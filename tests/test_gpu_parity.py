@@ -9,6 +9,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 S_RTOL = 1e-6          # BASELINE.json: "Euclidean action S within 1e-6 relative"
 S_RTOL_TIGHT = 1e-9    # what a trajectory-faithful FP64 restatement actually achieves on quartics
 J_ATOL = 1e-10         # BASELINE.json: "Jb/Jf within 1e-10 absolute on the shared spline grid"
@@ -426,19 +428,63 @@ def test_bounce_pipeline_streams(ctb):
 
 
 def test_multigpu_driver(ctb):
-    """Single-process multi-device driver: strided shards, gather in the original order.  With one
-    visible device it degenerates to one shard; with several the result must not change."""
+    """Single-process multi-device driver: block-cyclic shards moved by pitched DMA copies straight out of / into the
+    global host arrays.  With one visible device it degenerates to one shard; with several (or the same device
+    listed several times) and with any block size the result must not change by a bit."""
     import torch
     from cosmotransitions_b200 import _lib, batch, multigpu, potentials
     n = 777
     c = 0.02 + 0.475 * np.random.default_rng(2).random(n)
     p = potentials.quartic_family_params(c)
+    p[5] = [0, 0, -0.1, -0.8 / 3, 0.25]          # no barrier
     ref = _np(batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, kernel="thread"))
     devs = list(range(torch.cuda.device_count()))
-    for dl in ([0], devs, [0, 0, 0]):       # the same device three times exercises G > 1 on a 1-GPU box
-        got = _np(multigpu.find_bounce_batch_multi(_lib.POT_POLY4, p, 1.0, 0.0, devices=dl, kernel="thread"))
-        for k in ("S", "phi0", "rf", "status", "n_rkck"):
-            assert np.array_equal(got[k], ref[k], equal_nan=True), (dl, k)
+    for dl, blk in (([0], 256), (devs, 256), ([0, 0, 0], 256), ([0, 0, 0], 1), ([0, 0], 64), ([0] * 5, 100)):
+        got = _np(multigpu.find_bounce_batch_multi(_lib.POT_POLY4, p, 1.0, 0.0, devices=dl, block=blk, kernel="thread"))
+        assert set(got) == set(ref)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (dl, blk, k)
+    # arrays for the minima, pinned tensors as inputs, a subset of the outputs
+    pa, pm = torch.ones(n, dtype=torch.float64).pin_memory(), torch.zeros(n, dtype=torch.float64).pin_memory()
+    got = _np(multigpu.find_bounce_batch_multi(_lib.POT_POLY4, torch.from_numpy(p).pin_memory(), pa, pm,
+                                               devices=[0, 0, 0], block=32, outputs=("S", "status"), kernel="thread"))
+    assert set(got) == {"S", "status"}
+    assert np.array_equal(got["S"], ref["S"], equal_nan=True) and np.array_equal(got["status"], ref["status"])
+    assert got["status"][5] == 3
+
+
+def test_sharded_dma_matches_host_definition(ctb):
+    """ShardLayout.copy_in / copy_out (cudaMemcpy2DAsync descriptors) against take / put (numpy), incl. ragged tails."""
+    import torch
+    from cosmotransitions_b200 import multigpu
+    rng = np.random.default_rng(5)
+    st = torch.cuda.current_stream().cuda_stream
+    for n, G, B in ((1000, 3, 64), (1003, 8, 256), (5, 2, 1), (4096, 4, 256), (257, 2, 256)):
+        a = rng.random((n, 5))
+        back = np.full((n, 5), np.nan)
+        for r in range(G):
+            lay = multigpu.ShardLayout(n, G, r, B)
+            d = torch.full((max(lay.n_local, 1), 5), -1.0, dtype=torch.float64, device="cuda")
+            lay.copy_in(a.ctypes.data, d.data_ptr(), 40, st)
+            torch.cuda.synchronize()
+            assert np.array_equal(d.cpu().numpy()[:lay.n_local], lay.take(a)), (n, G, B, r)
+            lay.copy_out(d.data_ptr(), back.ctypes.data, 40, st)
+            torch.cuda.synchronize()
+        assert np.array_equal(back, a)
+
+
+@pytest.mark.timeout(600)
+def test_distributed_driver_one_rank_per_gpu(ctb):
+    """One process per GPU (here: two ranks sharing the visible device(s)) under gloo: every rank's DMA lands in the
+    shared, page-locked result segment; rank 0 reads the global result.  Bit-identical to the single-process solve."""
+    import subprocess
+    import sys
+    import torch
+    script = os.path.join(REPO, "tests", "_dist_gpu_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", script],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=560)
+    assert out.returncode == 0 and "DIST_GPU_OK" in out.stdout, out.stdout[-3000:]
 
 
 def test_edge_batches(ctb):
@@ -569,6 +615,70 @@ def test_model1_vtot_golden(ctb, gold_dir):
     Vb = m.Vtot(X[:, None, :], g["grid_T"][None, :])
     assert Vb.shape == ref.shape
     np.testing.assert_allclose(Vb, ref, rtol=1e-11, atol=1e-13 * scale)
+
+
+def _c4_axes():
+    x_low = np.array([286.39824989, 382.19727238])
+    x_high = np.array([231.10296383, -136.82260069])
+    L = np.linalg.norm(x_high - x_low)
+    return x_low, (x_high - x_low) / L, L
+
+
+def test_c4_full_size_grid_vs_oracle(ctb, oracle, tables):
+    """BASELINE.json configs[3] at its stated size: Vtot on the 4096 x 1024 (phi, T) grid of SURVEY.md s.8d C4 against
+    the CPU oracle (whose grid function is pinned to the reference's Vtot by tests/test_oracle_golden.py)."""
+    from cosmotransitions_b200 import generic_potential as gp
+    m = gp.model1()
+    x0, nhat, L = _c4_axes()
+    s, T = np.linspace(-0.2 * L, 1.2 * L, 4096), np.linspace(1, 250, 1024)
+    V = m.Vtot_grid(x0, nhat, s, T)
+    cfg = oracle.make_config(kind=oracle.POT_MODEL1_LINE, tables=tables)
+    ref = oracle.vtot_model1_grid(cfg, list(m.model8) + [0.0] + list(x0) + list(nhat), s, T)
+    assert V.shape == ref.shape == (4096, 1024)
+    scale = np.max(np.abs(ref))
+    np.testing.assert_allclose(V, ref, rtol=1e-11, atol=1e-13 * scale)
+    # the same grid through the pointwise kernel with the reference's broadcasting contract, one row block
+    X = x0[None, :] + s[1000:1064, None] * nhat[None, :]
+    np.testing.assert_allclose(m.Vtot(X[:, None, :], T[None, :]), ref[1000:1064], rtol=1e-11, atol=1e-13 * scale)
+
+
+@pytest.mark.parametrize("nT", [1, 2, 3, 4, 5, 7, 64, 300])
+def test_vtot_grid_shapes(ctb, nT):
+    """Grid kernel on degenerate shapes (a line at a single T, few temperatures, many field points per block ...):
+    every shape must agree with the pointwise kernel to rounding (nT <= 3 overflowed the row cache)."""
+    from cosmotransitions_b200 import generic_potential as gp
+    m = gp.model1()
+    x0, nhat, L = _c4_axes()
+    rng = np.random.default_rng(nT)
+    for ns in (1, 63, 65, 1000, 4097):
+        s, T = np.sort(rng.uniform(-0.2 * L, 1.2 * L, ns)), rng.uniform(1, 250, nT)
+        V = m.Vtot_grid(x0, nhat, s, T)
+        X = x0[None, :] + s[:, None] * nhat[None, :]
+        ref = m.Vtot(X[:, None, :], T[None, :])
+        assert V.shape == (ns, nT)
+        np.testing.assert_allclose(V, ref, rtol=1e-12, atol=1e-14 * np.max(np.abs(ref)))
+
+
+def test_vtot_unaligned_and_bad_out(ctb):
+    """A CUDA view of X with an odd storage offset (8-byte aligned only) and a wrong `out` tensor."""
+    import torch
+    from cosmotransitions_b200 import generic_potential as gp
+    m = gp.model1()
+    flat = torch.linspace(-300, 300, 2001, dtype=torch.float64, device="cuda")
+    Xodd = flat[1:].reshape(-1, 2)            # data_ptr % 16 == 8
+    assert Xodd.data_ptr() % 16 == 8
+    T = torch.full((1000,), 80.0, dtype=torch.float64, device="cuda")
+    a = m.Vtot(Xodd, T)
+    b = m.Vtot(Xodd.clone(), T)
+    assert torch.equal(a, b)
+    x0, nhat, L = _c4_axes()
+    s, Tg = torch.linspace(0, L, 100, dtype=torch.float64, device="cuda"), torch.linspace(50, 100, 10, dtype=torch.float64, device="cuda")
+    for bad in (torch.empty((100, 10), dtype=torch.float32, device="cuda"), torch.empty((10, 100), dtype=torch.float64, device="cuda"),
+                torch.empty((100, 10), dtype=torch.float64), torch.empty((100, 20), dtype=torch.float64, device="cuda")[:, ::2]):
+        with pytest.raises(ValueError):
+            m.Vtot_grid(x0, nhat, s, Tg, out=bad)
+    good = torch.empty((100, 10), dtype=torch.float64, device="cuda")
+    assert m.Vtot_grid(x0, nhat, s, Tg, out=good) is good
 
 
 def test_model1_finite_difference_surface(ctb, gold_dir):

@@ -115,11 +115,39 @@ def test_opts_marshalling_and_defaults():
 def test_partition_roundtrip():
     import torch
     from cosmotransitions_b200 import multigpu
-    n, world = 1003, 8
-    vals = torch.arange(n, dtype=torch.float64) * 1.5
-    shards = [vals[torch.from_numpy(multigpu.partition(n, world, r))] for r in range(world)]
-    assert sum(len(s) for s in shards) == n
-    assert torch.equal(multigpu.gather_strided(shards, n, world), vals)
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 255, 256, 257, 1003, 10000):
+        for world in (1, 2, 3, 8):
+            for block in (1, 7, 256):
+                vals = rng.random((n, 3))
+                out = np.full((n, 3), np.nan)
+                shards = []
+                for r in range(world):
+                    lay = multigpu.ShardLayout(n, world, r, block)
+                    idx = multigpu.partition(n, world, r, block)
+                    assert lay.n_local == len(idx) == lay.nfull * block + lay.tail
+                    shards.append(lay.take(vals))
+                    assert np.array_equal(shards[-1], vals[idx])
+                    lay.put(shards[-1], out)
+                assert sum(len(s) for s in shards) == n and np.array_equal(out, vals)
+                assert np.array_equal(multigpu.gather_blocks(shards, n, world, block), vals)
+    assert np.array_equal(multigpu.partition(10, 3, 1), [1, 4, 7])      # block = 1: plain round-robin
+
+
+def test_shared_host_arrays_roundtrip(tmp_path):
+    """The shared-memory result segment of the one-process-per-GPU driver: two mappings see the same pages."""
+    from cosmotransitions_b200 import multigpu
+    path = str(tmp_path / "seg")
+    spec = [("S_0", np.float64, 1000), ("status_0", np.int32, 1000)]
+    a = multigpu.SharedHostArrays(path, spec, create=True, register=False)
+    b = multigpu.SharedHostArrays(path, spec, create=False, register=False)
+    a.arrays["S_0"][:] = np.arange(1000) * 0.5
+    b.arrays["status_0"][7] = 3
+    assert np.array_equal(b.arrays["S_0"], np.arange(1000) * 0.5) and a.arrays["status_0"][7] == 3
+    assert a.arrays["status_0"].ctypes.data % 4096 == a.arrays["S_0"].ctypes.data % 4096      # page-aligned slots
+    b.close()
+    a.close()
+    assert not os.path.exists(path)
 
 
 def test_no_silent_cpu_fallback():
@@ -190,19 +218,48 @@ def test_spline_potential_row_layout():
     np.testing.assert_allclose(v, interpolate.splev(xs, tck), rtol=1e-12, atol=1e-13)
 
 
-def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the keys the
-    driver reads.  Runs on CPU in a few seconds."""
+def _run_bench(*flags):
     import json
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1"], stdout=subprocess.PIPE, text=True, timeout=600).stdout
-    j = json.loads(out.strip().splitlines()[-1])
+                          "--warmup", "1"] + list(flags), stdout=subprocess.PIPE, text=True, timeout=600).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the keys the driver reads.  `--port`: the C restatement
+    with pthreads; default (oracle/_ref built by oracle/make_ref.py): the unmodified Python reference under
+    multiprocessing.Pool.  Runs on CPU in well under a minute."""
+    j = _run_bench("--port")
     assert j["impl"] == "reference" and j["unit"] == "bounces/s" and j["higher_is_better"] is True
     assert j["value"] > 1e3 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert j["config"]["workload"].startswith("C2") and j["solved_fraction"] == 1.0
+    assert j["config"] == {"workload": j["config"]["workload"], "instances": 100000, "alpha": 2, "order": "natural"}
+    if not os.path.exists(os.path.join(REPO, "oracle", "_ref", "cosmoTransitions", "tunneling1D.py")):
+        pytest.skip("oracle/_ref not built here (python oracle/make_ref.py)")
+    r = _run_bench("--ref-seconds", "1.0")
+    assert r["cpu_baseline"]["kind"] == "reference" and r["config"] == j["config"]
+    assert 1.0 < r["value"] < 1e5 and r["solved_fraction"] == 1.0 and "scipy" in r["versions"]
+
+
+def test_live_reference_matches_oracle_and_goldens(oracle):
+    """The unmodified reference shipped as oracle/_ref (oracle/make_ref.py), run live through oracle/ref_runner.py, against
+    the C restatement on the same C2 instances: the pin of the oracle, re-checked wherever the suite runs."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref not built here (python oracle/make_ref.py)")
+    from cosmotransitions_b200 import potentials
+    n = 100000
+    idx = np.arange(7, n, 2500)
+    c = 0.02 + 0.475 * (idx + 0.5) / n
+    for alpha in (2, 3):
+        S, status, _ = ref_runner.quartic_pool(c, alpha, procs=min(8, len(os.sched_getaffinity(0))), chunksize=5)
+        assert set(status) == {"ok"}
+        o = oracle.bounce_batch(oracle.make_config(alpha=alpha), potentials.quartic_family_params(c), 1.0, 0.0)
+        assert (o["status"] <= 1).all()
+        assert np.max(np.abs(o["S"] - S) / np.abs(S)) < 1e-9
 
 
 def test_monotonic_indices_matches_the_sequential_definition():
