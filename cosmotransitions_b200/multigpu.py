@@ -391,6 +391,8 @@ class DistributedBounce:
 
     def submit(self, params, phi_absMin, phi_metaMin):
         k = self._submitted
+        if k >= self.depth:
+            self._signal_through(k - self.depth)     # this rank's part of the ticket whose slot is reused
         # the slot about to be overwritten held ticket k - depth: rank 0 frees it by submitting, the others wait for that
         if self.rank == 0:
             self._freed[0] = k - self.depth + 1
@@ -414,7 +416,8 @@ class DistributedBounce:
     def _signal_through(self, ticket):
         """Wait for this rank's own tickets up to `ticket` (stream events) and publish that in the shared segment."""
         while self._signalled <= ticket:
-            if self._sharded is not None:
+            # (a ticket that already left the in-flight window finished before its slot was reused)
+            if self._sharded is not None and self._signalled >= self._sharded._submitted - self._sharded.depth:
                 self._sharded.wait(self._signalled)
             self._signalled += 1
         self._done[8 * self.rank] = self._signalled
@@ -425,7 +428,7 @@ class DistributedBounce:
         right after signalling."""
         ticket = self._submitted - 1 if ticket is None else ticket
         if not (self._submitted - self.depth <= ticket < self._submitted):
-            raise ValueError("ticket %d is not in flight" % ticket)
+            raise ValueError("ticket %d is not in flight (its result slot has been reused)" % ticket)
         self._signal_through(ticket)
         if self.rank != 0:
             return None

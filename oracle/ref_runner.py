@@ -71,6 +71,15 @@ def _one_quartic(c):
         return float("nan"), type(e).__name__
 
 
+def quartic_band(c, alpha, eps=(0.0, 1e-15, -1e-15, 3e-15, -3e-15, 1e-14, -1e-14, 3e-14, -3e-14, 1e-13, -1e-13)):
+    """(min, max) of the reference's S over c (1 + eps): its own sensitivity to the last digits of the input.  At a
+    few instances per ten thousand a shot sits on the edge between "converged" and "overshoot" (tunneling1D.py:
+    511-513): one bisection step more or less moves S by up to ~1e-5 relative."""
+    _init_worker(alpha)
+    vals = [_one_quartic(c * (1.0 + e))[0] for e in eps]
+    return float(np.nanmin(vals)), float(np.nanmax(vals))
+
+
 def make_pool(alpha, procs):
     import multiprocessing as mp
     return mp.get_context("fork").Pool(procs, initializer=_init_worker, initargs=(alpha,))

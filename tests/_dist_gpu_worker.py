@@ -22,8 +22,13 @@ def main():
     res = multigpu.find_bounce_batch_distributed(_lib.POT_POLY4, p, 1.0, 0.0, alpha=3, block=256)
     db = multigpu.DistributedBounce(_lib.POT_POLY4, n, depth=2, outputs=("S", "status", "n_rkck"), alpha=3)
     pp = torch.from_numpy(p).pin_memory()
-    tickets = [db.submit(pp, 1.0, 0.0) for _ in range(3)]
+    tickets = [db.submit(pp, 1.0, 0.0) for _ in range(3)]      # depth 2: the third submit reuses ticket 0's slot
     pipe = [db.collect(t) for t in tickets[1:]]
+    try:
+        db.collect(tickets[0])
+        raise SystemExit("collect of a recycled ticket must raise")
+    except ValueError:
+        pass
     if rank == 0:
         ref = batch.find_bounce_batch(_lib.POT_POLY4, p, 1.0, 0.0, alpha=3)
         for k, v in ref.items():
