@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) vtot_model1_kernel(Model8 m, JTab g, cons
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double2 x = reinterpret_cast<const double2 *>(X)[i];
         const double Ti = T[i];
-        const Model1Field f = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, x.x, x.y);
+        const Model1Field f = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, 1.0 / m.rs, m.v2, x.x, x.y);
         const double T2 = Ti * Ti + 1e-100;
         const double v1t = (parts & CTB_V_THERMAL)
                                ? model1_v1t(f, m.nb, jb, 1.0 / T2, (Ti * Ti * Ti * Ti) / (2 * CTB_PI * CTB_PI)) : 0.0;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(VG_THREADS) vtot_model1_grid_kernel(Model8 m, 
         const int64_t i_first = p0 / nT, i_last = (p1 - 1) / nT;
         for (int64_t r = threadIdx.x; r <= i_last - i_first; r += VG_THREADS) {
             const double si = s[i_first + r];
-            rowc[r] = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, m.rs, m.v2, x0 + si * n0, x1 + si * n1);
+            rowc[r] = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, 1.0 / m.rs, m.v2, x0 + si * n0, x1 + si * n1);
         }
         __syncthreads();
         int64_t p = p0 + threadIdx.x;
@@ -406,10 +406,11 @@ __global__ void fp64_peak_kernel(int64_t iters, double *sink)
 
 JTab to_jtab(const ctb_jtable *t)
 {
-    JTab j{nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f};
+    JTab j{nullptr, nullptr, JT_GLOBAL, 0, 0, 0, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f, 0.0f};
     if (t) {
         j.brk = t->d_brk; j.coef = t->d_coef; j.nint = t->nint; j.xmin = t->xmin; j.xmax = t->xmax;
         j.loc_scale = (float)t->loc_scale; j.loc_u0 = (float)t->loc_u0; j.loc_inv_du = (float)t->loc_inv_du;
+        j.loc_c = (float)(-t->loc_u0 * t->loc_inv_du - 1.001);
     }
     return j;
 }
@@ -436,17 +437,17 @@ int launch_rows(int pot_kind, const double *d_params, const ctb_jtable *jb, cons
         break;
     case CTB_POT_THERMAL1F:
         if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
-        rows_kernel<PotThermal1F, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+        launch_k(rows_kernel<PotThermal1F, MINIMIZE>, g, 128, pot_smem_bytes<PotThermal1F>(jb->nint), st, d_params, to_jtab(jb), to_jtab(jf), a, b,
                                                                             xtol_rel, o0, o1, n);
         break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        rows_kernel<PotModel1Line, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+        launch_k(rows_kernel<PotModel1Line, MINIMIZE>, g, 128, pot_smem_bytes<PotModel1Line>(jb->nint), st, d_params, to_jtab(jb), to_jtab(jf), a, b,
                                                                              xtol_rel, o0, o1, n);
         break;
     case CTB_POT_MODEL1F:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        rows_kernel<PotModel1F, MINIMIZE><<<g, 128, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), a, b,
+        launch_k(rows_kernel<PotModel1F, MINIMIZE>, g, 128, pot_smem_bytes<PotModel1F>(jb->nint), st, d_params, to_jtab(jb), to_jtab(jf), a, b,
                                                                           xtol_rel, o0, o1, n);
         break;
     default: return CTB_ERR_UNSUPPORTED;
@@ -565,9 +566,9 @@ int launch_find_action(const double *params, const ctb_jtable *jb, const ctb_jta
 {
     const double d = alpha + 1.0; // T1D:782-790
     const double afac = 2.0 * pow(CTB_PI, 0.5 * d) / tgamma(0.5 * d), vfac = pow(CTB_PI, 0.5 * d) / tgamma(0.5 * d + 1.0);
-    const size_t sm = Pot::analytic ? 0 : table_bytes_compact(jb);
-    find_action_kernel<Pot><<<(unsigned)((n + 3) / 4), 128, sm, st>>>(params, to_jtab(jb), to_jtab(jf), phi_meta, R, Phi,
-                                                                      dPhi, stride, npts, n, alpha, afac, vfac, S);
+    const size_t sm = Pot::analytic ? 0 : pot_smem_bytes<Pot>(jb->nint);
+    launch_k(find_action_kernel<Pot>, (unsigned)((n + 3) / 4), 128, sm, st, params, to_jtab(jb), to_jtab(jf), phi_meta, R, Phi,
+             dPhi, stride, npts, n, alpha, afac, vfac, S);
     return (int)cudaGetLastError();
 }
 
@@ -835,21 +836,21 @@ CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable
     if (n == 0) return CTB_OK;
     if (!d_params || !d_phi || !d_out) return CTB_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    int g = grid_for(n, 256);
+    int g = grid_for(n, 128);
     switch (pot_kind) {
     case CTB_POT_POLY4: potential_kernel<PotPoly4><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n); break;
     case CTB_POT_SPLINE: potential_kernel<PotSpline><<<g, 256, 0, st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n); break;
     case CTB_POT_THERMAL1F:
         if (!(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotThermal1F><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        launch_k(potential_kernel<PotThermal1F>, g, 128, pot_smem_bytes<PotThermal1F>(jb->nint), st, d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     case CTB_POT_MODEL1_LINE:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotModel1Line><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        launch_k(potential_kernel<PotModel1Line>, g, 128, pot_smem_bytes<PotModel1Line>(jb->nint), st, d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     case CTB_POT_MODEL1F:
         if (!jtab_ok(jb)) return CTB_ERR_BAD_ARG;
-        potential_kernel<PotModel1F><<<g, 256, table_bytes_compact(jb), st>>>(d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
+        launch_k(potential_kernel<PotModel1F>, g, 128, pot_smem_bytes<PotModel1F>(jb->nint), st, d_params, to_jtab(jb), to_jtab(jf), d_phi, d_out, n);
         break;
     default: return CTB_ERR_UNSUPPORTED;
     }

@@ -131,8 +131,7 @@ __global__ void __launch_bounds__(128) setup_kernel(const BounceArgs a)
 template <class Pot>
 int launch_setup_any(const BounceArgs &a, cudaStream_t st)
 {
-    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double);
-    setup_kernel<Pot><<<(unsigned)((a.n + 127) / 128), 128, sm, st>>>(a);
+    launch_k(setup_kernel<Pot>, (unsigned)((a.n + 127) / 128), 128, pot_smem_bytes<Pot>(a.jb.nint), st, a);
     return (int)cudaGetLastError();
 }
 
@@ -142,7 +141,7 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     if (block < 32 || block > CTB_MAX_BLOCK || (block & 31)) return CTB_ERR_UNSUPPORTED;
     unsigned grid = (unsigned)((a.n + block - 1) / block);
     const bool prof = a.out.d_prof_R != nullptr;
-    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double);
+    const size_t sm = pot_smem_bytes<Pot>(a.jb.nint);
     // split solve (shoot kernel, then save kernel) when the caller provides scratch and all hand-over arrays
     const bool split = a.scratch && !prof && a.out.d_status && a.out.d_r0 && a.out.d_rf && a.out.d_n_shots &&
                        a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
@@ -154,20 +153,20 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
         const bool big = Pot::analytic && a.n >= 300000; // throughput regime: trade registers for warps
 #endif
         if (alpha == 2) {
-            if (big) bounce_kernel<Pot, 2, false, MODE_SHOOT, CTB_BIG_OCC><<<grid, block, sm, st>>>(a);
-            else bounce_kernel<Pot, 2, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
-            bounce_kernel<Pot, 2, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
+            if (big) launch_k(bounce_kernel<Pot, 2, false, MODE_SHOOT, CTB_BIG_OCC>, grid, block, sm, st, a);
+            else launch_k(bounce_kernel<Pot, 2, false, MODE_SHOOT, 3>, grid, block, sm, st, a);
+            launch_k(bounce_kernel<Pot, 2, false, MODE_SAVE>, grid, block, sm, st, a);
         } else {
-            if (big) bounce_kernel<Pot, 3, false, MODE_SHOOT, CTB_BIG_OCC><<<grid, block, sm, st>>>(a);
-            else bounce_kernel<Pot, 3, false, MODE_SHOOT, 3><<<grid, block, sm, st>>>(a);
-            bounce_kernel<Pot, 3, false, MODE_SAVE><<<grid, block, sm, st>>>(a);
+            if (big) launch_k(bounce_kernel<Pot, 3, false, MODE_SHOOT, CTB_BIG_OCC>, grid, block, sm, st, a);
+            else launch_k(bounce_kernel<Pot, 3, false, MODE_SHOOT, 3>, grid, block, sm, st, a);
+            launch_k(bounce_kernel<Pot, 3, false, MODE_SAVE>, grid, block, sm, st, a);
         }
     } else {
         // single-kernel form; the only one compiled for alpha = 1 and 4 (d = 2 and 5 dimensions)
 #define CTB_LAUNCH_FUSED(AL)                                                                     \
     do {                                                                                         \
-        if (prof) bounce_kernel<Pot, AL, true, MODE_FUSED><<<grid, block, sm, st>>>(a);          \
-        else bounce_kernel<Pot, AL, false, MODE_FUSED><<<grid, block, sm, st>>>(a);              \
+        if (prof) launch_k(bounce_kernel<Pot, AL, true, MODE_FUSED>, grid, block, sm, st, a);          \
+        else launch_k(bounce_kernel<Pot, AL, false, MODE_FUSED>, grid, block, sm, st, a);              \
     } while (0)
         switch (alpha) {
         case 1: CTB_LAUNCH_FUSED(1); break;
@@ -185,8 +184,7 @@ template <class Pot>
 int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((a.n + 3) / 4);
-    const size_t sm = (Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double))
-                      + (size_t)4 * 2 * stage_cap * sizeof(double);
+    const size_t sm = pot_smem_bytes<Pot>(a.jb.nint) + (size_t)4 * 2 * stage_cap * sizeof(double);
     if (sm > 200 * 1024) return CTB_ERR_UNSUPPORTED;
     const bool prof = a.out.d_prof_R != nullptr;
 #define CTB_LAUNCH_WARP(AL, PR)                                                                                  \

@@ -27,13 +27,24 @@ namespace ctb {
 
 // ------------------------------------------------------------------------------------------------
 // Jb / Jf spline tables (piecewise cubic, see ctbounce.h)                      FT:167-174,197-204
+//
+// Every kernel that evaluates a table stages it in DYNAMIC shared memory first.  The staged copy is addressed by
+// element offsets into the dynamic shared-memory window (ctb_dynsmem), not by pointers: the compiler then emits
+// LDS / LDS.128 directly.  (Through generic pointers held in a struct the same accesses were generic LD plus
+// register <-> uniform-register traffic: half of the instructions of the out-of-line V of round 1.)
+extern __shared__ double ctb_dynsmem[];
+
+enum { JT_GLOBAL = 0, JT_COMPACT = 1, JT_RECORDS = 2 };
 struct JTab {
     const double *brk;  // [nint + 1] global memory
     const double *coef; // [nint * 4] global memory
-    const double *rec;  // after stage_table: shared-memory records {brk_j, c0, c1, c2, c3, brk_{j+1}} (48 B each)
+    int mode;           // JT_GLOBAL: brk / coef above; JT_COMPACT: i_brk / i_coef; JT_RECORDS: i_rec
+    int i_brk, i_coef;  // offsets (in doubles) into ctb_dynsmem
+    int i_rec;          // records {brk_j, c0, c1, c2, c3, brk_{j+1}} (48 B each)
     int nint;
     double xmin, xmax;
     float loc_scale, loc_u0, loc_inv_du; // closed-form locator (see ctbounce.h); loc_inv_du == 0: bisection
+    float loc_c;                         // -loc_u0 loc_inv_du - 1 - 1e-3: offset of the one-sided interval guess
 };
 
 #define CTB_TABLE_DOUBLES(nint) ((size_t)(nint) * 6)
@@ -41,6 +52,7 @@ struct JTab {
 // Copies a table into shared memory (whole block cooperates; caller syncs) as one 48-byte record per knot
 // interval -- left breakpoint, the four coefficients, right breakpoint -- so that an evaluation touches
 // exactly three 16-byte words: the interval test and the polynomial come from the same record.
+// `smem` must point into the dynamic shared-memory window, 16-byte aligned.
 CTB_DEV JTab stage_table(const JTab &g, double *smem)
 {
     for (int j = threadIdx.x; j < g.nint; j += blockDim.x) {
@@ -50,85 +62,179 @@ CTB_DEV JTab stage_table(const JTab &g, double *smem)
         r[5] = g.brk[j + 1];
     }
     JTab t = g;
-    t.rec = smem;
+    t.mode = JT_RECORDS;
+    t.i_rec = (int)(smem - ctb_dynsmem);
     return t;
 }
 
-// Compact staging (40 KB: breakpoints, then coefficients) for the bounce / minimiser kernels, which are
-// register- and L1-hungry (local-memory stack of the out-of-line V): every KB of shared memory they do
-// not take stays L1.  (Measured: the 48 KB record layout slows the finite-T bounce kernel by 40 %.)
-#define CTB_TABLE_DOUBLES_COMPACT(nint) ((size_t)(nint) * 5 + 2)
+// Compact staging (40 KB) for the bounce / minimiser kernels: a 32-byte header (so that the out-of-line V needs
+// one offset, not a descriptor), breakpoints, coefficients; after it come the per-thread parameter slots of the
+// potential functor (CTB_SLOT_STRIDE doubles per parameter, slot k of thread t at [k * CTB_SLOT_STRIDE + t]).
+// Four 128-thread blocks (table + slots <= 55 KB) fit one SM.
+#define CTB_SLOT_STRIDE 128
+#define CTB_TABLE_DOUBLES_COMPACT(nint) ((size_t)(nint) * 5 + 6)
+struct JHeader { double xmin, xmax; int last; float loc_scale, loc_inv_du, loc_c; };
+CTB_DEV int jtab_compact_nb(int nint) { return (nint + 2) & ~1; }
 CTB_DEV JTab stage_table_compact(const JTab &g, double *smem)
 {
-    const int nb = (g.nint + 2) & ~1;
-    for (int i = threadIdx.x; i < g.nint + 1; i += blockDim.x) smem[i] = g.brk[i];
-    for (int i = threadIdx.x; i < 4 * g.nint; i += blockDim.x) smem[nb + i] = g.coef[i];
+    const int nb = jtab_compact_nb(g.nint);
+    if (threadIdx.x == 0) {
+        JHeader *h = reinterpret_cast<JHeader *>(smem);
+        h->xmin = g.xmin; h->xmax = g.xmax; h->last = g.nint - 1;
+        h->loc_scale = g.loc_scale; h->loc_inv_du = g.loc_inv_du; h->loc_c = g.loc_c;
+    }
+    for (int i = threadIdx.x; i < g.nint + 1; i += blockDim.x) smem[4 + i] = g.brk[i];
+    for (int i = threadIdx.x; i < 4 * g.nint; i += blockDim.x) smem[4 + nb + i] = g.coef[i];
     JTab t = g;
-    t.brk = smem;
-    t.coef = smem + nb;
-    t.rec = nullptr;
+    t.mode = JT_COMPACT;
+    t.i_brk = (int)(smem - ctb_dynsmem) + 4;
+    t.i_coef = t.i_brk + nb;
     return t;
 }
+// offset of the parameter slots that follow a compact table staged at ctb_dynsmem[i_brk - 4]
+CTB_DEV int jtab_slot_base(const JTab &t) { return t.i_coef + 4 * t.nint; }
 
-CTB_DEV int jtab_guess(const JTab &t, double x)
+// One-sided FP32 guess of the knot interval from the sinh spacing of the reference's sample grid
+// (x_k = |xmin| sinh(u_k)/20, u_k uniform; not-a-knot spline: interval j starts at sample j + 1 for j >= 1):
+// k = (asinh(x scale) - u0) / du computed with the MUFU approximations is good to ~3e-4 of an interval, so
+// g = floor(k - 1 - 1e-3), clamped, is either the interval that holds x or the one below it -- never above
+// (checked against bisection on 3e6 arguments incl. every breakpoint +- 1 ulp: 0.16 % one low, none high).
+CTB_DEV int jtab_guess_f(double x, float loc_scale, float loc_inv_du, float loc_c, int last)
 {
-    // FP32 guess of the knot interval from the sinh spacing of the reference's sample grid
-    const int last = t.nint - 1;
-    float z = (float)x * t.loc_scale;
-    float a = fabsf(z);
-    float u = copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), z);
-    float kf = floorf((u - t.loc_u0) * t.loc_inv_du) - 1.0f;
-    return (int)fminf(fmaxf(kf, 0.0f), (float)last);
+    const float z = (float)x * loc_scale;
+    const float a = fabsf(z);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(a, a, 1.0f)));
+    const float u = copysignf(__logf(a + r), z);
+    const int g = __float2int_rd(fmaf(u, loc_inv_du, loc_c));
+    return min(max(g, 0), last);
+}
+CTB_DEV int jtab_guess(const JTab &t, double x) { return jtab_guess_f(x, t.loc_scale, t.loc_inv_du, t.loc_c, t.nint - 1); }
+
+CTB_DEV double jtab_brk(const JTab &t, int j)
+{
+    return t.mode == JT_COMPACT ? ctb_dynsmem[t.i_brk + j] : t.mode == JT_RECORDS ? ctb_dynsmem[t.i_rec + 6 * j] : t.brk[j];
 }
 
 CTB_DEV int jtab_locate(const JTab &t, double x)
 {
     // largest j in [0, nint-1] with brk[j] <= x  (j = 0 below the table: first piece extrapolates)
-    const int last = t.nint - 1;
-    if (t.loc_inv_du != 0.0f) {
-        int j = jtab_guess(t, x);
-        while (j > 0 && x < t.brk[j]) --j;
-        while (j < last && x >= t.brk[j + 1]) ++j;
-        return j;
-    }
-    int lo = 0, hi = last;
+    int lo = 0, hi = t.nint - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
-        if (x >= t.brk[mid]) lo = mid; else hi = mid - 1;
+        if (x >= jtab_brk(t, mid)) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
 
 template <int DER>
+CTB_DEV double jtab_poly(double dx, double c0, double c1, double c2, double c3)
+{
+    if (DER == 0) return fma(dx, fma(dx, fma(dx, c3, c2), c1), c0);
+    if (DER == 1) return fma(dx, fma(dx, __dmul_rn(3.0, c3), __dmul_rn(2.0, c2)), c1);
+    if (DER == 2) return fma(dx, __dmul_rn(6.0, c3), __dmul_rn(2.0, c2));
+    return __dmul_rn(6.0, c3);
+}
+
+// Compact staged table, closed-form locator: guess, the two breakpoints around it, select, the coefficient pair.
+// Branch-free (two look-ups of one V interleave); relies on the one-sidedness of the guess.
+template <int DER>
+CTB_DEV double jtab_eval_compact(int i_brk, int i_coef, int last, double xmin, double xmax, float loc_scale,
+                                 float loc_inv_du, float loc_c, double theta)
+{
+    const double x = (theta < xmin) ? xmin : theta;
+    int j = jtab_guess_f(x, loc_scale, loc_inv_du, loc_c, last);
+    const double bg = ctb_dynsmem[i_brk + j], bn = ctb_dynsmem[i_brk + j + 1];
+    const bool up = (x >= bn) && (j < last);
+    const double b0 = up ? bn : bg;
+    j += up;
+    const double2 *c = reinterpret_cast<const double2 *>(ctb_dynsmem + i_coef) + 2 * j;
+    const double2 c01 = c[0], c23 = c[1];
+    const double v = jtab_poly<DER>(__dsub_rn(x, b0), c01.x, c01.y, c23.x, c23.y);
+    return (theta > xmax) ? 0.0 : v;
+}
+
+// Piecewise-cubic evaluation, any staging mode.
+template <int DER>
 CTB_DEV double jtab_eval(const JTab &t, double theta)
 {
-    double x = (theta < t.xmin) ? t.xmin : theta;
+    const int last = t.nint - 1;
+    if (t.loc_inv_du != 0.0f && t.mode == JT_COMPACT)
+        return jtab_eval_compact<DER>(t.i_brk, t.i_coef, last, t.xmin, t.xmax, t.loc_scale, t.loc_inv_du, t.loc_c, theta);
+    const double x = (theta < t.xmin) ? t.xmin : theta;
     double b0, c0, c1, c2, c3;
-    if (t.rec && t.loc_inv_du != 0.0f) { // staged records + closed-form guess: usually one record read
-        const int last = t.nint - 1;
+    if (t.loc_inv_du != 0.0f && t.mode == JT_RECORDS) {
+        // one staged 48-byte record (three 16-byte loads); the next one when the guess was one low (~0.2 %)
         int j = jtab_guess(t, x);
-        for (;;) {
-            const double2 *r = reinterpret_cast<const double2 *>(t.rec + 6 * j);
-            const double2 q0 = r[0], q1 = r[1], q2 = r[2];
-            b0 = q0.x; c0 = q0.y; c1 = q1.x; c2 = q1.y; c3 = q2.x;
-            if (x < b0 && j > 0) { --j; continue; }
-            if (x >= q2.y && j < last) { ++j; continue; }
-            break;
+        const double2 *r = reinterpret_cast<const double2 *>(ctb_dynsmem + t.i_rec) + 3 * j;
+        double2 q0 = r[0], q1 = r[1], q2 = r[2];
+        if (x >= q2.y && j < last) {
+            q0 = r[3]; q1 = r[4]; q2 = r[5];
         }
+        b0 = q0.x; c0 = q0.y; c1 = q1.x; c2 = q1.y; c3 = q2.x;
     } else {
-        const int j = jtab_locate(t, x);
-        b0 = t.brk[j];
-        const double2 c01 = reinterpret_cast<const double2 *>(t.coef)[2 * j];
-        const double2 c23 = reinterpret_cast<const double2 *>(t.coef)[2 * j + 1];
-        c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y;
+        int j;
+        if (t.loc_inv_du != 0.0f) {
+            j = jtab_guess(t, x);
+            j += (j < last && x >= jtab_brk(t, j + 1));
+        } else {
+            j = jtab_locate(t, x);
+        }
+        b0 = jtab_brk(t, j);
+        if (t.mode == JT_RECORDS) {
+            const double2 *r = reinterpret_cast<const double2 *>(ctb_dynsmem + t.i_rec) + 3 * j;
+            const double2 q0 = r[0], q1 = r[1], q2 = r[2];
+            c0 = q0.y; c1 = q1.x; c2 = q1.y; c3 = q2.x;
+        } else {
+            const double2 *c = (t.mode == JT_COMPACT ? reinterpret_cast<const double2 *>(ctb_dynsmem + t.i_coef)
+                                                     : reinterpret_cast<const double2 *>(t.coef)) + 2 * j;
+            const double2 c01 = c[0], c23 = c[1];
+            c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y;
+        }
     }
-    const double dx = x - b0;
-    double v;
-    if (DER == 0) v = c0 + dx * (c1 + dx * (c2 + dx * c3));
-    else if (DER == 1) v = c1 + dx * (2.0 * c2 + dx * (3.0 * c3));
-    else if (DER == 2) v = 2.0 * c2 + dx * (6.0 * c3);
-    else v = 6.0 * c3;
+    const double v = jtab_poly<DER>(__dsub_rn(x, b0), c0, c1, c2, c3);
     return (theta > t.xmax) ? 0.0 : v;
+}
+
+// log(x) for positive, finite, NORMAL x (the callers add 1e-100 to |m^2 / mu^2|, GP:250): branch-free, < 1 ulp.
+// Argument reduction x = 2^k m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = f / (2 + f), f = m - 1, with the
+// classic degree-14 even remainder polynomial (Lg1..Lg7) split into two chains; the division is a Newton reciprocal
+// plus one residual correction.  ~35 instructions where the library routine (special-case branches, call ABI) costs
+// ~80 inside the out-of-line V.  Non-finite x passes through (NaN stays NaN, inf stays inf).
+CTB_DEV double log_pos(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    hx += 0x3ff00000 - 0x3fe6a09e;
+    const int k = (hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffff) + 0x3fe6a09e;
+    const double m = __hiloint2double(hx, lx);
+    const double f = __dadd_rn(m, -1.0);
+    const double hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
+    const double d = __dadd_rn(2.0, f);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    double s = __dmul_rn(f, r);
+    s = fma(fma(-s, d, f), r, s);
+    const double z = __dmul_rn(s, s);
+    const double w = __dmul_rn(z, z);
+    const double t1 = __dmul_rn(w, fma(w, fma(w, Lg6, Lg4), Lg2));
+    const double t2 = __dmul_rn(z, fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1));
+    const double R = __dadd_rn(t2, t1);
+    const double dk = (double)k;
+    // s (hfsq + R) + dk ln2_lo - hfsq + f + dk ln2_hi, summed in fdlibm's order
+    double v = fma(s, __dadd_rn(hfsq, R), __dmul_rn(dk, ln2_lo));
+    v = __dadd_rn(__dsub_rn(v, hfsq), f);
+    v = fma(dk, ln2_hi, v);
+    return (fabs(x) < 1.7976931348623157e308) ? v : x;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -142,6 +248,7 @@ struct PotPoly4 {
     static constexpr bool analytic = true;
     static constexpr int min_blocks = CTB_POLY4_MIN_BLOCKS; // 128-thread blocks per SM the bounce kernel is compiled for (<= 168 regs)
     static constexpr int nparam = CTB_NPARAM_POLY4;
+    static constexpr int nslot = 0;
     double c0, c1, c2, c3, c4;
     CTB_DEV void load(const double *p, const JTab *, const JTab *)
     {
@@ -171,6 +278,7 @@ struct PotSpline {
     static constexpr bool analytic = true;
     static constexpr int min_blocks = 3;
     static constexpr int nparam = CTB_NPARAM_SPLINE;
+    static constexpr int nslot = 0;
     const double *brk, *coef;
     int nint;
     CTB_DEV void load(const double *p, const JTab *, const JTab *)
@@ -217,7 +325,7 @@ struct PotSpline {
 // Field-dependent part of model1's Vtot: the three boson masses (examples/testModel1.py:89-93) and
 // V0 + V1 (examples/testModel1.py:78-80, GP:240-256).  Independent of T.
 struct Model1Field { double m0, m1, mb, V01, V0, V1; };
-CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, double Y2, double nb, double rs, double v2,
+CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, double Y2, double nb, double inv_rs, double v2,
                                  double phi1, double phi2)
 {
     double a = l1 * (3 * phi1 * phi1 - v2);
@@ -229,15 +337,41 @@ CTB_DEV Model1Field model1_field(double l1, double l2, double mu2, double Y1, do
     f.m0 = A + B; f.m1 = A - B;
     double r = .25 * l1 * (phi1 * phi1 - v2) * (phi1 * phi1 - v2) + .25 * l2 * (phi2 * phi2 - v2) * (phi2 * phi2 - v2);
     r -= mu2 * phi1 * phi2;
-    const double inv_rs = 1.0 / rs;
     double y1 = 0.0;
-    y1 += 1.0 * f.m0 * f.m0 * (log(fabs(f.m0 * inv_rs) + 1e-100) - 1.5);
-    y1 += 1.0 * f.m1 * f.m1 * (log(fabs(f.m1 * inv_rs) + 1e-100) - 1.5);
-    y1 += nb * f.mb * f.mb * (log(fabs(f.mb * inv_rs) + 1e-100) - 1.5);
+    y1 += 1.0 * f.m0 * f.m0 * (log_pos(fabs(f.m0 * inv_rs) + 1e-100) - 1.5);
+    y1 += 1.0 * f.m1 * f.m1 * (log_pos(fabs(f.m1 * inv_rs) + 1e-100) - 1.5);
+    y1 += nb * f.mb * f.mb * (log_pos(fabs(f.mb * inv_rs) + 1e-100) - 1.5);
     f.V0 = r;
     f.V1 = y1 * (1.0 / (64 * CTB_PI * CTB_PI));
     f.V01 = r + f.V1;
     return f;
+}
+
+// Thermal functors with per-thread parameter SLOTS in shared memory.  V is ONE out-of-line function per functor
+// (it is called from ~15 places: 5-point stencils, bisection, fminbound, integrand; one copy keeps the kernel inside
+// the instruction cache) that takes the field value and two shared-memory offsets: the staged table and the
+// thread's slots.  Everything it needs comes in by LDS; nothing goes through a `this` pointer (which would put the
+// functor into local memory and turn every field access into a generic load).
+CTB_DEV double &pot_slot(int i_slot, int k) { return ctb_dynsmem[i_slot + k * CTB_SLOT_STRIDE + (threadIdx.x & (CTB_SLOT_STRIDE - 1))]; }
+
+struct TabView { // staged compact table as V sees it
+    int i_brk, i_coef, last;
+    double xmin, xmax;
+    float loc_scale, loc_inv_du, loc_c;
+};
+CTB_DEV TabView tab_view(int i_tab)
+{
+    const JHeader *h = reinterpret_cast<const JHeader *>(ctb_dynsmem + i_tab);
+    TabView t;
+    t.xmin = h->xmin; t.xmax = h->xmax; t.last = h->last;
+    t.loc_scale = h->loc_scale; t.loc_inv_du = h->loc_inv_du; t.loc_c = h->loc_c;
+    t.i_brk = i_tab + 4;
+    t.i_coef = t.i_brk + jtab_compact_nb(t.last + 1);
+    return t;
+}
+CTB_DEV double tab_J(const TabView &t, double theta)
+{
+    return jtab_eval_compact<0>(t.i_brk, t.i_coef, t.last, t.xmin, t.xmax, t.loc_scale, t.loc_inv_du, t.loc_c, theta);
 }
 
 // examples/testModel1.py:62-116 through GP:312-337, on the line X = x0 + phi*nhat
@@ -245,26 +379,33 @@ struct PotModel1Line {
     static constexpr bool analytic = false;
     static constexpr int min_blocks = CTB_THERMAL_MIN_BLOCKS;
     static constexpr int nparam = CTB_NPARAM_MODEL1_LINE;
-    double l1, l2, mu2, Y1, Y2, nb, rs, v2, inv_T2, T4c, x0, x1, n0, n1;
-    JTab jb;
+    static constexpr int nslot = 14;
+    enum { S_L1, S_L2, S_MU2, S_Y1, S_Y2, S_NB, S_INV_RS, S_V2, S_INV_T2, S_T4C, S_X0, S_X1, S_N0, S_N1 };
+    int i_tab, i_slot;
     CTB_DEV void load(const double *p, const JTab *jb_, const JTab *)
     {
-        l1 = p[0]; l2 = p[1]; mu2 = p[2]; Y1 = p[3]; Y2 = p[4]; nb = p[5]; rs = p[6]; v2 = p[7];
+        i_tab = jb_->i_brk - 4;
+        i_slot = jtab_slot_base(*jb_);
         const double T = p[8];
-        inv_T2 = 1.0 / (T * T + 1e-100);
-        T4c = (T * T * T * T) / (2 * CTB_PI * CTB_PI);
-        x0 = p[9]; x1 = p[10]; n0 = p[11]; n1 = p[12];
-        jb = *jb_;
+        pot_slot(i_slot, S_L1) = p[0]; pot_slot(i_slot, S_L2) = p[1]; pot_slot(i_slot, S_MU2) = p[2];
+        pot_slot(i_slot, S_Y1) = p[3]; pot_slot(i_slot, S_Y2) = p[4]; pot_slot(i_slot, S_NB) = p[5];
+        pot_slot(i_slot, S_INV_RS) = 1.0 / p[6]; pot_slot(i_slot, S_V2) = p[7];
+        pot_slot(i_slot, S_INV_T2) = 1.0 / (T * T + 1e-100);
+        pot_slot(i_slot, S_T4C) = (T * T * T * T) / (2 * CTB_PI * CTB_PI);
+        pot_slot(i_slot, S_X0) = p[9]; pot_slot(i_slot, S_X1) = p[10]; pot_slot(i_slot, S_N0) = p[11]; pot_slot(i_slot, S_N1) = p[12];
     }
-    // out of line: V is called from ~15 places (5-point stencils, bisection, fminbound, integrand);
-    // one copy keeps the kernel inside the instruction cache
-    __device__ __noinline__ double V(double phi) const
+    static __device__ __noinline__ double V_s(double phi, int i_tab, int i_slot)
     {
-        const Model1Field f = model1_field(l1, l2, mu2, Y1, Y2, nb, rs, v2, x0 + phi * n0, x1 + phi * n1);
-        const double yt = jtab_eval<0>(jb, f.m0 * inv_T2) + jtab_eval<0>(jb, f.m1 * inv_T2)
-                          + nb * jtab_eval<0>(jb, f.mb * inv_T2);
-        return f.V01 + yt * T4c;
+        const TabView t = tab_view(i_tab);
+        const double nb = pot_slot(i_slot, S_NB), inv_T2 = pot_slot(i_slot, S_INV_T2);
+        const Model1Field f = model1_field(pot_slot(i_slot, S_L1), pot_slot(i_slot, S_L2), pot_slot(i_slot, S_MU2),
+                                           pot_slot(i_slot, S_Y1), pot_slot(i_slot, S_Y2), nb, pot_slot(i_slot, S_INV_RS),
+                                           pot_slot(i_slot, S_V2), fma(phi, pot_slot(i_slot, S_N0), pot_slot(i_slot, S_X0)),
+                                           fma(phi, pot_slot(i_slot, S_N1), pot_slot(i_slot, S_X1)));
+        const double yt = tab_J(t, f.m0 * inv_T2) + tab_J(t, f.m1 * inv_T2) + nb * tab_J(t, f.mb * inv_T2);
+        return f.V01 + yt * pot_slot(i_slot, S_T4C);
     }
+    CTB_DEV double V(double phi) const { return V_s(phi, i_tab, i_slot); }
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
 
@@ -272,30 +413,39 @@ struct PotModel1F {
     static constexpr bool analytic = false;
     static constexpr int min_blocks = CTB_THERMAL_MIN_BLOCKS;
     static constexpr int nparam = CTB_NPARAM_MODEL1F;
-    double lam, v2, Y, nb, inv_rs, inv_T2, T4c;
-    JTab jb;
+    static constexpr int nslot = 7;
+    enum { S_LAM, S_V2, S_Y, S_NB, S_INV_RS, S_INV_T2, S_T4C };
+    int i_tab, i_slot;
     CTB_DEV void load(const double *p, const JTab *jb_, const JTab *)
     {
-        lam = p[0]; v2 = p[1]; Y = p[2]; nb = p[3];
+        i_tab = jb_->i_brk - 4;
+        i_slot = jtab_slot_base(*jb_);
         const double T = p[5];
+        pot_slot(i_slot, S_LAM) = p[0]; pot_slot(i_slot, S_V2) = p[1]; pot_slot(i_slot, S_Y) = p[2]; pot_slot(i_slot, S_NB) = p[3];
         // the reference divides by renormScaleSq, T^2 + 1e-100 and 2 pi^2 at every evaluation
         // (GP:250,282,296); the reciprocals are formed once here (<= 1 ulp per factor)
-        inv_rs = 1.0 / p[4];
-        inv_T2 = 1.0 / (T * T + 1e-100);
-        T4c = (T * T * T * T) / (2 * CTB_PI * CTB_PI);
-        jb = *jb_;
+        pot_slot(i_slot, S_INV_RS) = 1.0 / p[4];
+        pot_slot(i_slot, S_INV_T2) = 1.0 / (T * T + 1e-100);
+        pot_slot(i_slot, S_T4C) = (T * T * T * T) / (2 * CTB_PI * CTB_PI);
     }
-    __device__ __noinline__ double V(double phi) const // out of line, see PotModel1Line::V
+    static __device__ __noinline__ double V_s(double phi, int i_tab, int i_slot)
     {
+        const TabView t = tab_view(i_tab);
+        const double lam = pot_slot(i_slot, S_LAM), v2 = pot_slot(i_slot, S_V2), nb = pot_slot(i_slot, S_NB);
+        const double inv_rs = pot_slot(i_slot, S_INV_RS), inv_T2 = pot_slot(i_slot, S_INV_T2);
         const double p2 = phi * phi;
-        const double m0 = lam * (3 * p2 - v2), m1 = Y * p2;
+        const double m0 = lam * (3 * p2 - v2), m1 = pot_slot(i_slot, S_Y) * p2;
+        // (the two logarithms and the two table look-ups are branch-free: their instruction streams interleave)
+        const double l0 = log_pos(fabs(m0 * inv_rs) + 1e-100), l1 = log_pos(fabs(m1 * inv_rs) + 1e-100);
+        const double j0 = tab_J(t, m0 * inv_T2), j1 = tab_J(t, m1 * inv_T2);
         double r = .25 * lam * (p2 - v2) * (p2 - v2);
-        double y1 = m0 * m0 * (log(fabs(m0 * inv_rs) + 1e-100) - 1.5);
-        y1 += nb * m1 * m1 * (log(fabs(m1 * inv_rs) + 1e-100) - 1.5);
+        double y1 = m0 * m0 * (l0 - 1.5);
+        y1 += nb * m1 * m1 * (l1 - 1.5);
         r += y1 * (1.0 / (64 * CTB_PI * CTB_PI));
-        const double yt = jtab_eval<0>(jb, m0 * inv_T2) + nb * jtab_eval<0>(jb, m1 * inv_T2);
-        return r + yt * T4c;
+        const double yt = j0 + nb * j1;
+        return r + yt * pot_slot(i_slot, S_T4C);
     }
+    CTB_DEV double V(double phi) const { return V_s(phi, i_tab, i_slot); }
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
 
@@ -305,6 +455,7 @@ struct PotThermal1F {
     static constexpr bool analytic = false;
     static constexpr int min_blocks = CTB_THERMAL_MIN_BLOCKS;
     static constexpr int nparam = CTB_NPARAM_THERMAL1F;
+    static constexpr int nslot = 0;
     const double *p;
     double inv_rs, T2, inv_T2, T4c;
     int nb, nf;
@@ -334,13 +485,13 @@ struct PotThermal1F {
         for (int i = 0; i < nb; i++) { // GP:249-251, 285-286
             const double *q = p + 9 + 5 * i;
             const double m2 = q[0] + q[1] * p2 + q[2] * T2, dof = q[3];
-            y1 += dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - q[4]);
+            y1 += dof * m2 * m2 * (log_pos(fabs(m2 * inv_rs) + 1e-100) - q[4]);
             yt += dof * jtab_eval<0>(jb, m2 * inv_T2);
         }
         for (int j = 0; j < nf; j++) { // GP:252-255, 287-288
             const double *q = p + 49 + 3 * j;
             const double m2 = q[0] + q[1] * p2, dof = q[2];
-            y1 -= dof * m2 * m2 * (log(fabs(m2 * inv_rs) + 1e-100) - 1.5);
+            y1 -= dof * m2 * m2 * (log_pos(fabs(m2 * inv_rs) + 1e-100) - 1.5);
             yt += dof * jtab_eval<0>(jf, m2 * inv_T2);
         }
         o.v1 = y1 * (1.0 / (64 * CTB_PI * CTB_PI));
@@ -354,6 +505,21 @@ struct PotThermal1F {
     }
     CTB_DEV double V_quad(double phi) const { return V(phi); }
 };
+
+// Dynamic shared memory of a kernel that evaluates functor Pot on a staged compact table: the table plus the
+// functor's per-thread parameter slots (blocks of at most CTB_SLOT_STRIDE threads).
+template <class Pot>
+inline size_t pot_smem_bytes(int nint)
+{
+    return Pot::analytic ? 0 : (CTB_TABLE_DOUBLES_COMPACT(nint) + (size_t)Pot::nslot * CTB_SLOT_STRIDE) * sizeof(double);
+}
+// Launch with the opt-in for more than 48 KB of dynamic shared memory where needed.
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args)
+{
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, block, smem, st>>>(args...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers

@@ -192,9 +192,9 @@ template <class Pot>
 int launch_wall_any(const WallArgs &a, cudaStream_t st)
 {
     const unsigned grid = (unsigned)((a.n + 127) / 128);
-    const size_t sm = Pot::analytic ? 0 : CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) * sizeof(double);
-    if (a.out.d_prof_R) wall_kernel<Pot, true><<<grid, 128, sm, st>>>(a);
-    else wall_kernel<Pot, false><<<grid, 128, sm, st>>>(a);
+    const size_t sm = pot_smem_bytes<Pot>(a.jb.nint);
+    if (a.out.d_prof_R) launch_k(wall_kernel<Pot, true>, grid, 128, sm, st, a);
+    else launch_k(wall_kernel<Pot, false>, grid, 128, sm, st, a);
     return (int)cudaGetLastError();
 }
 

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128, 3) bounce_warp_kernel(const BounceArgs a,
     double *stage = ctb_smem;
     if (!Pot::analytic) {
         jb = stage_table_compact(a.jb, ctb_smem);
-        stage = ctb_smem + CTB_TABLE_DOUBLES_COMPACT(a.jb.nint);
+        stage = ctb_smem + CTB_TABLE_DOUBLES_COMPACT(a.jb.nint) + Pot::nslot * CTB_SLOT_STRIDE;
         __syncthreads();
     }
     const int wib = threadIdx.x >> 5;
