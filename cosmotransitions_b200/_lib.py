@@ -11,7 +11,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CTB_LIB") or os.path.join(_PKG, "libctbounce.so")
 
 # keep in sync with include/ctbounce.h
-ABI_VERSION = 11
+ABI_VERSION = 12
 V_TREE, V_ONELOOP, V_THERMAL, V_TOTAL = 1, 2, 4, 7
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 EXACT_X, EXACT_DX, EXACT_THETA = 0, 1, 2
@@ -25,7 +25,9 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
            "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_vtot_thermal1f", "ctb_potential", "ctb_fp64_peak", "ctb_sm_count",
-           "ctb_copy_blocks", "ctb_host_register", "ctb_host_unregister"]
+           "ctb_copy_blocks", "ctb_host_register", "ctb_host_unregister", "ctb_trace_minima"]
+MODEL_MODEL1 = 0
+MIN_OK, MIN_NOT_CONVERGED, MIN_NOT_A_MINIMUM, MIN_JUMPED, MIN_NOT_TRACED = range(5)
 
 
 class JTable(C.Structure):
@@ -44,6 +46,11 @@ class Opts(C.Structure):
 class WallOpts(C.Structure):
     _fields_ = [("Fguess", C.c_double), ("Ftol", C.c_double), ("phitol", C.c_double), ("rmin", C.c_double),
                 ("rmax", C.c_double), ("phi0_rel", C.c_double), ("phi_eps", C.c_double), ("npoints", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class MinOpts(C.Structure):
+    _fields_ = [("x_eps", C.c_double), ("xtol", C.c_double), ("jump_tol", C.c_double), ("max_iter", C.c_int32),
                 ("reserved", C.c_int32)]
 
 
@@ -125,6 +132,10 @@ def load():
     lib.ctb_find_action.argtypes = [C.c_int, C.c_void_p, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
                                     C.c_void_p]
+    lib.ctb_trace_minima.restype = C.c_int
+    lib.ctb_trace_minima.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(MinOpts), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ctb_copy_blocks.restype = C.c_int
     lib.ctb_copy_blocks.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
     lib.ctb_host_register.restype = C.c_int

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libctbounce.so")
 SOURCES = ["ctb_api.cu", "ctb_bounce_poly4.cu", "ctb_bounce_spline.cu", "ctb_bounce_model1_line.cu",
-           "ctb_bounce_model1f.cu", "ctb_bounce_thermal1f.cu"]
+           "ctb_bounce_model1f.cu", "ctb_bounce_thermal1f.cu", "ctb_phases.cu"]
 HEADER = os.path.join(PKG, "..", "include", "ctbounce.h")
 OBJDIR = os.path.join(PKG, "build")
 

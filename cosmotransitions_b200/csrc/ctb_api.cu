@@ -4,8 +4,16 @@
 #include "ctb_device.cuh"
 #include "ctb_bounce.cuh"
 #include "ctb_wall.cuh"
+#include "ctb_phases.cuh"
 
 using namespace ctb;
+
+namespace ctb {
+int launch_trace_minima_model1(const double *d_params, int64_t param_stride, const JTab &jb, const double *d_X0,
+                               const double *d_T, int64_t T_stride, const int32_t *d_t_begin, const int32_t *d_t_dir,
+                               int64_t n, int nT, const MinKnobs &k, double *d_X, double *d_V, int32_t *d_flag,
+                               int32_t *d_iters, cudaStream_t st);
+}
 
 namespace {
 
@@ -316,6 +324,56 @@ __global__ void __launch_bounds__(VG_THREADS) vtot_model1_grid_kernel(Model8 m, 
         }
     } else {
         __syncthreads();
+    }
+}
+
+// The same grid, tiled: a block owns VGT_THREADS consecutive temperatures and a range of field points.  Each THREAD
+// keeps one temperature (1 / T^2 and T^4 / 2 pi^2 are formed once, in registers) and walks down the block's rows; the
+// field-dependent part of a row (three masses, V0 + V1: three logs and a square root) is computed once per block and
+// row and broadcast from shared memory.  Per point that leaves three table look-ups, three multiplies and the
+// coalesced 8-byte store: no index arithmetic, no division.  Used when the grid is at least half a tile wide.
+#define VGT_THREADS 256
+#define VGT_ROWS 32
+__global__ void __launch_bounds__(VGT_THREADS, 4) vtot_model1_grid_tiled_kernel(Model8 m, double x0, double x1, double n0,
+                                                                               double n1, JTab g, const double *__restrict__ s,
+                                                                               int64_t ns, const double *__restrict__ T,
+                                                                               int64_t nT, double *__restrict__ out,
+                                                                               int rows_per_block, int col_tiles)
+{
+    extern __shared__ double smem[];
+    double4 *rowc = reinterpret_cast<double4 *>(smem); // {m0, m1, mb, V0 + V1} per cached row
+    const JTab jb = stage_table(g, smem + VGT_ROWS * 4);
+    const int ct = blockIdx.x % col_tiles, rb = blockIdx.x / col_tiles;
+    const int64_t j = (int64_t)ct * VGT_THREADS + threadIdx.x;
+    const int64_t i0 = (int64_t)rb * rows_per_block;
+    const int64_t i1 = (i0 + rows_per_block < ns) ? i0 + rows_per_block : ns;
+    const bool on = j < nT;
+    double inv_T2 = 0.0, T4c = 0.0;
+    if (on) {
+        const double Tj = T[j], T2 = Tj * Tj;
+        inv_T2 = 1.0 / (T2 + 1e-100);
+        T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
+    }
+    const double inv_rs = 1.0 / m.rs;
+    for (int64_t ib = i0; ib < i1; ib += VGT_ROWS) {
+        const int nrows = (int)((i1 - ib < VGT_ROWS) ? i1 - ib : VGT_ROWS);
+        __syncthreads(); // table staged / previous pass has finished reading the row cache
+        if (threadIdx.x < nrows) {
+            const double si = s[ib + threadIdx.x];
+            const Model1Field f = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, inv_rs, m.v2, x0 + si * n0, x1 + si * n1);
+            rowc[threadIdx.x] = make_double4(f.m0, f.m1, f.mb, f.V01);
+        }
+        __syncthreads();
+        if (on) {
+            double *o = out + ib * nT + j;
+#pragma unroll 2
+            for (int r = 0; r < nrows; r++) {
+                const double4 q = rowc[r];
+                const double yt = jtab_eval<0>(jb, q.x * inv_T2) + jtab_eval<0>(jb, q.y * inv_T2)
+                                  + m.nb * jtab_eval<0>(jb, q.z * inv_T2);
+                __stcs(o + (int64_t)r * nT, q.w + yt * T4c);
+            }
+        }
     }
 }
 
@@ -795,6 +853,20 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     if (ns == 0 || nT == 0) return CTB_OK;
     if (!d_s || !d_T || !d_out) return CTB_ERR_BAD_ARG;
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
+    if (nT >= VGT_THREADS / 2) { // tiled form: one temperature per thread
+        const int64_t col_tiles = (nT + VGT_THREADS - 1) / VGT_THREADS;
+        int64_t row_chunks = ((int64_t)sm_count() * 4 + col_tiles - 1) / col_tiles;
+        if (row_chunks > ns) row_chunks = ns;
+        if (row_chunks < 1) row_chunks = 1;
+        const int64_t rows_per_block = (ns + row_chunks - 1) / row_chunks;
+        row_chunks = (ns + rows_per_block - 1) / rows_per_block;
+        if (col_tiles * row_chunks > 0x7fffffff || rows_per_block > 0x7fffffff) return CTB_ERR_UNSUPPORTED;
+        const size_t tsm = table_bytes(jb) + VGT_ROWS * 4 * sizeof(double);
+        cudaFuncSetAttribute(vtot_model1_grid_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        vtot_model1_grid_tiled_kernel<<<(unsigned)(col_tiles * row_chunks), VGT_THREADS, tsm, (cudaStream_t)stream>>>(
+            m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns, d_T, nT, d_out, (int)rows_per_block, (int)col_tiles);
+        return (int)cudaGetLastError();
+    }
     // persistent grid: 4 blocks per SM unless that would make a block span more than VG_ROWCAP field points
     const int64_t total = ns * nT;
     int64_t nblk = (int64_t)sm_count() * 4;
@@ -930,6 +1002,21 @@ CTB_API int ctb_find_action(int pot_kind, const double *d_params, const ctb_jtab
         return launch_find_action<PotModel1F>(d_params, jb, jf, d_phi_meta, d_R, d_Phi, d_dPhi, stride, d_npts, n, alpha, d_S, st);
     }
     return CTB_ERR_UNSUPPORTED;
+}
+
+CTB_API int ctb_trace_minima(int model_kind, const double *d_params, int64_t param_stride, const ctb_jtable *jb,
+                             const double *d_X0, const double *d_T, int64_t T_stride, const int32_t *d_t_begin,
+                             const int32_t *d_t_dir, int64_t n, int32_t nT, const ctb_min_opts *opts, double *d_X,
+                             double *d_V, int32_t *d_flag, int32_t *d_iters, void *stream)
+{
+    if (n < 0 || nT < 0 || !opts || param_stride < 0 || T_stride < 0) return CTB_ERR_BAD_ARG;
+    if (model_kind != CTB_MODEL_MODEL1) return CTB_ERR_UNSUPPORTED;
+    if (n == 0 || nT == 0) return CTB_OK;
+    if (!d_params || !d_X0 || !d_T || !d_X || !d_flag || !jtab_ok(jb)) return CTB_ERR_BAD_ARG;
+    if (!(opts->x_eps > 0.0) || !(opts->xtol > 0.0) || !(opts->jump_tol > 0.0) || opts->max_iter < 1) return CTB_ERR_BAD_ARG;
+    const MinKnobs k{opts->x_eps, opts->xtol, opts->jump_tol, opts->max_iter};
+    return launch_trace_minima_model1(d_params, param_stride, to_jtab(jb), d_X0, d_T, T_stride, d_t_begin, d_t_dir, n, nT, k,
+                                      d_X, d_V, d_flag, d_iters, (cudaStream_t)stream);
 }
 
 CTB_API int ctb_copy_blocks(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,

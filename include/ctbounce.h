@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CTB_ABI_VERSION 11
+#define CTB_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define CTB_API __attribute__((visibility("default")))
@@ -298,6 +298,38 @@ CTB_API int ctb_potential_batch(int pot_kind, const double *d_params, const ctb_
 CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,
                             const double *d_lo, const double *d_hi, double xtol_rel, int64_t n, double *d_xmin,
                             double *d_vmin, void *stream);
+
+/* ---- batched N-field minimum finder / phase follower -----------------------------------
+ * Replaces one scipy.optimize.fmin call per point and temperature in generic_potential.findMinimum
+ * (generic_potential.py:477-484), transitionFinder.traceMinimum (transitionFinder.py:34-128) and the polish of both
+ * minima before a tunnelling (transitionFinder.py:658-664).  Instance i starts from d_X0[i] at temperature index
+ * d_t_begin[i] (NULL: 0) and walks t += d_t_dir[i] (+1 / -1; NULL: +1) to the end of its temperature row
+ * d_T[i * T_stride + t] (T_stride = 0: one shared grid; nT = 1 and T_stride = 1: findMinimum(X_i, T_i)).  At every
+ * temperature: damped Newton on the reference's 4th-order finite-difference gradient and Hessian of Vtot
+ * (helper_functions.py:446-554 with eps = x_eps), warm-started by extrapolating the previous two minima.  The walk of
+ * an instance ends at the first temperature whose result is not CTB_MIN_OK (that entry holds the point it ended on);
+ * entries never visited are NaN / CTB_MIN_NOT_TRACED.  model_kind: CTB_MODEL_MODEL1 (examples/testModel1.py, two
+ * fields): d_params rows of 8 = l1, l2, mu2, Y1, Y2, n_boson, renormScaleSq, v2, param_stride doubles apart (0: one
+ * row for all instances).  Outputs: d_X [n, nT, ndim], d_V [n, nT] (may be NULL), d_flag [n, nT], d_iters [n] (Newton
+ * iterations, may be NULL).                                                                                         */
+#define CTB_MODEL_MODEL1 0
+#define CTB_MIN_OK 0             /* converged on a point with a positive definite Hessian                          */
+#define CTB_MIN_NOT_CONVERGED 1  /* max_iter iterations (or a non-finite potential)                                 */
+#define CTB_MIN_NOT_A_MINIMUM 2  /* converged on a saddle / maximum (Hessian had to be lifted)                      */
+#define CTB_MIN_JUMPED 3         /* converged farther than jump_tol (|X0| + 1) from the previous minimum: a different
+                                    phase (the traced one has ended, transitionFinder.py:118-126)                  */
+#define CTB_MIN_NOT_TRACED 4     /* not visited                                                                     */
+typedef struct ctb_min_opts {
+    double x_eps;     /* 1e-3: finite-difference step, generic_potential.x_eps (generic_potential.py:104)          */
+    double xtol;      /* 1e-9: converged when the Newton step is below xtol (|X| + 1)                               */
+    double jump_tol;  /* 0.1                                                                                        */
+    int32_t max_iter; /* 60                                                                                         */
+    int32_t reserved;
+} ctb_min_opts;
+CTB_API int ctb_trace_minima(int model_kind, const double *d_params, int64_t param_stride, const ctb_jtable *jb,
+                             const double *d_X0, const double *d_T, int64_t T_stride, const int32_t *d_t_begin,
+                             const int32_t *d_t_dir, int64_t n, int32_t nT, const ctb_min_opts *opts, double *d_X,
+                             double *d_V, int32_t *d_flag, int32_t *d_iters, void *stream);
 
 /* ---- host-side gather plumbing of the multi-GPU partition (no collective on the data path) ----
  * Block-cyclic partition: with blocks of B instances, device r of G owns global blocks r, r + G, r + 2G, ...

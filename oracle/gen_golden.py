@@ -706,6 +706,74 @@ def gen_model1_derivs():
     print({k: np.asarray(v).shape for k, v in out.items()})
 
 
+def gen_phases():
+    """Minima of examples/testModel1.py's Vtot followed in temperature for 10 parameter points (SURVEY s.8f row 1):
+    phase A from approxZeroTMin()[0] at T = 0 upwards until it ends, phase B from the point the minimiser lands on
+    downwards (a phase has ended when the minimiser lands more than 0.3 (|X_start| + 1) away from the previous
+    minimum: the spinodal end moves the minimum by ~0.1 of that per 4 K step, the neighbouring phase is ~1 away) -- each
+    point by the reference's own tool, scipy.optimize.fmin on m.Vtot (generic_potential.py:477-484,
+    transitionFinder.py:127-129, 658-664) with tight tolerances, then polished by Newton steps on the reference's own
+    finite-difference gradV / d2V (generic_potential.py:347-442).  Plus getPhases() of the default model."""
+    from scipy import optimize
+    import testModel1
+    rng = np.random.default_rng(77)
+    base = dict(m1=120., m2=50., mu=25., Y1=.1, Y2=.15, n=30)
+    pts = [dict(base)]
+    for _ in range(9):
+        pts.append({k: (v * rng.uniform(.85, 1.15) if k != "n" else float(int(v * rng.uniform(.85, 1.15)))) for k, v in base.items()})
+    T = np.linspace(0.0, 240.0, 61)
+
+    def tight(m, x, t):
+        x = optimize.fmin(m.Vtot, x, args=(t,), xtol=1e-9, ftol=1e-13, maxiter=4000, maxfun=8000, disp=0)
+        xn = np.array(x, float)
+        for _ in range(4):
+            H = m.d2V(xn, t)
+            if np.linalg.eigvalsh(H)[0] <= 0:
+                break
+            xn = xn - np.linalg.solve(H, m.gradV(xn, t))
+        return np.array(x, float), xn
+
+    model8, XA, XB, XAn, XBn, VA, VB, eA = [], [], [], [], [], [], [], []
+    for kw in pts:
+        m = testModel1.model1(**kw)
+        model8.append([m.l1, m.l2, m.mu2, m.Y1, m.Y2, float(m.n), m.renormScaleSq, testModel1.v2])
+        xa = np.full((len(T), 2), np.nan); xan = xa.copy(); xb = xa.copy(); xbn = xa.copy()
+        x = np.array(m.approxZeroTMin()[0], float)
+        scale = np.linalg.norm(x) + 1.0
+        end = len(T)
+        for k, t in enumerate(T):
+            xf, xn = tight(m, x if k < 2 else 2 * xan[k - 1] - xan[k - 2], t)
+            if k and np.linalg.norm(xn - xan[k - 1]) > 0.3 * scale:
+                xf, xn = tight(m, xan[k - 1], t)     # the extrapolated start may overshoot: retry from the last minimum
+            if k and np.linalg.norm(xn - xan[k - 1]) > 0.3 * scale:
+                end = k
+                xb[k], xbn[k] = xf, xn
+                break
+            xa[k], xan[k] = xf, xn
+            x = xn
+        if end < len(T):
+            for k in range(end - 1, -1, -1):
+                xf, xn = tight(m, xbn[k + 1] if k > end - 3 else 2 * xbn[k + 1] - xbn[k + 2], T[k])
+                H = m.d2V(xn, T[k])
+                if np.linalg.norm(xn - xbn[k + 1]) > 0.3 * (np.linalg.norm(xbn[end]) + 1.0) or np.linalg.eigvalsh(H)[0] <= 0:
+                    break
+                xb[k], xbn[k] = xf, xn
+        XA.append(xa); XAn.append(xan); XB.append(xb); XBn.append(xbn); eA.append(end)
+        with np.errstate(invalid="ignore"):
+            VA.append(np.array([m.Vtot(xan[k], T[k]) if np.isfinite(xan[k, 0]) else np.nan for k in range(len(T))]))
+            VB.append(np.array([m.Vtot(xbn[k], T[k]) if np.isfinite(xbn[k, 0]) else np.nan for k in range(len(T))]))
+        print("phases", kw, "A ends at index", end, "B from", int(np.argmax(np.isfinite(xb[:, 0]))),
+              "max |fmin - newton| A %.2e B %.2e" % (np.nanmax(np.abs(xa - xan)), np.nanmax(np.abs(xb - xbn)) if np.isfinite(xb).any() else 0))
+    out = dict(model8=np.array(model8), T=T, XA_fmin=np.array(XA), XA=np.array(XAn), XB_fmin=np.array(XB), XB=np.array(XBn),
+               VA=np.array(VA), VB=np.array(VB), endA=np.array(eA))
+    # the reference's own phase tracing of the default model (transitionFinder.traceMultiMin through getPhases)
+    m = testModel1.model1()
+    ph = m.getPhases()
+    for key, p in ph.items():
+        out["ref_phase%d_T" % key], out["ref_phase%d_X" % key] = np.array(p.T), np.array(p.X)
+    np.savez(os.path.join(GOLD, "phases.npz"), **out)
+
+
 def gen_alpha14():
     """alpha = 1 and 4 (d = 2 and 5 dimensions, Bessel order nu = 0 and 3/2): quartic family, a few knob sets,
     and exactSolution unit vectors -> tests/golden/alpha14.json"""
@@ -747,7 +815,7 @@ def gen_alpha14():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs"]
+                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs", "phases"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()
