@@ -330,11 +330,91 @@ __global__ void __launch_bounds__(VG_THREADS) vtot_model1_grid_kernel(Model8 m, 
 // The same grid, tiled: a block owns VGT_THREADS consecutive temperatures and a range of field points.  Each THREAD
 // keeps one temperature (1 / T^2 and T^4 / 2 pi^2 are formed once, in registers) and walks down the block's rows; the
 // field-dependent part of a row (three masses, V0 + V1: three logs and a square root) is computed once per block and
-// row and broadcast from shared memory.  Per point that leaves three table look-ups, three multiplies and the
-// coalesced 8-byte store: no index arithmetic, no division.  Used when the grid is at least half a tile wide.
+// row and broadcast from shared memory.
+//
+// INTERVAL TRACKING.  The first tiled version looked every theta = m^2 / T^2 up from scratch (FP32 asinh guess, 48-byte
+// record from shared memory): ncu showed it bound by the shared-memory data pipe -- 12 wavefronts per warp look-up is the
+// floor for delivering 48 B to each of 32 lanes, 5.7e6 wavefronts = 57 % of the run time -- with the XU pipe (sqrt,
+// log, conversions of the guess) second.  But down a column theta moves by ~1e-3 of itself per row while a knot
+// interval is ~1e-2 wide, so a thread KEEPS the record of each of its three look-ups in registers (b0, b1, c0..c3)
+// and re-uses it while theta stays inside [b0, b1): one subtraction and two compares instead of the guess and the
+// loads.  When theta has left the interval the neighbouring record is fetched (predicated loads: only the lanes that
+// moved cost shared-memory wavefronts); only if that is not enough either (first row of a block, a jump) the closed-form
+// guess runs, under a warp-uniform branch.
 #define VGT_THREADS 256
 #define VGT_ROWS 32
-__global__ void __launch_bounds__(VGT_THREADS, 4) vtot_model1_grid_tiled_kernel(Model8 m, double x0, double x1, double n0,
+#ifndef VGT_MIN_BLOCKS
+#define VGT_MIN_BLOCKS 2
+#endif
+struct TrackRec { double b0, b1, c0, c1, c2, c3; int j; };
+
+// Staging for the tracked look-up: nint + 1 records.  The last real record ends just above xmax (so that theta = xmax
+// still evaluates the spline, finiteT.py:173) and is followed by an all-zero record [nextafter(xmax), inf) -- "theta >
+// xmax -> 0" then needs no test of its own.  `smem` 16-byte aligned, (nint + 1) * 6 doubles.
+// Split in two so that the global loads are in flight while the block computes its first row cache: stage_tracked_load
+// reads the records of this thread (4 per thread at 256 threads) into registers, stage_tracked_store writes them out.
+// d_coef must be 16-byte aligned (ctbounce.h asks for 32).
+#define VGT_STAGE_PER_THREAD 4
+struct StageRegs { double b0[VGT_STAGE_PER_THREAD], b1[VGT_STAGE_PER_THREAD]; double2 c01[VGT_STAGE_PER_THREAD], c23[VGT_STAGE_PER_THREAD]; };
+CTB_DEV void stage_tracked_load(const JTab &g, StageRegs &q)
+{
+    const double2 *c2 = reinterpret_cast<const double2 *>(g.coef);
+#pragma unroll
+    for (int u = 0; u < VGT_STAGE_PER_THREAD; u++) {
+        const int j = threadIdx.x + u * VGT_THREADS;
+        if (j < g.nint) {
+            q.b0[u] = __ldg(g.brk + j); q.b1[u] = __ldg(g.brk + j + 1);
+            q.c01[u] = __ldg(c2 + 2 * j); q.c23[u] = __ldg(c2 + 2 * j + 1);
+        }
+    }
+}
+CTB_DEV JTab stage_tracked_store(const JTab &g, const StageRegs &q, double *smem)
+{
+    const double top = __longlong_as_double(__double_as_longlong(g.xmax) + (g.xmax > 0.0 ? 1 : -1)); // nextafter(xmax, inf), xmax != 0
+    double2 *rec = reinterpret_cast<double2 *>(smem);
+#pragma unroll
+    for (int u = 0; u < VGT_STAGE_PER_THREAD; u++) {
+        const int j = threadIdx.x + u * VGT_THREADS;
+        if (j < g.nint) {
+            rec[3 * j] = make_double2(q.b0[u], q.c01[u].x);
+            rec[3 * j + 1] = make_double2(q.c01[u].y, q.c23[u].x);
+            rec[3 * j + 2] = make_double2(q.c23[u].y, (j == g.nint - 1) ? top : q.b1[u]);
+        } else if (j == g.nint) {
+            rec[3 * j] = make_double2(top, 0.0);
+            rec[3 * j + 1] = make_double2(0.0, 0.0);
+            rec[3 * j + 2] = make_double2(0.0, __longlong_as_double(0x7ff0000000000000LL));
+        }
+    }
+    JTab t = g;
+    t.mode = JT_RECORDS;
+    t.i_rec = (int)(smem - ctb_dynsmem);
+    return t;
+}
+
+CTB_DEV void track_load(TrackRec &k, int i_rec, int j)
+{
+    const double2 *r = reinterpret_cast<const double2 *>(ctb_dynsmem + i_rec) + 3 * j;
+    const double2 q0 = r[0], q1 = r[1], q2 = r[2];
+    k.b0 = q0.x; k.c0 = q0.y; k.c1 = q1.x; k.c2 = q1.y; k.c3 = q2.x; k.b1 = q2.y; k.j = j;
+}
+
+// value of the staged piecewise cubic at theta through the tracked record (same arithmetic as jtab_eval<0>)
+CTB_DEV double track_eval(TrackRec &k, int i_rec, int nint, double xmin, float loc_scale, float loc_inv_du, float loc_c,
+                          double theta)
+{
+    const double x = (theta < xmin) ? xmin : theta;
+    if (!(x >= k.b0 && x < k.b1)) {
+        track_load(k, i_rec, min(max(k.j + ((x >= k.b1) ? 1 : -1), 0), nint)); // the neighbouring interval
+        if (!(x >= k.b0 && x < k.b1)) { // far away (first row, a jump, NaN): locate from scratch (one-sided guess)
+            const int j = jtab_guess_f(x, loc_scale, loc_inv_du, loc_c, nint - 1);
+            track_load(k, i_rec, j);
+            if (x >= k.b1) track_load(k, i_rec, j + 1);
+        }
+    }
+    return jtab_poly<0>(__dsub_rn(x, k.b0), k.c0, k.c1, k.c2, k.c3);
+}
+
+__global__ void __launch_bounds__(VGT_THREADS, VGT_MIN_BLOCKS) vtot_model1_grid_tiled_kernel(Model8 m, double x0, double x1, double n0,
                                                                                double n1, JTab g, const double *__restrict__ s,
                                                                                int64_t ns, const double *__restrict__ T,
                                                                                int64_t nT, double *__restrict__ out,
@@ -342,37 +422,44 @@ __global__ void __launch_bounds__(VGT_THREADS, 4) vtot_model1_grid_tiled_kernel(
 {
     extern __shared__ double smem[];
     double4 *rowc = reinterpret_cast<double4 *>(smem); // {m0, m1, mb, V0 + V1} per cached row
-    const JTab jb = stage_table(g, smem + VGT_ROWS * 4);
-    const int ct = blockIdx.x % col_tiles, rb = blockIdx.x / col_tiles;
+    StageRegs sq;
+    stage_tracked_load(g, sq);
+    JTab jb = g;
+    // consecutive block ids go down the rows of one column tile: the block scheduler hands an SM ids k, k + #SM, ... ,
+    // i.e. (when the grid is one wave) one block of EACH column tile -- the tiles differ in cost (share of far look-ups)
+    const int row_chunks = gridDim.x / col_tiles;
+    const int ct = blockIdx.x / row_chunks, rb = blockIdx.x - ct * row_chunks;
     const int64_t j = (int64_t)ct * VGT_THREADS + threadIdx.x;
     const int64_t i0 = (int64_t)rb * rows_per_block;
     const int64_t i1 = (i0 + rows_per_block < ns) ? i0 + rows_per_block : ns;
     const bool on = j < nT;
-    double inv_T2 = 0.0, T4c = 0.0;
-    if (on) {
-        const double Tj = T[j], T2 = Tj * Tj;
-        inv_T2 = 1.0 / (T2 + 1e-100);
-        T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
-    }
+    // columns past the end of the grid follow the last one (nothing is stored)
+    const double Tj = T[on ? j : nT - 1], T2 = Tj * Tj;
+    const double inv_T2 = 1.0 / (T2 + 1e-100);
+    const double T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
     const double inv_rs = 1.0 / m.rs;
+    TrackRec k0, k1, kb;
+    k0.b0 = k1.b0 = kb.b0 = 1.0; k0.b1 = k1.b1 = kb.b1 = 0.0; // empty interval: the first look-up locates from scratch
+    k0.c0 = k0.c1 = k0.c2 = k0.c3 = k1.c0 = k1.c1 = k1.c2 = k1.c3 = kb.c0 = kb.c1 = kb.c2 = kb.c3 = 0.0;
+    k0.j = k1.j = kb.j = 0;
     for (int64_t ib = i0; ib < i1; ib += VGT_ROWS) {
         const int nrows = (int)((i1 - ib < VGT_ROWS) ? i1 - ib : VGT_ROWS);
-        __syncthreads(); // table staged / previous pass has finished reading the row cache
+        if (ib != i0) __syncthreads(); // previous pass has finished reading the row cache
         if (threadIdx.x < nrows) {
             const double si = s[ib + threadIdx.x];
             const Model1Field f = model1_field(m.l1, m.l2, m.mu2, m.Y1, m.Y2, m.nb, inv_rs, m.v2, x0 + si * n0, x1 + si * n1);
             rowc[threadIdx.x] = make_double4(f.m0, f.m1, f.mb, f.V01);
         }
+        if (ib == i0) jb = stage_tracked_store(g, sq, smem + VGT_ROWS * 4);
         __syncthreads();
-        if (on) {
-            double *o = out + ib * nT + j;
-#pragma unroll 2
-            for (int r = 0; r < nrows; r++) {
-                const double4 q = rowc[r];
-                const double yt = jtab_eval<0>(jb, q.x * inv_T2) + jtab_eval<0>(jb, q.y * inv_T2)
-                                  + m.nb * jtab_eval<0>(jb, q.z * inv_T2);
-                __stcs(o + (int64_t)r * nT, q.w + yt * T4c);
-            }
+        double *o = out + ib * nT + (on ? j : 0);
+#pragma unroll 1
+        for (int r = 0; r < nrows; r++) {
+            const double4 q = rowc[r];
+            const double yt = track_eval(k0, jb.i_rec, jb.nint, jb.xmin, jb.loc_scale, jb.loc_inv_du, jb.loc_c, q.x * inv_T2)
+                              + track_eval(k1, jb.i_rec, jb.nint, jb.xmin, jb.loc_scale, jb.loc_inv_du, jb.loc_c, q.y * inv_T2)
+                              + m.nb * track_eval(kb, jb.i_rec, jb.nint, jb.xmin, jb.loc_scale, jb.loc_inv_du, jb.loc_c, q.z * inv_T2);
+            if (on) __stcs(o + (int64_t)r * nT, q.w + yt * T4c);
         }
     }
 }
@@ -853,15 +940,16 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
     if (ns == 0 || nT == 0) return CTB_OK;
     if (!d_s || !d_T || !d_out) return CTB_ERR_BAD_ARG;
     Model8 m{model8[0], model8[1], model8[2], model8[3], model8[4], model8[5], model8[6], model8[7]};
-    if (nT >= VGT_THREADS / 2) { // tiled form: one temperature per thread
+    if (nT >= VGT_THREADS / 2 && jb->loc_inv_du != 0.0 && jb->xmax != 0.0 && ((uintptr_t)jb->d_coef & 15) == 0 &&
+        jb->nint < VGT_STAGE_PER_THREAD * VGT_THREADS) { // tiled form: one temperature per thread
         const int64_t col_tiles = (nT + VGT_THREADS - 1) / VGT_THREADS;
-        int64_t row_chunks = ((int64_t)sm_count() * 4 + col_tiles - 1) / col_tiles;
+        int64_t row_chunks = ((int64_t)sm_count() * VGT_MIN_BLOCKS + col_tiles - 1) / col_tiles;
         if (row_chunks > ns) row_chunks = ns;
         if (row_chunks < 1) row_chunks = 1;
         const int64_t rows_per_block = (ns + row_chunks - 1) / row_chunks;
         row_chunks = (ns + rows_per_block - 1) / rows_per_block;
         if (col_tiles * row_chunks > 0x7fffffff || rows_per_block > 0x7fffffff) return CTB_ERR_UNSUPPORTED;
-        const size_t tsm = table_bytes(jb) + VGT_ROWS * 4 * sizeof(double);
+        const size_t tsm = table_bytes(jb) + (6 + VGT_ROWS * 4) * sizeof(double);
         cudaFuncSetAttribute(vtot_model1_grid_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         vtot_model1_grid_tiled_kernel<<<(unsigned)(col_tiles * row_chunks), VGT_THREADS, tsm, (cudaStream_t)stream>>>(
             m, line4[0], line4[1], line4[2], line4[3], to_jtab(jb), d_s, ns, d_T, nT, d_out, (int)rows_per_block, (int)col_tiles);
