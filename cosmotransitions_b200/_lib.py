@@ -25,7 +25,7 @@ NPARAM = {POT_POLY4: 5, POT_MODEL1_LINE: 13, POT_MODEL1F: 6, POT_SPLINE: 1280, P
 EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_ok", "ctb_bounce_batch",
            "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
            "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_vtot_thermal1f", "ctb_potential", "ctb_fp64_peak", "ctb_sm_count",
-           "ctb_copy_blocks", "ctb_host_register", "ctb_host_unregister", "ctb_trace_minima"]
+           "ctb_copy_blocks", "ctb_host_register", "ctb_host_unregister", "ctb_trace_minima", "ctb_exact_solution"]
 MODEL_MODEL1 = 0
 MIN_OK, MIN_NOT_CONVERGED, MIN_NOT_A_MINIMUM, MIN_JUMPED, MIN_NOT_TRACED = range(5)
 
@@ -40,7 +40,7 @@ class Opts(C.Structure):
     _fields_ = [("xtol", C.c_double), ("phitol", C.c_double), ("thinCutoff", C.c_double), ("rmin", C.c_double),
                 ("rmax", C.c_double), ("phi_eps", C.c_double), ("xguess", C.c_double), ("npoints", C.c_int32),
                 ("max_interior_pts", C.c_int32), ("alpha", C.c_int32), ("block_threads", C.c_int32),
-                ("kernel", C.c_int32), ("reserved", C.c_int32)]
+                ("kernel", C.c_int32), ("reserved", C.c_int32), ("alpha_real", C.c_double)]
 
 
 class WallOpts(C.Structure):
@@ -136,6 +136,8 @@ def load():
     lib.ctb_trace_minima.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(MinOpts), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ctb_exact_solution.restype = C.c_int
+    lib.ctb_exact_solution.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ctb_copy_blocks.restype = C.c_int
     lib.ctb_copy_blocks.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
     lib.ctb_host_register.restype = C.c_int

@@ -1,6 +1,7 @@
 """Batched entry point: SingleFieldInstanton(...).findProfile() + .findAction() for N independent
 instances in one kernel launch (tunneling1D.py:128-791; behaviour spec in SURVEY.md Appendix A)."""
 import math
+import os
 
 import numpy as np
 
@@ -22,19 +23,38 @@ def make_opts(alpha=2, phi_eps=1e-3, block_threads=0, kernel="auto", **knobs):
         if k not in kw:
             raise TypeError("unexpected findProfile argument %r" % k)
         kw[k] = v
-    if alpha not in (1, 2, 3, 4):
-        raise NotImplementedError("alpha must be 1, 2, 3 or 4 (d = alpha + 1 dimensions; Bessel start of order "
-                                  "nu = (alpha - 1)/2 = 0, 1/2, 1, 3/2)")
+    # alpha in {1, 2, 3, 4}: the specialised kernels (closed-form / I0-I1 Bessel start); any other real alpha in
+    # [0, 8]: the general-order start of tunneling1D.py:336-372 (thread kernel, polynomial / tabulated potentials)
+    alpha = float(alpha)
+    if not (0.0 <= alpha <= 8.0):
+        raise ValueError("alpha must be a real number in [0, 8] (d = alpha + 1 dimensions; the general-order Bessel "
+                         "start is validated for nu = (alpha - 1) / 2 <= 7/2)")
     o = _lib.Opts()
     o.xtol, o.phitol, o.thinCutoff, o.rmin, o.rmax = kw["xtol"], kw["phitol"], kw["thinCutoff"], kw["rmin"], kw["rmax"]
     o.phi_eps = phi_eps
     o.xguess = math.nan if kw["xguess"] is None else float(kw["xguess"])
     o.npoints = int(kw["npoints"])
     o.max_interior_pts = -1 if kw["max_interior_pts"] is None else int(kw["max_interior_pts"])
-    o.alpha = int(alpha)
+    o.alpha = int(alpha) if alpha in (1.0, 2.0, 3.0, 4.0) else 0
+    o.alpha_real = alpha
     o.block_threads = int(block_threads)
     o.kernel = _KERNELS[kernel]
     return o
+
+
+def exact_solution_batch(alpha, r, phi0, dV, d2V):
+    """SingleFieldInstanton.exactSolution (tunneling1D.py:294-373) for n argument sets on the device (parity aid for
+    the Bessel start conditions): arrays r, phi0, dV, d2V [n] -> (phi [n], dphi [n]) numpy arrays."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = np.stack([np.asarray(a, dtype=np.float64).reshape(-1) for a in (r, phi0, dV, d2V)], axis=1)
+    d_in = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
+    d_out = torch.empty((rows.shape[0], 2), dtype=torch.float64, device=dev)
+    _lib.check(lib.ctb_exact_solution(float(alpha), d_in.data_ptr(), d_out.data_ptr(), rows.shape[0],
+                                      torch.cuda.current_stream(dev).cuda_stream), "ctb_exact_solution")
+    o = d_out.cpu().numpy()
+    return o[:, 0], o[:, 1]
 
 
 def profile_capacity(opts):

@@ -245,6 +245,18 @@ __global__ void __launch_bounds__(128) jexact_kernel(int mode, const double *__r
     out[i] = y;
 }
 
+// exactSolution for rows of (r, phi0, dV, d2V): parity aid for the Bessel start conditions (T1D:294-373)
+template <int ALPHA>
+__global__ void __launch_bounds__(128) exact_solution_kernel(double alpha, const double *__restrict__ in,
+                                                             double *__restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 e = exact_solution<ALPHA>(in[4 * i], exact_coef(in[4 * i + 1], in[4 * i + 2], in[4 * i + 3], 0.5 * (alpha - 1.0)));
+    out[2 * i] = e.x;
+    out[2 * i + 1] = e.y;
+}
+
 struct Model8 { double l1, l2, mu2, Y1, Y2, nb, rs, v2; };
 
 CTB_DEV double model1_v1t(const Model1Field &f, double nb, const JTab &jb, double inv_T2, double T4c)
@@ -812,12 +824,14 @@ CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_op
     a.knobs.xtol = o->xtol; a.knobs.phitol = o->phitol; a.knobs.thinCutoff = o->thinCutoff; a.knobs.rmin = o->rmin;
     a.knobs.rmax = o->rmax; a.knobs.phi_eps = o->phi_eps; a.knobs.xguess = o->xguess;
     a.knobs.npoints = o->npoints; a.knobs.max_interior_pts = o->max_interior_pts;
+    a.knobs.alpha_real = o->alpha_real;
+    if (o->alpha == 0 && !(o->alpha_real >= 0.0 && o->alpha_real <= 8.0)) return CTB_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     // quartic potential, 64-thread blocks below the throughput regime: finer-grained hand-out of the work-sorted instances (C2: -2 %)
     int block = o->block_threads ? o->block_threads : (pot_kind == CTB_POT_POLY4 && a.n < 300000 ? 64 : 128);
     const int stage_cap = o->npoints + (o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts);
     bool warp = o->kernel == CTB_KERNEL_WARP;
-    if (o->kernel == CTB_KERNEL_AUTO) warp = a.n < 4096 && stage_cap <= 2048;
+    if (o->kernel == CTB_KERNEL_AUTO) warp = a.n < 4096 && stage_cap <= 2048 && o->alpha != 0;
     if (o->kernel < 0 || o->kernel > 2 || (warp && stage_cap > 2048)) return CTB_ERR_UNSUPPORTED;
     if ((pot_kind == CTB_POT_MODEL1_LINE || pot_kind == CTB_POT_MODEL1F) && !jtab_ok(jb)) return CTB_ERR_BAD_ARG;
     if (pot_kind == CTB_POT_THERMAL1F && !(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
@@ -1105,6 +1119,21 @@ CTB_API int ctb_trace_minima(int model_kind, const double *d_params, int64_t par
     const MinKnobs k{opts->x_eps, opts->xtol, opts->jump_tol, opts->max_iter};
     return launch_trace_minima_model1(d_params, param_stride, to_jtab(jb), d_X0, d_T, T_stride, d_t_begin, d_t_dir, n, nT, k,
                                       d_X, d_V, d_flag, d_iters, (cudaStream_t)stream);
+}
+
+CTB_API int ctb_exact_solution(double alpha, const double *d_in, double *d_out, int64_t n, void *stream)
+{
+    if (n < 0 || !(alpha >= 0.0 && alpha <= 64.0)) return CTB_ERR_BAD_ARG;
+    if (n == 0) return CTB_OK;
+    if (!d_in || !d_out) return CTB_ERR_BAD_ARG;
+    const unsigned g = (unsigned)((n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (alpha == 1.0) exact_solution_kernel<1><<<g, 128, 0, st>>>(alpha, d_in, d_out, n);
+    else if (alpha == 2.0) exact_solution_kernel<2><<<g, 128, 0, st>>>(alpha, d_in, d_out, n);
+    else if (alpha == 3.0) exact_solution_kernel<3><<<g, 128, 0, st>>>(alpha, d_in, d_out, n);
+    else if (alpha == 4.0) exact_solution_kernel<4><<<g, 128, 0, st>>>(alpha, d_in, d_out, n);
+    else exact_solution_kernel<CTB_ALPHA_REAL><<<g, 128, 0, st>>>(alpha, d_in, d_out, n);
+    return (int)cudaGetLastError();
 }
 
 CTB_API int ctb_copy_blocks(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,

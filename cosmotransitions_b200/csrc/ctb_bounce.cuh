@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(CTB_MAX_BLOCK, bounce_min_blocks<Pot, MODE, OC
         sink.dPhi = a.out.d_prof_dPhi + i * a.out.prof_stride;
     }
     HandOff h{nullptr, nullptr, nullptr};
-    if (MODE != MODE_FUSED) { h.y00 = a.scratch + i; h.y01 = a.scratch + a.n + i; h.dphi0 = a.scratch + 2 * a.n + i; }
+    // hand-over slots are indexed by the launch-local thread index t (not by the instance): coalesced, and a launch over a
+    // slice of a permutation needs only 3 n doubles of its own
+    if (MODE != MODE_FUSED) { const int64_t ts = valid ? t : 0; h.y00 = a.scratch + ts; h.y01 = a.scratch + a.n + ts; h.dphi0 = a.scratch + 2 * a.n + ts; }
     const double qn = nan("");
     double phi_bar_in = a.phi_bar_in ? a.phi_bar_in[i] : qn, rscale_in = a.rscale_in ? a.rscale_in[i] : qn;
     if (MODE == MODE_SAVE) { // what the shoot kernel left behind (these outputs are mandatory in split mode)
@@ -145,7 +147,8 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
     // split solve (shoot kernel, then save kernel) when the caller provides scratch and all hand-over arrays
     const bool split = a.scratch && !prof && a.out.d_status && a.out.d_r0 && a.out.d_rf && a.out.d_n_shots &&
                        a.out.d_n_rkck && a.out.d_phi_bar && a.out.d_rscale;
-    if (alpha < 1 || alpha > 4) return CTB_ERR_UNSUPPORTED;
+    if (alpha < 0 || alpha > 4) return CTB_ERR_UNSUPPORTED;
+    if (alpha == CTB_ALPHA_REAL && !Pot::analytic) return CTB_ERR_UNSUPPORTED; // real alpha: polynomial / tabulated functors
     if (split && (alpha == 2 || alpha == 3)) {
 #ifdef CTB_FORCE_BIG // tuning builds: -DCTB_FORCE_BIG=0|1 pins the occupancy variant of the shoot kernel
         const bool big = Pot::analytic && CTB_FORCE_BIG;
@@ -162,13 +165,16 @@ int launch_bounce_any(const BounceArgs &a, int alpha, int block, cudaStream_t st
             launch_k(bounce_kernel<Pot, 3, false, MODE_SAVE>, grid, block, sm, st, a);
         }
     } else {
-        // single-kernel form; the only one compiled for alpha = 1 and 4 (d = 2 and 5 dimensions)
+        // single-kernel form; the only one compiled for alpha = 1 and 4 (d = 2 and 5 dimensions) and for real alpha
 #define CTB_LAUNCH_FUSED(AL)                                                                     \
     do {                                                                                         \
         if (prof) launch_k(bounce_kernel<Pot, AL, true, MODE_FUSED>, grid, block, sm, st, a);          \
         else launch_k(bounce_kernel<Pot, AL, false, MODE_FUSED>, grid, block, sm, st, a);              \
     } while (0)
         switch (alpha) {
+        case CTB_ALPHA_REAL:
+            if constexpr (Pot::analytic) CTB_LAUNCH_FUSED(CTB_ALPHA_REAL);
+            break;
         case 1: CTB_LAUNCH_FUSED(1); break;
         case 2: CTB_LAUNCH_FUSED(2); break;
         case 3: CTB_LAUNCH_FUSED(3); break;

@@ -774,6 +774,7 @@ struct SimpsonStream {
 struct Knobs {
     double xtol, phitol, thinCutoff, rmin, rmax, phi_eps, xguess;
     int npoints, max_interior_pts;
+    double alpha_real; // the friction coefficient when the kernel is the ALPHA = CTB_ALPHA_REAL instantiation
 };
 
 struct ProfileSink { // optional Profile1D dump
@@ -782,24 +783,30 @@ struct ProfileSink { // optional Profile1D dump
 
 enum { CT_CONVERGED = 0, CT_UNDERSHOOT = 1, CT_OVERSHOOT = 2 };
 
-// Geometry factors of findAction (T1D:782-790) for d = ALPHA + 1 dimensions, ALPHA in {1, 2, 3, 4}:
-// area of the unit ALPHA-sphere 2 pi^(d/2) / Gamma(d/2), volume of the unit d-ball pi^(d/2) / Gamma(d/2 + 1).
-template <int ALPHA> CTB_DEV double area_fac()
+// Geometry factors of findAction (T1D:782-790) for d = ALPHA + 1 dimensions: area of the unit ALPHA-sphere
+// 2 pi^(d/2) / Gamma(d/2), volume of the unit d-ball pi^(d/2) / Gamma(d/2 + 1).  ALPHA in {1, 2, 3, 4}: constants;
+// ALPHA = CTB_ALPHA_REAL (0): any real alpha >= 0, passed at run time.
+#define CTB_ALPHA_REAL 0
+template <int ALPHA> CTB_DEV double area_fac(double alpha)
 {
+    if (ALPHA == CTB_ALPHA_REAL) return 2.0 * pow(CTB_PI, 0.5 * (alpha + 1.0)) / tgamma(0.5 * (alpha + 1.0));
     return (ALPHA == 1) ? 6.283185307179586 : (ALPHA == 2) ? 12.566370614359172 : (ALPHA == 3) ? 19.739208802178716
                                                                                                : 26.318945069571623;
 }
-template <int ALPHA> CTB_DEV double vol_fac()
+template <int ALPHA> CTB_DEV double vol_fac(double alpha)
 {
+    if (ALPHA == CTB_ALPHA_REAL) return pow(CTB_PI, 0.5 * (alpha + 1.0)) / tgamma(0.5 * (alpha + 1.0) + 1.0);
     return (ALPHA == 1) ? 3.141592653589793 : (ALPHA == 2) ? 4.1887902047863905 : (ALPHA == 3) ? 4.934802200544679
                                                                                                : 5.263789013914325;
 }
-template <int ALPHA> CTB_DEV double pow_alpha(double r) // r^ALPHA
+template <int ALPHA> CTB_DEV double pow_alpha(double r, double alpha) // r^ALPHA
 {
+    if (ALPHA == CTB_ALPHA_REAL) return pow(r, alpha);
     return (ALPHA == 1) ? r : (ALPHA == 2) ? r * r : (ALPHA == 3) ? r * r * r : (r * r) * (r * r);
 }
-template <int ALPHA> CTB_DEV double pow_dim(double r) // r^(ALPHA+1)
+template <int ALPHA> CTB_DEV double pow_dim(double r, double alpha) // r^(ALPHA+1)
 {
+    if (ALPHA == CTB_ALPHA_REAL) return pow(r, alpha + 1.0);
     return (ALPHA == 1) ? r * r : (ALPHA == 2) ? r * r * r : (ALPHA == 3) ? (r * r) * (r * r) : (r * r) * (r * r) * r;
 }
 
@@ -811,10 +818,67 @@ template <int ALPHA> CTB_DEV double pow_dim(double r) // r^(ALPHA+1)
 // to 250 interior points: the caller computes them once, see exact_coef)
 struct ExactCoef {
     double phi0, dv, d2v, beta, ratio;
+    double nu; // (alpha - 1) / 2, read by the ALPHA = CTB_ALPHA_REAL instantiation only
 };
-CTB_DEV ExactCoef exact_coef(double phi0, double dv, double d2v)
+CTB_DEV ExactCoef exact_coef(double phi0, double dv, double d2v, double nu = 0.0)
 {
-    return ExactCoef{phi0, dv, d2v, sqrt(fabs(d2v)), dv / d2v};
+    return ExactCoef{phi0, dv, d2v, sqrt(fabs(d2v)), dv / d2v, nu};
+}
+
+// General order nu >= -1/2 (any real alpha >= 0, T1D:336-372): with Lambda_nu(z) = Gamma(nu+1) (z/2)^-nu I_nu(z) =
+// 0F1(; nu+1; z^2/4) (J_nu: 0F1(; nu+1; -z^2/4)) the reference's expressions are phi - phi0 = (Lambda_nu - 1) V'/V'' and
+// phi' = beta Lambda_nu'(z) V'/V'' with Lambda_nu' = +-z / (2 (nu+1)) Lambda_{nu+1}.  hyp0f1m1(b, z, modified) returns
+// 0F1(; b; +-z^2/4) - 1:
+//   ascending series (all terms positive for I: no cancellation; for J it loses ~e^z eps, so only below z = 12);
+//   I, z >= 25 and z >= 2 nu^2 + 10: Hankel's asymptotic expansion e^z / sqrt(2 pi z) sum (-1)^k a_k(nu) / z^k;
+//   J, z >= 12: sqrt(2 / pi z) (P cos chi - Q sin chi), chi = z - (nu/2 + 1/4) pi.
+// Truncated at the smallest term.  Checked against 50-digit mpmath values for nu in [-1/2, 7/2] (alpha in [0, 8], the
+// range the API accepts): I to 2e-15 relative, J (value and derivative) to 4e-12 absolute.  exp overflow (z > 709) gives
+// inf like scipy's iv.
+CTB_DEV double hyp0f1m1(double b, double z, bool modified)
+{
+    const double nu = b - 1.0;
+    if (modified ? (z < 25.0 || z < 2.0 * nu * nu + 10.0) : (z < 12.0 + 2.0 * fabs(nu))) {
+        const double t = (modified ? 0.25 : -0.25) * z * z;
+        double term = 1.0, sum = 0.0;
+        for (int k = 1; k < 2000; k++) {
+            term *= t / ((double)k * (b + (double)(k - 1)));
+            sum += term;
+            if (fabs(term) <= 1e-17 * fabs(sum) && (double)k > 0.5 * z) break;
+        }
+        return sum;
+    }
+    const double mu = 4.0 * nu * nu;
+    const double pref = tgamma(b) * pow(0.5 * z, -nu); // Gamma(nu+1) (z/2)^-nu
+    if (modified) {
+        double term = 1.0, sum = 1.0, last = 1.0;
+        for (int k = 1; k < 200; k++) {
+            const double q = (double)(2 * k - 1);
+            term *= -(mu - q * q) / ((double)k * 8.0 * z);
+            if (fabs(term) > last) break; // the series is asymptotic: stop at the smallest term
+            sum += term;
+            last = fabs(term);
+            if (last < 1e-18) break;
+        }
+        const double amp = sum * rsqrt(2.0 * CTB_PI * z) * pref;
+        if (z < 700.0) return exp(z) * amp - 1.0;
+        const double e2 = exp(0.5 * z);
+        return (e2 * amp) * e2 - 1.0;
+    }
+    double P = 1.0, Q = 0.0, term = 1.0, last = 1.0;
+    for (int k = 1; k < 200; k++) {
+        const double q = (double)(2 * k - 1);
+        term *= (mu - q * q) / ((double)k * 8.0 * z);
+        if (fabs(term) > last) break;
+        last = fabs(term);
+        // a_k / z^k enters Q for odd k and P for even k, with signs (+ - - + + - - ...) -> (-1)^(k/2)
+        const double sg = ((k >> 1) & 1) ? -1.0 : 1.0;
+        if (k & 1) Q += sg * term; else P += sg * term;
+        if (last < 1e-18) break;
+    }
+    double sn, cs;
+    sincos(z - (0.5 * nu + 0.25) * CTB_PI, &sn, &cs);
+    return sqrt(2.0 / (CTB_PI * z)) * (P * cs - Q * sn) * pref - 1.0;
 }
 
 template <int ALPHA>
@@ -823,6 +887,26 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
     double phi, dphi;
     const double phi0 = c.phi0, dv = c.dv, d2v = c.d2v, beta = c.beta;
     double z = beta * r;
+    if (ALPHA == CTB_ALPHA_REAL) { // any real alpha >= 0: general-order Bessel functions (see hyp0f1m1)
+        const double nu = c.nu;
+        if (z < 1e-2) {
+            const double s = (d2v > 0) ? 1.0 : -1.0;
+            const double g = tgamma(nu + 1.0);
+            const double h2 = (0.5 * z) * (0.5 * z);
+            double p = 0.0, dp = 0.0, hk = 1.0, sk = 1.0;
+            for (int k = 1; k <= 3; k++) {
+                sk *= s;
+                const double q = hk * sk / (tgamma((double)k + 1.0) * tgamma((double)k + 1.0 + nu));
+                p += q; dp += q * (2.0 * k);
+                hk *= h2;
+            }
+            return make_double2(p * (0.25 * g * (r * r) * dv * s) + phi0, dp * (0.25 * g * r * dv * s));
+        }
+        const bool modified = d2v > 0;
+        const double fm1 = hyp0f1m1(nu + 1.0, z, modified);
+        const double fp = (modified ? 0.5 : -0.5) * z / (nu + 1.0) * (hyp0f1m1(nu + 2.0, z, modified) + 1.0);
+        return make_double2(fm1 * c.ratio + phi0, (beta * fp) * c.ratio);
+    }
     if (z < 1e-2) {
         const double s = (d2v > 0) ? 1.0 : -1.0;
         // Gamma(k+1) Gamma(k+1+nu), k = 1..3 ; Gamma(nu+1)
@@ -924,6 +1008,7 @@ struct Sfi {
     Pot pot;
     double phi_abs, phi_meta, phi_eps, inv_12eps;
     double friction; // used by ALPHA == CTB_ALPHA_WALL only
+    double alpha_rt; // used by ALPHA == CTB_ALPHA_REAL only: the real friction coefficient alpha
     double inv_r_end; // 1 / (t + dt) of the last Cash-Karp attempt
     int n_rkck;
     CTB_DEV void set_phi_eps(double e) { phi_eps = e; inv_12eps = 1.0 / (12. * e); }
@@ -1047,7 +1132,7 @@ struct Sfi {
     CTB_DEV int initial_conditions(double delta_phi0, double dv, double d2v, double rmin, double cutoff, double &r0,
                                    double &phi_r0, double &dphi_r0) const
     {
-        const ExactCoef ec = exact_coef(phi_abs + delta_phi0, dv, d2v);
+        const ExactCoef ec = exact_coef(phi_abs + delta_phi0, dv, d2v, ALPHA == CTB_ALPHA_REAL ? 0.5 * (alpha_rt - 1.0) : 0.0);
         double2 e = exact_solution<ALPHA>(rmin, ec);
         phi_r0 = e.x; dphi_r0 = e.y;
         r0 = rmin;
@@ -1103,7 +1188,7 @@ struct Sfi {
     {
         f0 = y1;
         if constexpr (ALPHA == CTB_ALPHA_WALL) f1 = fma(-friction, y1, dV(y0)); // T1D:912-916
-        else f1 = fma(-CTB_MUL((double)ALPHA, y1), inv_r, dV(y0));
+        else f1 = fma(-CTB_MUL(ALPHA == CTB_ALPHA_REAL ? alpha_rt : (double)ALPHA, y1), inv_r, dV(y0));
     }
 
     // HF:204-236 Cash-Karp step
@@ -1297,6 +1382,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
         valid = valid && (status_in == CTB_ST_CONVERGED || status_in == CTB_ST_XTOL);
     }
     s.phi_eps = 0.0; s.inv_12eps = 0.0;
+    s.alpha_rt = (ALPHA == CTB_ALPHA_REAL) ? k.alpha_real : (double)ALPHA;
     const double phi_abs = s.phi_abs, phi_meta = s.phi_meta;
     const Pot &pot = s.pot;
     int phase = valid ? (MODE == MODE_SAVE ? PH_WAIT : PH_SHOOT) : PH_DONE;
@@ -1329,7 +1415,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
     const double inv_ea0 = 1.0 / ea0, inv_ea1 = 1.0 / ea1;
     const double cutoff = k.thinCutoff * delta_phi;
     const int npoints = k.npoints;
-    const double afac = area_fac<ALPHA>(), vfac = vol_fac<ALPHA>();
+    const double afac = area_fac<ALPHA>(s.alpha_rt), vfac = vol_fac<ALPHA>(s.alpha_rt);
 
     bool have_rf = false;
     double rf = qnan, r0 = qnan, y00 = qnan, y01 = qnan, delta_phi0 = qnan, dv0 = qnan, d2v0 = qnan;
@@ -1347,7 +1433,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
 
     int g_dense = 0, g0 = 0; // global index of the next dense-output point; start of the uniform Simpson part
     auto emit = [&](double r, double phi, double dphi, bool dense) {
-        double ra = pow_alpha<ALPHA>(r);
+        double ra = pow_alpha<ALPHA>(r, s.alpha_rt);
         double integrand = (0.5 * (dphi * dphi) + pot.V_quad(phi) - V_meta) * (ra * afac);
         if (dense && simp.uniform_on) simp.feed_uniform(integrand, g_dense & 1);
         else {
@@ -1407,7 +1493,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
             R_first = (nint > 0) ? 0.0 : r0;
             Phi_first = (nint > 0) ? phi_c : y00;
             if (nint > 0) {
-                const ExactCoef ec = exact_coef(phi_c, dv0, d2v0);
+                const ExactCoef ec = exact_coef(phi_c, dv0, d2v0, 0.5 * (s.alpha_rt - 1.0));
                 emit(0.0, phi_c, 0.0, false);
                 for (int i = 1; i < nint; i++) {
                     double ri;
@@ -1499,7 +1585,7 @@ __device__ void solve_instance(Sfi<Pot, ALPHA> &s, const Knobs &k, bool valid, d
                 const double x_m2 = (npoints >= 3) ? __dadd_rn(__dmul_rn((double)(npoints - 3), step), r0) : r0;
                 const double x_m1 = (npoints >= 2) ? __dadd_rn(__dmul_rn((double)(npoints - 2), step), r0) : r0;
                 double S = simp.finish(N, step, x_m2, x_m1, rf);
-                double Rd = pow_dim<ALPHA>(R_first);
+                double Rd = pow_dim<ALPHA>(R_first, s.alpha_rt);
                 S += (Rd * vfac) * (pot.V_quad(Phi_first) - V_meta);
                 res.S = S;
                 res.status = status;

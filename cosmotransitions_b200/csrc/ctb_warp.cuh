@@ -195,7 +195,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
     // ---- save pass, lane-parallel: T1D:729-791 ----
     res.r0 = r0; res.rf = rf;
     res.phi0 = phi_abs + delta_phi0;
-    const double afac = area_fac<ALPHA>(), vfac = vol_fac<ALPHA>();
+    const double afac = area_fac<ALPHA>(0.0), vfac = vol_fac<ALPHA>(0.0);
     const double step = (rf - r0) / (npoints - 1);
     const double Rl1 = (npoints == 2) ? rf : __dadd_rn(__dmul_rn(1.0, step), r0);
     int nint = 0;
@@ -210,7 +210,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
     res.n_points = N;
     const double phi_c = phi_abs + delta_phi0;
     auto put = [&](int slot, double r, double phi, double dphi) {
-        const double ra = pow_alpha<ALPHA>(r);
+        const double ra = pow_alpha<ALPHA>(r, 0.0);
         stage_r[slot] = r;
         stage_y[slot] = (0.5 * (dphi * dphi) + pot.V_quad(phi) - V_meta) * (ra * afac);
         if (PROFILE) { sink.R[slot] = r; sink.Phi[slot] = phi; sink.dPhi[slot] = dphi; }
@@ -297,7 +297,7 @@ __device__ void solve_instance_warp(Sfi<Pot, ALPHA> &s, const Knobs &k, double p
         }
     }
     const double R_first = (nint > 0) ? 0.0 : r0, Phi_first = (nint > 0) ? phi_c : y00;
-    const double Rd = pow_dim<ALPHA>(R_first);
+    const double Rd = pow_dim<ALPHA>(R_first, 0.0);
     S += (Rd * vfac) * (pot.V_quad(Phi_first) - V_meta);
     res.S = S;
     res.n_rkck = s.n_rkck;

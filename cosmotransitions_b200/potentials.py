@@ -90,6 +90,58 @@ class SplinePotential(DevicePotential):
         return cls(tck) if tck is not None else None
 
 
+class SampledPotential(SplinePotential):
+    """Arbitrary Python callables V (and dV) as a device functor: what the reference accepts as
+    SingleFieldInstanton(phi_absMin, phi_metaMin, V, dV, d2V) (tunneling1D.py:112-149) and what
+    pathDeformation.fullTunneling passes when V_spline_samples is None (raw path.V, path.dV, pathDeformation.py:
+    959-964).  A Python function cannot run inside a CUDA kernel, so it is SAMPLED ONCE on the host -- `pieces` + 1
+    equidistant points covering [phi_lo, phi_hi] -- and handed to the tabulated functor (CTB_POT_SPLINE) as a piecewise
+    cubic: the Hermite interpolant of (V, dV) when dV is given (C1, exact V and dV at the knots, error
+    h^4 max|d4V| / 384 between them), otherwise scipy's not-a-knot C2 spline of the V samples.  V, dV and d2V inside
+    the solver are that cubic and its derivatives: SPLINE-ACCURATE, NOT TRAJECTORY-EXACT -- the action converges like
+    pieces^-4, but step and shot counts may differ from a run on the callable itself.  The integration itself
+    (everything after the sampling) runs on the GPU."""
+
+    def __init__(self, V, phi_lo, phi_hi, dV=None, pieces=None):
+        from scipy import interpolate
+        pieces = _lib.SPLINE_MAX_PIECES if pieces is None else int(pieces)
+        if not (4 <= pieces <= _lib.SPLINE_MAX_PIECES):
+            raise ValueError("pieces must be in [4, %d]" % _lib.SPLINE_MAX_PIECES)
+        x = np.linspace(float(phi_lo), float(phi_hi), pieces + 1)
+
+        def sample(f):
+            try:
+                y = np.asarray(f(x), dtype=np.float64)
+                if y.shape == x.shape:
+                    return y
+            except Exception:
+                pass
+            return np.array([float(f(xi)) for xi in x], dtype=np.float64)
+
+        v = sample(V)
+        if not np.isfinite(v).all():
+            raise ValueError("V is not finite on [%g, %g]" % (phi_lo, phi_hi))
+        pp = (interpolate.CubicHermiteSpline(x, v, sample(dV)) if dV is not None
+              else interpolate.CubicSpline(x, v, bc_type="not-a-knot"))
+        row = np.zeros(_lib.NPARAM[self.kind])
+        row[0] = pieces
+        row[1:1 + pieces + 1] = pp.x
+        off = 1 + _lib.SPLINE_MAX_PIECES + 1
+        row[off:off + 4 * pieces] = pp.c[::-1, :].T.reshape(-1)      # c0..c3 per piece (PPoly stores descending powers)
+        self.tck = None
+        self.pieces = pieces
+        DevicePotential.__init__(self, row)
+
+    @classmethod
+    def for_instanton(cls, V, dV, phi_absMin, phi_metaMin, pieces=None, pad=0.05):
+        """Sampling window of a bounce between the two minima: the interval between them plus `pad` of its length on
+        either side (the 5-point stencils and an overshooting trajectory step slightly past the ends; farther out the
+        end pieces extrapolate)."""
+        lo, hi = min(phi_absMin, phi_metaMin), max(phi_absMin, phi_metaMin)
+        d = hi - lo
+        return cls(V, lo - pad * d, hi + pad * d, dV=dV, pieces=pieces)
+
+
 def thermal1f_params(V0_coefs, renormScaleSq, T, bosons=(), fermions=()):
     """Rows of CTB_POT_THERMAL1F (include/ctbounce.h): a one-field generic_potential with
     V0 = sum_k V0_coefs[k] phi^k (k <= 4), bosons = [(a, b, t, dof, c), ...] with m^2 = a + b phi^2 + t T^2,

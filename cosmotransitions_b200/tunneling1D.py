@@ -7,10 +7,14 @@ exceptions (PotentialError(msg, kind) with kind in {"no barrier", "stable, not m
 helper_functions.IntegrationError), so it can be handed to pathDeformation.fullTunneling as
 `tunneling_class=` (pathDeformation.py:849,959-968) for potentials the device knows.
 
-The one difference: V must be a device functor (cosmotransitions_b200.potentials.DevicePotential),
-not an arbitrary Python callable -- arbitrary callables cannot run inside a CUDA kernel and there is
-no CPU fallback.  dV / d2V are taken from the functor (analytic where it has them, otherwise the
-reference's own 5-point stencils, tunneling1D.py:151-161,191-201, evaluated on the device).
+V is a device functor (cosmotransitions_b200.potentials.DevicePotential): dV / d2V are then taken from the
+functor (analytic where it has them, otherwise the reference's own 5-point stencils, tunneling1D.py:151-161,191-201,
+evaluated on the device) and the solve is trajectory-faithful to the reference.  Plain Python callables -- which the
+reference accepts, tunneling1D.py:112-149 -- cannot run inside a CUDA kernel and there is no CPU fallback for the
+integration: they are sampled once onto the tabulated functor (potentials.SampledPotential: `V_spline_pieces`
+cubic pieces between the two minima, Hermite data from dV when it is given) and the solve runs on the GPU on that
+table -- spline-accurate (S converges like pieces^-4), not trajectory-exact.  SplinePath.V / .dV / .d2V of the
+reference's path deformation are recognised and use the path's own spline exactly.
 """
 from collections import namedtuple
 
@@ -47,6 +51,18 @@ _ERRORS = {
 }
 
 
+def _as_device_potential(V, dV, phi_absMin, phi_metaMin, pieces):
+    """DevicePotential as is; SplinePath.V of the reference (pathDeformation.py:959-964: V, dV, d2V are splev() of one
+    cubic spline) -> that spline, exactly; any other callable -> sampled (potentials.SampledPotential)."""
+    if isinstance(V, DevicePotential):
+        return V
+    from .potentials import SampledPotential, SplinePotential
+    if not callable(V):
+        raise TypeError("V must be a DevicePotential or a callable")
+    return SplinePotential.from_callable(V) or SampledPotential.for_instanton(V, dV, float(phi_absMin), float(phi_metaMin),
+                                                                             pieces=pieces)
+
+
 def raise_for_status(status):
     """Maps a per-instance status code to the exception the reference raises at that point."""
     status = int(status)
@@ -62,15 +78,8 @@ class SingleFieldInstanton:
     profile_rval = namedtuple("Profile1D", "R Phi dPhi Rerr")
 
     def __init__(self, phi_absMin, phi_metaMin, V, dV=None, d2V=None, phi_eps=1e-3, alpha=2, phi_bar=None,
-                 rscale=None):
-        if not isinstance(V, DevicePotential):
-            # pathDeformation.fullTunneling passes path.V, path.dV, path.d2V of a SplinePath
-            # (pathDeformation.py:959-964): all three are splev() of one cubic spline -> tabulated functor
-            from .potentials import SplinePotential
-            V = SplinePotential.from_callable(V) or V
-        if not isinstance(V, DevicePotential):
-            raise TypeError("V must be a cosmotransitions_b200.potentials.DevicePotential (device functor); "
-                            "arbitrary Python callables cannot run on the GPU and there is no CPU fallback")
+                 rscale=None, V_spline_pieces=None):
+        V = _as_device_potential(V, dV, phi_absMin, phi_metaMin, V_spline_pieces)
         self.phi_absMin, self.phi_metaMin = float(phi_absMin), float(phi_metaMin)
         self.V = V
         self.alpha = alpha
@@ -142,13 +151,8 @@ class WallWithConstFriction(SingleFieldInstanton):
     profile_rval = namedtuple("Profile1D", "R Phi dPhi F Rerr")
 
     def __init__(self, phi_absMin, phi_metaMin, V, dV=None, d2V=None, phi_eps=1e-3, alpha=2, phi_bar=None,
-                 rscale=None):
-        if not isinstance(V, DevicePotential):
-            from .potentials import SplinePotential
-            V = SplinePotential.from_callable(V) or V
-        if not isinstance(V, DevicePotential):
-            raise TypeError("V must be a cosmotransitions_b200.potentials.DevicePotential (device functor); "
-                            "arbitrary Python callables cannot run on the GPU and there is no CPU fallback")
+                 rscale=None, V_spline_pieces=None):
+        V = _as_device_potential(V, dV, phi_absMin, phi_metaMin, V_spline_pieces)
         if phi_bar is not None or rscale is not None:
             raise NotImplementedError("phi_bar / rscale overrides are not wired for WallWithConstFriction")
         self.phi_absMin, self.phi_metaMin = float(phi_absMin), float(phi_metaMin)

@@ -39,7 +39,7 @@ extern "C" {
 /* ---- return codes --------------------------------------------------------------------------- */
 #define CTB_OK 0
 #define CTB_ERR_BAD_ARG (-1)      /* NULL pointer, n < 0, bad enum ...                       */
-#define CTB_ERR_UNSUPPORTED (-2)  /* alpha not in 1..4, npoints out of range, unknown kind     */
+#define CTB_ERR_UNSUPPORTED (-2)  /* alpha out of range, npoints out of range, unknown kind    */
 #define CTB_ERR_NO_DEVICE (-3)    /* no CUDA device / not an sm_100 device                   */
 
 /* ---- per-instance status (int32) ------------------------------------------------------------ */
@@ -126,10 +126,13 @@ typedef struct ctb_opts {
     double xguess;            /* NaN = None */
     int32_t npoints;          /* 500; 2 <= npoints <= 4096 */
     int32_t max_interior_pts; /* -1 = None (npoints/2) */
-    int32_t alpha;            /* 1..4: d = alpha + 1 dimensions; 2 = O(3) finite T, 3 = O(4) zero T */
+    int32_t alpha;            /* 1..4: d = alpha + 1 dimensions; 2 = O(3) finite T, 3 = O(4) zero T;
+                                 0 = the real value in alpha_real (general-order Bessel start, tunneling1D.py:336-372;
+                                 thread-per-instance kernel, CTB_POT_POLY4 / CTB_POT_SPLINE functors)               */
     int32_t block_threads;    /* 0 = library default (thread-per-instance kernel only) */
     int32_t kernel;           /* CTB_KERNEL_AUTO / _THREAD / _WARP, see below */
     int32_t reserved;
+    double alpha_real;        /* used when alpha == 0: any real 0 <= alpha <= 8 (Bessel order nu = (alpha-1)/2 <= 7/2) */
 } ctb_opts;
 
 /* Two kernels implement the same solve (identical shooting sequence and results up to the summation
@@ -282,6 +285,11 @@ CTB_API int ctb_vtot_model1_grid(const double *model8, const double *line4, cons
  * constant of V1T (generic_potential.py:289-295; 0 when include_radiation is off or the totals are None).         */
 CTB_API int ctb_vtot_thermal1f(const double *model64, double rad, const ctb_jtable *jb, const ctb_jtable *jf,
                                const double *d_phi, const double *d_T, double *d_out, int64_t n, int parts, void *stream);
+
+/* SingleFieldInstanton.exactSolution(r, phi0, dV, d2V) (tunneling1D.py:294-373) for n argument rows (parity aid):
+ * d_in [n, 4] = r, phi0, dV, d2V  ->  d_out [n, 2] = phi(r), phi'(r).  alpha: 1, 2, 3, 4 evaluate the specialised forms
+ * the bounce kernels use (closed forms, I0 / I1 / J0 / J1); any other real alpha in [0, 8] the general-order form. */
+CTB_API int ctb_exact_solution(double alpha, const double *d_in, double *d_out, int64_t n, void *stream);
 
 /* Potential functor evaluation V(phi_j) for one parameter row (debug / parity aid). */
 CTB_API int ctb_potential(int pot_kind, const double *d_params, const ctb_jtable *jb, const ctb_jtable *jf,

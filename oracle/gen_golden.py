@@ -812,10 +812,41 @@ def gen_alpha14():
         print("alpha14", c_["alpha"], c_["c"], c_["opts"], {q: c_.get(q) for q in ("S", "npts", "n_shots", "error")})
 
 
+def gen_alpha_real():
+    """Real-valued alpha (d = alpha + 1 dimensions, any real alpha >= 0): the reference's general-order Bessel start
+    conditions (tunneling1D.py:336-372, scipy.special.iv / jv / gamma) -- exactSolution on random arguments, and full
+    bounces of the quartic family."""
+    alphas = [0.0, 0.5, 1.5, 2.5, 3.3, 5.0, 7.25]
+    cases = []
+    for alpha in alphas:
+        for c in (0.05, 0.2, 0.35, 0.47):
+            V, dV, d2V = quartic_lambdas(c)
+            r = run_case(V, dV, d2V, 1.0, 0.0, alpha)
+            r.update(kind="quartic", c=float(c), alpha=alpha, coef=[0, 0, c / 2, -(1 + c) / 3, 0.25], phi_abs=1.0,
+                     phi_meta=0.0, opts={})
+            cases.append(r)
+            print("alpha_real", alpha, c, {q: r.get(q) for q in ("S", "npts", "n_shots", "n_rkck", "error")})
+    rng = np.random.default_rng(1414)
+    rows, vals = [], []
+    for alpha in alphas + [1.0, 2.0, 3.0, 4.0]:
+        o = t1.SingleFieldInstanton(1.0, 0.0, *quartic_lambdas(0.3), alpha=alpha)
+        for k in range(300):
+            r = 10 ** rng.uniform(-5, 2.7)
+            phi0 = rng.uniform(-2, 2)
+            dV = rng.normal() * 10 ** rng.uniform(-20, 1)
+            d2V = rng.normal() * 10 ** rng.uniform(-3, 1)
+            with np.errstate(all="ignore"):
+                ph, dph = o.exactSolution(r, phi0, dV, d2V)
+            rows.append([alpha, r, phi0, dV, d2V])
+            vals.append([float(ph), float(dph)])
+    with open(os.path.join(GOLD, "alpha_real.json"), "w") as f:
+        json.dump(dict(cases=cases, exact_in=rows, exact_out=vals), f, indent=0)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs", "phases"]
+                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs", "phases", "alpha_real"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()

@@ -149,3 +149,17 @@ def test_thermal_functions_vs_live_reference(ref):
     T = rng.uniform(0, 250, 3000)
     v_ref, v_gpu = m_ref.Vtot(X, T), m_gpu.Vtot(X, T)
     assert np.max(np.abs(v_gpu - v_ref) / np.maximum(1.0, np.abs(v_ref))) < 1e-11
+
+
+def test_full_tunneling_without_path_spline(ref):
+    """pathDeformation.fullTunneling(..., V_spline_samples=None) hands the tunneling class the raw path.V / path.dV
+    callables instead of a spline (pathDeformation.py:959-964); the GPU class samples them onto its tabulated functor.
+    The action agrees with the reference's own run of the same branch to the accuracy of that table."""
+    from cosmoTransitions.examples import fullTunneling as ft
+    from cosmotransitions_b200.tunneling1D import SingleFieldInstanton as GpuSFI
+    pd = ref["pd"]
+    m = ft.Potential(c=5., fx=0., fy=2.)
+    Yref = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV, V_spline_samples=None)
+    Y = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV, V_spline_samples=None, tunneling_class=GpuSFI)
+    assert abs(Y.action - Yref.action) < 2e-5 * Yref.action, (Y.action, Yref.action)
+    assert abs(Yref.action - 1766.9) < 0.5

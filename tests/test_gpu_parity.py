@@ -221,9 +221,48 @@ def test_scalar_api_errors(ctb):
         t1.SingleFieldInstanton(1.0, 0.0, potentials.Poly4Potential(0, 0, -0.1, -0.8 / 3, 0.25))
     assert e.value.args[1] == "no barrier"
     with pytest.raises(TypeError):
+        t1.SingleFieldInstanton(1.0, 0.0, 3.0)                       # neither a functor nor a callable
+    with pytest.raises(t1.PotentialError) as e:                     # a callable goes through the sampled functor
         t1.SingleFieldInstanton(1.0, 0.0, lambda x: x ** 2)
+    assert e.value.args[1] == "stable, not metastable"
     with pytest.raises(ValueError):   # the reference's brentq ValueError zone
         t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(0.499)).findProfile()
+
+
+def test_python_callables_are_sampled_onto_the_device(ctb, gold_dir):
+    """SingleFieldInstanton(phi_absMin, phi_metaMin, V, dV) with plain Python callables (the reference's own docstring
+    example, tunneling1D.py:112-122): sampled once onto the tabulated functor, solved on the GPU.  Spline-accurate: S
+    converges to the value of the exact quartic as the table is refined (measured: 3e-6 relative for the thickest walls
+    at the maximum of 255 pieces, where the piecewise d2V of the cubic matters most; 1e-7 and below for thin walls)."""
+    from cosmotransitions_b200 import potentials, tunneling1D as t1
+    fam = [c for c in json.load(open(os.path.join(gold_dir, "quartic.json")))
+           if c.get("kind") == "family" and c["alpha"] == 2 and not c["error"] and not c["opts"]]
+    done = 0
+    for g in fam[::max(1, len(fam) // 6)]:
+        c = g["c"]
+        done += 1
+        V = lambda p, c=c: .25 * p ** 4 - (1 + c) / 3 * p ** 3 + c / 2 * p ** 2
+        dV = lambda p, c=c: p * (p - c) * (p - 1.0)
+        # (i) the table converges to the potential like pieces^-4: with the solver's own tolerances tightened (at the
+        # defaults the bisection in phi(0) stops within xtol = 1e-4 of the bounce, and WHERE it stops -- hence S at the
+        # 1e-5 level -- depends on the last bits of V), S of the sampled potential approaches S of the exact quartic
+        tight = dict(xtol=1e-9, phitol=1e-9)
+        exact = t1.SingleFieldInstanton(1.0, 0.0, potentials.QuarticPotential(c))
+        S_exact = exact.findAction(exact.findProfile(**tight))
+        errs = []
+        for pieces in (16, 32, 64, 128, 255):
+            inst = t1.SingleFieldInstanton(1.0, 0.0, V, dV, V_spline_pieces=pieces)
+            assert isinstance(inst.V, potentials.SampledPotential)
+            errs.append(abs(inst.findAction(inst.findProfile(**tight)) - S_exact) / S_exact)
+        print("sampled callable, c = %.4f: rel. error of S for 16..255 pieces:" % c, ["%.1e" % e for e in errs])
+        assert max(errs[-2:]) < 1e-5 and errs[0] > 10 * max(errs[-2:]), (c, errs)
+        # (ii) at the default tolerances: inside the solver's own xtol band around the reference's value
+        inst = t1.SingleFieldInstanton(1.0, 0.0, V, dV)
+        assert abs(inst.findAction(inst.findProfile()) - g["S"]) < 2e-4 * g["S"]
+        # without dV: not-a-knot spline of the V samples alone; scalar (non-vectorised) callables work too
+        inst = t1.SingleFieldInstanton(1.0, 0.0, lambda p, c=c: float(V(float(p))))
+        assert abs(inst.findAction(inst.findProfile(**tight)) - S_exact) < 1e-5 * S_exact
+    assert done >= 3
 
 
 @pytest.mark.parametrize("alpha", [1, 2, 3, 4])

@@ -27,7 +27,7 @@ def test_struct_layout_matches_header():
     import ctypes as C
     from cosmotransitions_b200 import _lib
     assert C.sizeof(_lib.JTable) == 64
-    assert C.sizeof(_lib.Opts) == 7 * 8 + 6 * 4
+    assert C.sizeof(_lib.Opts) == 7 * 8 + 6 * 4 + 8
     assert C.sizeof(_lib.BounceOut) == 15 * 8
     assert C.sizeof(_lib.BounceIn) == 8 * 8
 
@@ -107,9 +107,13 @@ def test_opts_marshalling_and_defaults():
     assert batch.profile_capacity(o) == 200 and o.xguess == 2.5
     with pytest.raises(TypeError):
         batch.make_opts(bogus=1)
-    with pytest.raises(NotImplementedError):
-        batch.make_opts(alpha=5)
+    # integer alpha 1..4: the specialised kernels; any other real alpha in [0, 8]: alpha = 0 + alpha_real
     assert batch.make_opts(alpha=1).alpha == 1 and batch.make_opts(alpha=4).alpha == 4
+    o = batch.make_opts(alpha=2.5)
+    assert o.alpha == 0 and o.alpha_real == 2.5 and batch.make_opts(alpha=5).alpha == 0
+    for bad in (-0.5, 8.5, float("nan")):
+        with pytest.raises(ValueError):
+            batch.make_opts(alpha=bad)
 
 
 def test_partition_roundtrip():
