@@ -41,6 +41,10 @@ WORKLOADS = {
     "c5": dict(n=256000, alpha=2, name="C5 (one GPU's share): 1000 parameter points x 256 temperatures of the one-field "
                                        "thermal model, bounded minimiser + finite-T bounce per (point, T)",
                flop_per_bounce=1.8e6),
+    "c5m": dict(n=10000 * 256, alpha=2, name="C5 on the two-field model (examples/testModel1.py): 10000 parameter points x "
+                                             "256 temperatures, both phases followed on the device (ctb_trace_minima), "
+                                             "then one bounce along the straight line between the minima wherever the "
+                                             "high-T phase is metastable", flop_per_bounce=1.8e6),
     "c4": dict(n=4096 * 1024, alpha=2, name="C4: model1 Vtot on a 4096 x 1024 (phi, T) grid + 512-temperature bounce "
                                             "scan along the line between the phases"),
 }
@@ -728,6 +732,86 @@ def run_c5(args, wl, e, mode):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# workload c5m: BASELINE.json configs[4] on the real two-field model1 -- phase following + straight-line bounces
+
+def run_c5m(args, wl, e, mode):
+    torch, _lib = e.torch, e._lib
+    from cosmotransitions_b200 import phases, potentials
+    P_all, nT = 10000, 256
+    rng = np.random.default_rng(20260102)
+    jit = rng.uniform(.9, 1.1, (P_all, 5))
+    rows = np.stack([potentials.model1_model8(120. * a, 50. * b, 25. * c, .1 * d, .15 * f) for a, b, c, d, f in jit])
+    sel = np.arange(e.rank, P_all, e.world)
+    m8 = torch.as_tensor(rows[sel], dtype=torch.float64, device=e.dev).contiguous()
+    P = m8.shape[0]
+    T = torch.linspace(40.0, 135.0, nT, dtype=torch.float64, device=e.dev)
+    res = {}
+
+    def step():
+        res["r"] = phases.model1_phase_scan(m8, T)
+
+    sampler = ClockSampler(e.local)
+    sampler.start()
+    t_load0 = time.perf_counter()
+    kern_ms, t_wall = timed_device_loop(e, args, step, sampler, t_load0)
+    total_ms = e.max_over_ranks(sum(kern_ms))
+    r = res["r"]
+    nb = r["n_bounces"]
+    st = r["status"].cpu().numpy()
+    solved = int(((st == 0) | (st == 1)).sum())
+    # e2e: pinned host parameter rows in, S / status / Tnuc out
+    m8_h = m8.cpu().pin_memory()
+    S_h = torch.empty((P, nT), dtype=torch.float64).pin_memory()
+    Tn_h = torch.empty(P, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        q = phases.model1_phase_scan(m8_h.to(e.dev, non_blocking=True), T)
+        S_h.copy_(q["S"], non_blocking=True)
+        Tn_h.copy_(q["Tnuc"], non_blocking=True)
+        torch.cuda.synchronize()
+        return float(Tn_h[0])
+
+    e2e_step()
+    e.barrier()
+    t0 = time.perf_counter()
+    ks = max(1, min(args.steps, 5))
+    for _ in range(ks):
+        e2e_step()
+    e.barrier()
+    e2e_ms = e.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    sampler.mark("load", t_load0, time.perf_counter())
+    clocks = sampler.stop()
+    if e.rank != 0:
+        return None
+    kern_avg_ms = float(np.mean(kern_ms))
+    fp64_peak = fp64_peak_tflops(_lib, torch, e.dev)
+    achieved = wl["flop_per_bounce"] * nb / (kern_avg_ms * 1e-3) / 1e12
+    Tn = r["Tnuc"].cpu().numpy()
+    return {
+        "metric": "bounce actions/sec", "value": e.world * nb * args.steps / (total_ms * 1e-3), "unit": "bounces/s",
+        "n_gpus": e.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(args, wl, e.world, mode),
+        "timing": "CUDA events around each step (two ctb_trace_minima launches, the torch bookkeeping between them, setup + "
+                  "sort + shoot + save kernels of the bounce batch) on the launching stream; 256 MiB L2 flush between iterations",
+        "wall_s_timed_region": t_wall,
+        "scan": {"parameter_points_this_rank": P, "temperatures": nT, "point_T_pairs_per_s": e.world * P * nT * args.steps / (total_ms * 1e-3),
+                 "bounces_per_step_this_rank": nb, "solved": solved, "newton_iterations": r["newton_iters"],
+                 "points_with_Tnuc": int(np.isfinite(Tn).sum()), "Tnuc_median": float(np.nanmedian(Tn)) if np.isfinite(Tn).any() else None,
+                 "Tcrit_median": float(np.nanmedian(r["Tcrit"].cpu().numpy()))},
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                     "traffic": None, "algorithmic_flop_per_bounce": wl["flop_per_bounce"], "kernel_ms": kern_avg_ms,
+                     "peak_source": "ctb_fp64_peak register-resident DFMA loop, measured in this run",
+                     "scope": "whole step, bounces only (the phase following is extra work on top): ~6e3 Vtot evaluations x 300 "
+                              "flop per finite-T bounce (SURVEY.md s.8d)"},
+        "e2e": {"value": e.world * nb * ks / (e2e_ms * 1e-3), "unit": "bounces/s", "h2d_bytes_per_step": P * 64,
+                "d2h_bytes_per_step": P * nT * 8 + P * 8, "steps": ks,
+                "how": "pinned host model rows -> phases.model1_phase_scan (public API) -> pinned host S[P, nT] and Tnuc[P]"},
+        "gpu_launches": args.steps * 6, "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
 # workload c4: model1 Vtot on the 4096 x 1024 grid (+ the line bounce scan as a second figure)
 
 def run_c4(args, wl, e, mode):
@@ -834,6 +918,8 @@ def main():
     e = setup_env(args)
     if args.workload == "c5":
         line = run_c5(args, wl, e, mode)
+    elif args.workload == "c5m":
+        line = run_c5m(args, wl, e, mode)
     elif args.workload == "c4":
         line = run_c4(args, wl, e, mode)
     elif mode == "global":

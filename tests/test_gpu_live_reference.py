@@ -154,12 +154,30 @@ def test_thermal_functions_vs_live_reference(ref):
 def test_full_tunneling_without_path_spline(ref):
     """pathDeformation.fullTunneling(..., V_spline_samples=None) hands the tunneling class the raw path.V / path.dV
     callables instead of a spline (pathDeformation.py:959-964); the GPU class samples them onto its tabulated functor.
-    The action agrees with the reference's own run of the same branch to the accuracy of that table."""
+
+    (i) One 1-D solve along the initial straight path (SplinePath with extend_to_minima, as fullTunneling builds it):
+    the GPU class on the sampled callables against the reference's class on the callables themselves.  Measured with
+    the reference's own solver on the same 255-piece table: -5e-7 relative (its bisection noise at xtol = 1e-4).
+    (ii) The whole deformation loop.  Its stopping rule (fRatio < 2e-2) makes the final action depend on the 1-D
+    profiles at the 1e-4 level -- the reference's own two branches (V_spline_samples = 100 vs None) differ by 4e-5 -- so
+    the bar there is 5e-4."""
     from cosmoTransitions.examples import fullTunneling as ft
+    from cosmotransitions_b200 import potentials
     from cosmotransitions_b200.tunneling1D import SingleFieldInstanton as GpuSFI
-    pd = ref["pd"]
+    pd, t1 = ref["pd"], ref["t1"]
     m = ft.Potential(c=5., fx=0., fy=2.)
+    path = pd.SplinePath(np.array([[1, 1.], [0, 0]]), m.V, m.dV, V_spline_samples=None, extend_to_minima=True)
+    robj = t1.SingleFieldInstanton(0.0, path.L, path.V, path.dV, None)
+    S_ref = robj.findAction(robj.findProfile())
+    gobj = GpuSFI(0.0, path.L, path.V, path.dV, None)
+    assert isinstance(gobj.V, potentials.SampledPotential)
+    S_gpu = gobj.findAction(gobj.findProfile())
+    print("1-D solve on raw path callables: GPU (sampled) S = %.8f, reference S = %.8f, rel %.1e"
+          % (S_gpu, S_ref, abs(S_gpu - S_ref) / S_ref))
+    assert abs(S_gpu - S_ref) < 3e-6 * S_ref
     Yref = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV, V_spline_samples=None)
     Y = pd.fullTunneling([[1, 1.], [0, 0]], m.V, m.dV, V_spline_samples=None, tunneling_class=GpuSFI)
-    assert abs(Y.action - Yref.action) < 2e-5 * Yref.action, (Y.action, Yref.action)
-    assert abs(Yref.action - 1766.9) < 0.5
+    print("fullTunneling(V_spline_samples=None): GPU class (sampled callables) S = %.8f, reference S = %.8f"
+          % (Y.action, Yref.action))
+    assert abs(Yref.action - 1766.86) < 0.05
+    assert abs(Y.action - Yref.action) < 5e-4 * Yref.action, (Y.action, Yref.action)
