@@ -48,6 +48,9 @@ WORKLOADS = {
     "c4": dict(n=4096 * 1024, alpha=2, name="C4: model1 Vtot on a 4096 x 1024 (phi, T) grid + 512-temperature bounce "
                                             "scan along the line between the phases"),
 }
+# slots (streams) of the end-to-end pipelines: with three batches in flight the thinning tails of one batch's kernels are
+# filled by the heads of the next two (C2: 1.28e8 -> 1.42e8 bounces/s end to end; four slots: 1.35e8)
+PIPE_DEPTH = 3
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
 # dram__bytes_read.sum + dram__bytes_write.sum per STEP (every kernel of the step: setup + sort + shoot + save), from the
 # `ncu --set full` captures under profiles/ (see profiles/README.md); None until captured for a workload
@@ -442,9 +445,9 @@ def run_quartic_single(args, wl, e, mode):
     out_np = {k: v.cpu().numpy() for k, v in out.items()}
 
     # ---- end to end through the public API: host buffers in, host results out, every step ----
-    # BouncePipeline: two slots, each with its own stream -- the H2D copy of step k+1 and the D2H copy of step k-1
+    # BouncePipeline: PIPE_DEPTH slots, each with its own stream -- the H2D copy of step k+1 and the D2H copy of step k-1
     # overlap the kernels of step k; every step's copies happen inside the timed region
-    pipe = batch.BouncePipeline(_lib.POT_POLY4, n, depth=2, device=e.dev, outputs=("S", "status"), alpha=wl["alpha"],
+    pipe = batch.BouncePipeline(_lib.POT_POLY4, n, depth=PIPE_DEPTH, device=e.dev, outputs=("S", "status"), alpha=wl["alpha"],
                                 block_threads=args.block, schedule=args.schedule)
 
     def e2e_run(steps):
@@ -491,9 +494,9 @@ def run_quartic_single(args, wl, e, mode):
                                      "whole step: setup + sort + shoot + save kernels (the flop count per bounce covers "
                                      "shooting, dense output and quadrature)"),
         "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "how": "batch.BouncePipeline (public API), pinned host buffers in / pinned host results out every step, two "
-                       "slots on two CUDA streams so the copies of neighbouring steps overlap the kernels; wall clock "
-                       "around the whole loop including the final synchronisation"},
+                "how": "batch.BouncePipeline (public API), pinned host buffers in / pinned host results out every step, %d "
+                       "slots on as many CUDA streams so the copies and kernel tails of neighbouring steps overlap; wall "
+                       "clock around the whole loop including the final synchronisation" % PIPE_DEPTH},
         # per step: setup_kernel + shoot kernel + save kernel (work-sorted, split solve); fused otherwise
         "gpu_launches": args.steps * (3 if sorted_sched else 1),
         "clocks": clocks,
@@ -520,7 +523,7 @@ def run_quartic_global(args, wl, e, mode):
     abs_h = torch.ones(n, dtype=torch.float64).pin_memory()
     meta_h = torch.zeros(n, dtype=torch.float64).pin_memory()
     outs = ("S", "status")
-    db = multigpu.DistributedBounce(_lib.POT_POLY4, n, block=args.partition_block, depth=2, outputs=outs, device=e.dev,
+    db = multigpu.DistributedBounce(_lib.POT_POLY4, n, block=args.partition_block, depth=PIPE_DEPTH, outputs=outs, device=e.dev,
                                     alpha=wl["alpha"], block_threads=args.block, schedule=args.schedule)
     lay = db.layout
     n_local = lay.n_local
@@ -595,7 +598,7 @@ def run_quartic_global(args, wl, e, mode):
             b.record()
             torch.cuda.synchronize()
             ms1.append(a.elapsed_time(b))
-        sb = multigpu.ShardedBounce(_lib.POT_POLY4, n, 1, 0, device=e.dev, depth=2, outputs=outs, alpha=wl["alpha"],
+        sb = multigpu.ShardedBounce(_lib.POT_POLY4, n, 1, 0, device=e.dev, depth=PIPE_DEPTH, outputs=outs, alpha=wl["alpha"],
                                     block_threads=args.block, schedule=args.schedule)
         res1 = {"S": torch.empty(n, dtype=torch.float64).pin_memory(), "status": torch.empty(n, dtype=torch.int32).pin_memory()}
         for _ in range(2):
@@ -639,7 +642,7 @@ def run_quartic_global(args, wl, e, mode):
         "e2e": {"value": e2e_value, "unit": "bounces/s", "h2d_bytes_per_step": h2d * e.world, "d2h_bytes_per_step": d2h * e.world,
                 "how": "multigpu.DistributedBounce (public API): every rank DMAs its block-cyclic shard out of the pinned "
                        "GLOBAL input array, solves it, and DMAs S / status into the shared pinned GLOBAL result segment; "
-                       "rank 0 reads every step's gathered result; two result slots rotate so consecutive steps overlap; "
+                       "rank 0 reads every step's gathered result; three result slots rotate so consecutive steps overlap; "
                        "wall clock over all steps, max over ranks"},
         "gpu_launches": args.steps * (3 if sorted_sched else 1) * e.world,
         "clocks": clocks,
@@ -859,7 +862,7 @@ def run_c4(args, wl, e, mode):
     kern_avg_ms = float(np.mean(kern_ms))
     hbm = 8.0 * npts / (kern_avg_ms * 1e-3) / 1e9
     fp64_peak = fp64_peak_tflops(_lib, torch, e.dev)
-    flop_pt = 120.0
+    flop_pt = 40.0   # executed per point by the tracked kernel: 3 x (subtract, 2 compares, 3 FMA) + 3 multiplies + the final FMA
     return {
         "metric": "Vtot grid points/sec", "value": value, "unit": "points/s", "n_gpus": e.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -871,8 +874,9 @@ def run_c4(args, wl, e, mode):
                      "algorithmic_bytes_per_point": 8.0, "kernel_ms": kern_avg_ms,
                      "fp64": {"achieved": flop_pt * npts / (kern_avg_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                               "flop_per_point_executed": flop_pt,
-                              "note": "3 table look-ups + cubics, 1/T^2, T^4 per point; the three logs + sqrt of the "
-                                      "field-dependent part are per ROW (hoisted), not per point"}},
+                              "note": "per point: three tracked spline look-ups (interval test + cubic) and the final FMA; "
+                                      "1/T^2 and T^4 are per THREAD, the three logs + sqrt of the field-dependent part "
+                                      "per ROW; the kernel is latency / issue-bound table work (DESIGN.md s.4.6)"}},
         "e2e": {"value": npts / e2e_s, "unit": "points/s", "h2d_bytes_per_step": (4096 + 1024) * 8, "d2h_bytes_per_step": npts * 8,
                 "how": "generic_potential.model1.Vtot_grid with numpy axes in, numpy grid out"},
         "line_bounce_scan": {"temperatures": len(Ts), "seconds": t_scan, "bounces_per_s": len(Ts) / t_scan,

@@ -312,7 +312,7 @@ class BouncePipeline:
         ... collect the last `depth` tickets
     """
 
-    def __init__(self, potential_kind, n, depth=2, device=None, outputs=("S", "status"), alpha=2, phi_eps=1e-3,
+    def __init__(self, potential_kind, n, depth=3, device=None, outputs=("S", "status"), alpha=2, phi_eps=1e-3,
                  schedule="auto", split="auto", block_threads=0, kernel="auto", **findProfile_knobs):
         torch = _lib.require_cuda()
         self._torch = torch

@@ -205,6 +205,23 @@ class model1(_FiniteDifferences):
             return out
         return out.cpu() if is_tensor else out.cpu().numpy()
 
+    def findMinimum(self, X=None, T=0.0, max_iter=60, xtol=1e-9):
+        """generic_potential.findMinimum (generic_potential.py:477-484: one scipy.optimize.fmin call per point) for any
+        number of points at once, entirely on the device: X [..., 2] against T [...] -> minima of the broadcast shape +
+        (2,).  One launch of the warp-per-point damped Newton kernel (ctb_trace_minima, csrc/ctb_phases.cuh); points
+        whose iteration does not end on a minimum come back as NaN."""
+        from . import phases
+        if X is None:
+            X = self.approxZeroTMin()[0]
+        X = np.asarray(X, dtype=np.float64)
+        shape = np.broadcast_shapes(X.shape[:-1], np.shape(T))
+        Xb = np.ascontiguousarray(np.broadcast_to(X, shape + (2,))).reshape(-1, 2)
+        Tb = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.float64), shape)).reshape(-1)
+        r = phases.find_minimum(self.model8, Xb, Tb, max_iter=max_iter, xtol=xtol, x_eps=self.x_eps)
+        out = r["X"].cpu().numpy()
+        out[r["flag"].cpu().numpy() != _lib.MIN_OK] = np.nan
+        return out.reshape(shape + (2,))
+
     def approxZeroTMin(self):
         """The two tree-level minima (examples/testModel1.py:118-122)."""
         v = float(self.v2) ** .5

@@ -346,7 +346,7 @@ class DistributedBounce:
 
     TIMEOUT_S = 300.0
 
-    def __init__(self, potential_kind, n, block=DEFAULT_BLOCK, depth=2, outputs=("S", "status"), device=None,
+    def __init__(self, potential_kind, n, block=DEFAULT_BLOCK, depth=3, outputs=("S", "status"), device=None,
                  solve=None, shm_dir="/dev/shm", **kw):
         import torch.distributed as dist
         self._dist = dist
