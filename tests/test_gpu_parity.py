@@ -624,14 +624,26 @@ def test_jexact_golden(ctb, gold_dir):
     np.testing.assert_allclose(fT.Jf_exact2(h.xf), h.yf, rtol=0, atol=1e-7)
 
 
-def test_jspline_large_vs_oracle(ctb, oracle, tables):
+@pytest.mark.parametrize("n", [1 << 20, (1 << 22) + 5])
+def test_jspline_large_vs_oracle(ctb, oracle, tables, n):
+    """Large random arrays (one with an odd tail) with every breakpoint +- 1 ulp and the table ends among the arguments,
+    all four derivative orders."""
     from cosmotransitions_b200 import finiteT
     rng = np.random.default_rng(42)
-    th = rng.uniform(-10, 2000, 1 << 20)
+    th = rng.uniform(-10, 2000, n)
+    brk = np.unique(tables.tb)
+    edge = np.concatenate([brk, np.nextafter(brk, -np.inf), np.nextafter(brk, np.inf), [tables.xbmin, tables.xbmax, 0.0, -0.0]])
+    th[:edge.size] = edge
     np.testing.assert_allclose(finiteT.Jb_spline(th), oracle.jspline(tables.tb, tables.cb, tables.xbmin, tables.xbmax, th),
                                rtol=0, atol=J_ATOL)
     np.testing.assert_allclose(finiteT.Jf_spline(th), oracle.jspline(tables.tf, tables.cf, tables.xfmin, tables.xfmax, th),
                                rtol=0, atol=J_ATOL)
+    for d in (1, 2, 3):
+        got = finiteT.Jb_spline(th, n=d)
+        want = oracle.jspline(tables.tb, tables.cb, tables.xbmin, tables.xbmax, th, d)
+        # (derivative d of a cubic spline jumps at the knots for d = 3: compare away from the +-1 ulp neighbours)
+        sel = slice(edge.size, None) if d == 3 else slice(None)
+        np.testing.assert_allclose(got[sel], want[sel], rtol=1e-9, atol=1e-9)
 
 
 def test_model1_vtot_golden(ctb, gold_dir):
