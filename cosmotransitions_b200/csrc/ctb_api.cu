@@ -561,17 +561,6 @@ __global__ void fp64_peak_kernel(int64_t iters, double *sink)
     if (r == 12345.678) sink[0] = r; // never true; keeps the loop alive
 }
 
-JTab to_jtab(const ctb_jtable *t)
-{
-    JTab j{nullptr, nullptr, JT_GLOBAL, 0, 0, 0, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (t) {
-        j.brk = t->d_brk; j.coef = t->d_coef; j.nint = t->nint; j.xmin = t->xmin; j.xmax = t->xmax;
-        j.loc_scale = (float)t->loc_scale; j.loc_u0 = (float)t->loc_u0; j.loc_inv_du = (float)t->loc_inv_du;
-        j.loc_c = (float)(-t->loc_u0 * t->loc_inv_du - 1.001);
-    }
-    return j;
-}
-
 size_t table_bytes(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES(t->nint) * sizeof(double) : 0; }
 size_t table_bytes_compact(const ctb_jtable *t) { return t ? CTB_TABLE_DOUBLES_COMPACT(t->nint) * sizeof(double) : 0; }
 

@@ -49,6 +49,18 @@ struct JTab {
 
 #define CTB_TABLE_DOUBLES(nint) ((size_t)(nint) * 6)
 
+// host side: the C-ABI table descriptor -> the kernels' view of it (NULL: an empty table)
+inline JTab to_jtab(const ctb_jtable *t)
+{
+    JTab j{nullptr, nullptr, JT_GLOBAL, 0, 0, 0, 0, 0.0, 0.0, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (t) {
+        j.brk = t->d_brk; j.coef = t->d_coef; j.nint = t->nint; j.xmin = t->xmin; j.xmax = t->xmax;
+        j.loc_scale = (float)t->loc_scale; j.loc_u0 = (float)t->loc_u0; j.loc_inv_du = (float)t->loc_inv_du;
+        j.loc_c = (float)(-t->loc_u0 * t->loc_inv_du - 1.001);
+    }
+    return j;
+}
+
 // Copies a table into shared memory (whole block cooperates; caller syncs) as one 48-byte record per knot
 // interval -- left breakpoint, the four coefficients, right breakpoint -- so that an evaluation touches
 // exactly three 16-byte words: the interval test and the polynomial come from the same record.

@@ -7,10 +7,9 @@ int launch_trace_minima_model1(const double *d_params, int64_t param_stride, con
                                int64_t n, int nT, const MinKnobs &k, double *d_X, double *d_V, int32_t *d_flag,
                                int32_t *d_iters, cudaStream_t st)
 {
-    const int64_t blocks = (n + 7) / 8; // 8 warps = 8 instances per 256-thread block
-    if (blocks > 0x7fffffff) return CTB_ERR_UNSUPPORTED;
-    launch_k(trace_minima_kernel<Model1XY>, (unsigned)blocks, 256, CTB_TABLE_DOUBLES(jb.nint) * sizeof(double), st, d_params,
-             param_stride, jb, d_X0, d_T, T_stride, d_t_begin, d_t_dir, n, nT, k, d_X, d_V, d_flag, d_iters);
-    return (int)cudaGetLastError();
+    JTab none = jb;
+    none.nint = 0;
+    return launch_trace_minima<Model1XY>(d_params, param_stride, jb, none, d_X0, d_T, T_stride, d_t_begin, d_t_dir, n, nT, k, d_X,
+                                         d_V, d_flag, d_iters, st);
 }
 } // namespace ctb

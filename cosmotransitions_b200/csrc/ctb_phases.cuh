@@ -23,6 +23,16 @@
 
 namespace ctb {
 
+// The staged Jb / Jf tables as a model's V sees them (jf.nint = 0: the model has no fermions, nothing staged)
+struct Tabs { JTab jb, jf; };
+
+// A MODEL is a struct with
+//   static constexpr int ndim, nparam;   number of fields, doubles per parameter row
+//   void load(const double *row);        take one parameter row
+//   void set_T(double T);                temperature-dependent constants
+//   double V(const Tabs &, const double *X) const;   Vtot(X, T) = V0 + V1 + V1T (GP:240-337)
+// Built in: Model1XY.  Others are compiled at run time from a few lines of CUDA (cosmotransitions_b200/jit.py).
+
 // model1 (examples/testModel1.py:62-116) at a two-field point: V0 + V1 + V1T (GP:240-337)
 struct Model1XY {
     static constexpr int ndim = 2;
@@ -39,8 +49,9 @@ struct Model1XY {
         inv_T2 = 1.0 / (T2 + 1e-100);
         T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
     }
-    CTB_DEV double V(const JTab &jb, const double *X) const
+    CTB_DEV double V(const Tabs &tb, const double *X) const
     {
+        const JTab &jb = tb.jb;
         const Model1Field f = model1_field(l1, l2, mu2, Y1, Y2, nb, inv_rs, v2, X[0], X[1]);
         const double yt = jtab_eval<0>(jb, f.m0 * inv_T2) + jtab_eval<0>(jb, f.m1 * inv_T2) + nb * jtab_eval<0>(jb, f.mb * inv_T2);
         return f.V01 + yt * T4c;
@@ -117,7 +128,7 @@ CTB_DEV double warp_sum(double v)
 // {1,-8,8,-1}/12h for the gradient and {-1,16,16,-1}/12h^2 for H_ii), the rest move a pair (i < j) by the 4 x 4
 // products (weights c_a c_b / 144 h^2 for H_ij).  Every lane returns the same f0, g, H.
 template <class Model>
-__device__ __forceinline__ void warp_grad_hess(const Model &m, const JTab &jb, const double (&X)[Model::ndim], double h,
+__device__ __forceinline__ void warp_grad_hess(const Model &m, const Tabs &jb, const double (&X)[Model::ndim], double h,
                                                int lane, double &f0, double (&g)[Model::ndim],
                                                double (&H)[Model::ndim][Model::ndim])
 {
@@ -183,7 +194,7 @@ __device__ __forceinline__ void warp_grad_hess(const Model &m, const JTab &jb, c
 // Damped Newton from X (in/out), the whole warp on one point.  Returns CTB_MIN_OK, CTB_MIN_NOT_CONVERGED or
 // CTB_MIN_NOT_A_MINIMUM (converged with a lifted Hessian: a saddle or a maximum); fmin = V at the result.
 template <class Model>
-__device__ __forceinline__ int warp_newton_minimize(const Model &m, const JTab &jb, const MinKnobs &k, int lane,
+__device__ __forceinline__ int warp_newton_minimize(const Model &m, const Tabs &jb, const MinKnobs &k, int lane,
                                                     double (&X)[Model::ndim], double &fmin, int &iters)
 {
     constexpr int N = Model::ndim;
@@ -244,6 +255,7 @@ __device__ __forceinline__ int warp_newton_minimize(const Model &m, const JTab &
 // Entries it does not reach are NaN / CTB_MIN_NOT_TRACED.  param_stride = 0: one model for all instances.
 template <class Model>
 __global__ void __launch_bounds__(256) trace_minima_kernel(const double *__restrict__ params, int64_t param_stride, JTab g,
+                                                          JTab gf,
                                                           const double *__restrict__ X0, const double *__restrict__ T,
                                                           int64_t T_stride, const int32_t *__restrict__ t_begin,
                                                           const int32_t *__restrict__ t_dir, int64_t n, int nT, MinKnobs k,
@@ -251,7 +263,10 @@ __global__ void __launch_bounds__(256) trace_minima_kernel(const double *__restr
                                                           int32_t *__restrict__ flag, int32_t *__restrict__ iters_out)
 {
     constexpr int N = Model::ndim;
-    const JTab jb = stage_table(g, ctb_dynsmem);
+    Tabs jb;
+    jb.jb = stage_table(g, ctb_dynsmem);
+    jb.jf = gf;
+    if (gf.nint > 0) jb.jf = stage_table(gf, ctb_dynsmem + CTB_TABLE_DOUBLES(g.nint));
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -352,5 +367,20 @@ __global__ void __launch_bounds__(256) trace_minima_kernel(const double *__restr
     }
     if (iters_out && lane == 0) iters_out[i] = total_iters;
 }
+
+// host-side launcher (8 warps = 8 instances per 256-thread block; both tables staged as 48-byte records)
+template <class Model>
+inline int launch_trace_minima(const double *d_params, int64_t param_stride, const JTab &jb, const JTab &jf, const double *d_X0,
+                        const double *d_T, int64_t T_stride, const int32_t *d_t_begin, const int32_t *d_t_dir, int64_t n, int nT,
+                        const MinKnobs &k, double *d_X, double *d_V, int32_t *d_flag, int32_t *d_iters, cudaStream_t st)
+{
+    const int64_t blocks = (n + 7) / 8; // 8 warps = 8 instances per 256-thread block
+    if (blocks > 0x7fffffff) return CTB_ERR_UNSUPPORTED;
+    const size_t sm = (CTB_TABLE_DOUBLES(jb.nint) + (jf.nint > 0 ? CTB_TABLE_DOUBLES(jf.nint) : 0)) * sizeof(double);
+    launch_k(trace_minima_kernel<Model>, (unsigned)blocks, 256, sm, st, d_params, param_stride, jb, jf, d_X0, d_T, T_stride,
+             d_t_begin, d_t_dir, n, nT, k, d_X, d_V, d_flag, d_iters);
+    return (int)cudaGetLastError();
+}
+
 
 } // namespace ctb

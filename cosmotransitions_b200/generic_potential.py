@@ -310,3 +310,60 @@ class one_field_model(_FiniteDifferences):
         """Vtot offset such that V(0, T) = 0 (generic_potential.py:339-345)."""
         X0 = np.zeros(self.Ndim)
         return self.Vtot(X, T, False) - self.Vtot(X0, T, False)
+
+
+class compiled_model(_FiniteDifferences):
+    """A generic_potential whose Vtot(X, T) is a run-time compiled CUDA body (jit.CompiledModel): the counterpart of
+    subclassing the reference's generic_potential with new V0 / boson_massSq / fermion_massSq
+    (generic_potential.py:132-238) for ANY number of fields up to four.  `params` is this model's parameter row.
+
+    Same broadcasting contract as the reference (X[..., Ndim] against T[...]): Vtot, DVtot, gradV, d2V (the reference's
+    finite-difference stencils, every stencil point in one launch), findMinimum (device Newton), plus
+    trace_minima / phase_scan / line_bounces through `phases` with `model=self.model`."""
+
+    def __init__(self, model, params, x_eps=.001, T_eps=.001, deriv_order=4):
+        self.model, self.Ndim = model, model.ndim
+        self.params = np.ascontiguousarray(params, dtype=np.float64).reshape(max(1, model.nparam))
+        self.x_eps, self.T_eps, self.deriv_order = x_eps, T_eps, deriv_order
+
+    def _combo(self, X, T, parts, include_radiation=True, shifts=None):
+        if parts != _lib.V_TOTAL:
+            raise NotImplementedError("a compiled model evaluates Vtot as a whole (V0 / V1 / V1T are not separable)")
+        torch = _lib.require_cuda()
+        is_tensor = isinstance(X, torch.Tensor)
+        dev = X.device if is_tensor and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        Xd = (X if is_tensor else torch.from_numpy(np.asarray(X, dtype=np.float64))).to(dev, torch.float64)
+        Td = (T if isinstance(T, torch.Tensor) else torch.from_numpy(np.asarray(T, dtype=np.float64))).to(dev, torch.float64)
+        if Xd.dim() == 0 or Xd.shape[-1] != self.Ndim:
+            raise ValueError("X must have a last axis of length Ndim = %d" % self.Ndim)
+        shape = torch.broadcast_shapes(Xd.shape[:-1], Td.shape)
+        Xf = Xd.expand(shape + (self.Ndim,)).reshape(-1, self.Ndim)
+        Tf = Td.expand(shape).reshape(-1)
+        n = Tf.numel()
+        shifts = shifts or [(np.zeros(self.Ndim), 0.0, 1.0)]
+        Xs = torch.cat([Xf + torch.as_tensor(np.asarray(dx, dtype=np.float64), device=dev) for dx, _, _ in shifts]).contiguous()
+        Ts = torch.cat([Tf + dT for _, dT, _ in shifts]).contiguous()
+        out = self.model.vtot(self.params, Xs, Ts)
+        res = sum(w * out[k * n:(k + 1) * n] for k, (_, _, w) in enumerate(shifts)).reshape(shape)
+        if is_tensor:
+            return res if X.is_cuda else res.cpu()
+        res = res.cpu().numpy()
+        return float(res) if res.ndim == 0 else res
+
+    def Vtot(self, X, T, include_radiation=True):
+        return self._combo(X, T, _lib.V_TOTAL)
+
+    def DVtot(self, X, T):
+        return self.Vtot(X, T) - self.Vtot(np.zeros(self.Ndim), T)
+
+    def findMinimum(self, X, T=0.0, max_iter=60, xtol=1e-9):
+        """generic_potential.findMinimum (generic_potential.py:477-484) for any number of points, on the device."""
+        from . import phases
+        X = np.asarray(X, dtype=np.float64)
+        shape = np.broadcast_shapes(X.shape[:-1], np.shape(T))
+        Xb = np.ascontiguousarray(np.broadcast_to(X, shape + (self.Ndim,))).reshape(-1, self.Ndim)
+        Tb = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.float64), shape)).reshape(-1)
+        r = phases.find_minimum(self.params, Xb, Tb, max_iter=max_iter, xtol=xtol, x_eps=self.x_eps, model=self.model)
+        out = r["X"].cpu().numpy()
+        out[r["flag"].cpu().numpy() != _lib.MIN_OK] = np.nan
+        return out.reshape(shape + (self.Ndim,))

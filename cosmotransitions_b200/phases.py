@@ -15,22 +15,25 @@ FLAG_NAMES = {_lib.MIN_OK: "ok", _lib.MIN_NOT_CONVERGED: "not converged", _lib.M
               _lib.MIN_JUMPED: "jumped to another phase", _lib.MIN_NOT_TRACED: "not traced"}
 
 
-def trace_minima(model8, X0, T, t_begin=None, t_dir=None, x_eps=1e-3, xtol=1e-9, jump_tol=0.1, max_iter=60):
-    """Follow the minimum of model1's Vtot(., T) that starts at X0[i] along a temperature grid.
+def trace_minima(model8, X0, T, t_begin=None, t_dir=None, x_eps=1e-3, xtol=1e-9, jump_tol=0.1, max_iter=60, model=None):
+    """Follow the minimum of Vtot(., T) that starts at X0[i] along a temperature grid.
 
-    model8: [8] (one model for all instances) or [n, 8] rows (potentials.model1_model8); X0: [n, 2];
+    model = None: the built-in model1 (examples/testModel1.py); model8: [8] (one model for all instances) or [n, 8] rows
+    (potentials.model1_model8); X0: [n, 2].  model = a jit.CompiledModel: model8 holds its parameter rows ([nparam] or
+    [n, nparam]) and X0 is [n, model.ndim].
     T: [nT] shared grid or [n, nT] one row per instance; t_begin / t_dir: optional [n] start index and +1 / -1
-    direction of the walk.  Returns device tensors dict(X [n, nT, 2], V [n, nT], flag [n, nT] (MIN_*), iters [n]).
+    direction of the walk.  Returns device tensors dict(X [n, nT, ndim], V [n, nT], flag [n, nT] (MIN_*), iters [n]).
     An instance's walk stops at the first temperature whose flag is not MIN_OK; that entry holds the point the
     iteration ended on (for MIN_JUMPED: a minimum of the neighbouring phase)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
+    ndim, nparam = (2, 8) if model is None else (model.ndim, max(1, model.nparam))
     dev = X0.device if isinstance(X0, torch.Tensor) and X0.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    X0d = batch._as_device(torch, X0, dev).reshape(-1, 2).contiguous()
+    X0d = batch._as_device(torch, X0, dev).reshape(-1, ndim).contiguous()
     n = X0d.shape[0]
-    m8 = batch._as_device(torch, model8, dev).reshape(-1, 8).contiguous()
+    m8 = batch._as_device(torch, model8, dev).reshape(-1, nparam).contiguous()
     if m8.shape[0] not in (1, n):
-        raise ValueError("model8 must be one row or one row per instance")
+        raise ValueError("the model parameters must be one row or one row per instance")
     Td = batch._as_device(torch, T, dev).contiguous()
     if Td.dim() == 1:
         nT, T_stride = Td.numel(), 0
@@ -42,14 +45,18 @@ def trace_minima(model8, X0, T, t_begin=None, t_dir=None, x_eps=1e-3, xtol=1e-9,
     tb, td = i32(t_begin), i32(t_dir)
     if tb is not None and n and nT and (int(tb.min()) < 0 or int(tb.max()) >= nT):
         raise ValueError("t_begin out of range")
-    X = torch.empty((n, nT, 2), dtype=torch.float64, device=dev)
+    X = torch.empty((n, nT, ndim), dtype=torch.float64, device=dev)
     V = torch.empty((n, nT), dtype=torch.float64, device=dev)
     flag = torch.empty((n, nT), dtype=torch.int32, device=dev)
     iters = torch.empty((n,), dtype=torch.int32, device=dev)
     opts = _lib.MinOpts(float(x_eps), float(xtol), float(jump_tol), int(max_iter), 0)
+    stride = nparam if (m8.shape[0] == n and n > 1) else 0
+    if model is not None:
+        model.trace_minima_raw(m8, stride, X0d, Td, T_stride, tb, td, n, nT, opts, X, V, flag, iters, dev)
+        return dict(X=X, V=V, flag=flag, iters=iters)
     tabs = _tables.device_tables(dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.ctb_trace_minima(_lib.MODEL_MODEL1, m8.data_ptr(), 8 if m8.shape[0] == n and n > 1 else 0, tabs.jb,
+        _lib.check(lib.ctb_trace_minima(_lib.MODEL_MODEL1, m8.data_ptr(), stride, tabs.jb,
                                         X0d.data_ptr(), Td.data_ptr(), T_stride, tb.data_ptr() if tb is not None else None,
                                         td.data_ptr() if td is not None else None, n, nT, opts, X.data_ptr(), V.data_ptr(),
                                         flag.data_ptr(), iters.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
@@ -58,7 +65,8 @@ def trace_minima(model8, X0, T, t_begin=None, t_dir=None, x_eps=1e-3, xtol=1e-9,
 
 
 def find_minimum(model8, X, T, **knobs):
-    """generic_potential.findMinimum for n (X_i, T_i) pairs at once: X [n, 2], T [n] -> dict(X [n, 2], V [n], flag [n])."""
+    """generic_potential.findMinimum for n (X_i, T_i) pairs at once: X [n, ndim], T [n] -> dict(X [n, ndim], V [n],
+    flag [n]); model= as in trace_minima."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device())
     Td = batch._as_device(torch, T, dev).reshape(-1, 1)
@@ -134,3 +142,114 @@ def model1_phase_scan(model8, T, alpha=2, target=140.0, bounce_mask=None, **knob
     return dict(T=Td, XA=A["X"], XB=B["X"], VA=A["V"], VB=B["V"], flagA=A["flag"], flagB=B["flag"], S=S, status=status,
                 S_over_T=soT, Tcrit=Tcrit, Tnuc=Tnuc, n_bounces=int(idx.shape[0]), endA=eA,
                 newton_iters=int(A["iters"].sum() + B["iters"].sum()))
+
+
+def line_bounces(model, params, T, X_abs, X_meta, alpha=2, pieces=255, pad=0.06, chunk=32768, **knobs):
+    """One bounce per instance along the straight line from X_meta (metastable) to X_abs for ANY model that can be
+    evaluated on the device (a jit.CompiledModel): the line potential V(s) = Vtot(X_abs + s nhat, T), s in [0, L], is
+    SAMPLED by the model's own kernel on `pieces` + 5 equidistant points covering [-pad L, (1 + pad) L], turned into the
+    piecewise cubic Hermite interpolant on the device (derivatives at the knots by the 5-point stencil over the samples)
+    and solved by the tabulated functor (CTB_POT_SPLINE).  Spline-accurate, like potentials.SampledPotential.
+    params [n, nparam] (or one row), T [n], X_abs / X_meta [n, ndim].  Returns dict(S, status, L) device tensors [n]."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if not (8 <= pieces <= _lib.SPLINE_MAX_PIECES):
+        raise ValueError("pieces must be in [8, %d]" % _lib.SPLINE_MAX_PIECES)
+    Xa = batch._as_device(torch, X_abs, dev).reshape(-1, model.ndim)
+    Xm = batch._as_device(torch, X_meta, dev).reshape(-1, model.ndim)
+    n = Xa.shape[0]
+    Td = batch._as_device(torch, T, dev, (n,))
+    P = batch._as_device(torch, params, dev).reshape(-1, max(1, model.nparam))
+    if P.shape[0] == 1:
+        P = P.expand(n, -1)
+    d = Xm - Xa
+    L = torch.linalg.norm(d, dim=-1)
+    nhat = d / L[:, None]
+    K = pieces
+    # knots k = 0..K at s_k = -pad L + k h; two more samples on either side for the derivative stencil
+    h = (1.0 + 2.0 * pad) * L / K
+    j = torch.arange(-2, K + 3, dtype=torch.float64, device=dev)
+    S_out = torch.empty(n, dtype=torch.float64, device=dev)
+    st_out = torch.empty(n, dtype=torch.int32, device=dev)
+    off = 1 + _lib.SPLINE_MAX_PIECES + 1
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        m = hi - lo
+        s = -pad * L[lo:hi, None] + j[None, :] * h[lo:hi, None]                       # [m, K + 5]
+        Xs = (Xa[lo:hi, None, :] + s[:, :, None] * nhat[lo:hi, None, :]).reshape(-1, model.ndim)
+        Ts = Td[lo:hi, None].expand(m, K + 5).reshape(-1)
+        Ps = P[lo:hi, None, :].expand(m, K + 5, P.shape[1]).reshape(-1, P.shape[1])
+        v = model.vtot(Ps, Xs, Ts).reshape(m, K + 5)
+        v = v - v[:, 2:3]                                                              # (offset: keeps the cubic's c0 small)
+        dv = (v[:, :-4] - 8.0 * v[:, 1:-3] + 8.0 * v[:, 3:-1] - v[:, 4:]) / (12.0 * h[lo:hi, None])    # at the K + 1 knots
+        vk = v[:, 2:-2]
+        hh = h[lo:hi, None]
+        v0, v1, d0, d1 = vk[:, :-1], vk[:, 1:], dv[:, :-1], dv[:, 1:]
+        c2 = (3.0 * (v1 - v0) / hh - 2.0 * d0 - d1) / hh
+        c3 = (2.0 * (v0 - v1) / hh + d0 + d1) / (hh * hh)
+        rows = torch.zeros((m, _lib.NPARAM[_lib.POT_SPLINE]), dtype=torch.float64, device=dev)
+        rows[:, 0] = K
+        rows[:, 1:K + 2] = s[:, 2:-2]
+        rows[:, off:off + 4 * K] = torch.stack([v0, d0, c2, c3], dim=-1).reshape(m, 4 * K)
+        r = batch.find_bounce_batch(_lib.POT_SPLINE, rows, torch.zeros(m, dtype=torch.float64, device=dev), L[lo:hi],
+                                    alpha=alpha, **knobs)
+        S_out[lo:hi] = r["S"]
+        st_out[lo:hi] = r["status"]
+    return dict(S=S_out, status=st_out, L=L)
+
+
+def phase_scan(model, params, T, seed_A, seed_B=None, alpha=2, target=140.0, pieces=255, **knobs):
+    """model1_phase_scan for any compiled model: phase A from seed_A [P, ndim] at T[0] upwards until it ends, phase B from
+    A's landing point downwards (or, where A never jumps, from seed_B at T[0] upwards), then line_bounces wherever both
+    exist and B is metastable.  Returns the same dict as model1_phase_scan."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    P8 = batch._as_device(torch, params, dev).reshape(-1, max(1, model.nparam)).contiguous()
+    P = P8.shape[0]
+    Td = batch._as_device(torch, T, dev).reshape(-1).contiguous()
+    nT = Td.numel()
+    sA = batch._as_device(torch, seed_A, dev).reshape(-1, model.ndim)
+    sA = sA.expand(P, -1) if sA.shape[0] == 1 else sA
+    A = trace_minima(P8, sA, Td, model=model)
+    okA = A["flag"] == _lib.MIN_OK
+    ar = torch.arange(nT, device=dev)
+    eA = torch.where(okA.all(dim=1), torch.full((P,), nT, device=dev), (~okA).to(torch.int64).argmax(dim=1))
+    e_idx = eA.clamp(max=nT - 1)
+    jumped = (eA < nT) & (A["flag"].gather(1, e_idx[:, None])[:, 0] == _lib.MIN_JUMPED)
+    seedB = A["X"].gather(1, e_idx[:, None, None].expand(P, 1, model.ndim))[:, 0, :]
+    if seed_B is not None:
+        sB = batch._as_device(torch, seed_B, dev).reshape(-1, model.ndim)
+        seedB = torch.where(jumped[:, None], seedB, sB.expand(P, -1) if sB.shape[0] == 1 else sB)
+    tbB = torch.where(jumped, e_idx, torch.zeros_like(e_idx))
+    dirB = torch.where(jumped, -torch.ones_like(e_idx), torch.ones_like(e_idx))
+    B = trace_minima(P8, seedB, Td, t_begin=tbB, t_dir=dirB, model=model)
+    okB = B["flag"] == _lib.MIN_OK
+    if seed_B is None:
+        okB = okB & jumped[:, None]
+    dX = B["X"] - A["X"]
+    L = torch.linalg.norm(dX, dim=-1)
+    distinct = okA & okB & (L > 1e-3 * (torch.linalg.norm(A["X"], dim=-1) + 1.0))
+    want = distinct & (B["V"] > A["V"])
+    S = torch.full((P, nT), float("nan"), dtype=torch.float64, device=dev)
+    status = torch.full((P, nT), -1, dtype=torch.int32, device=dev)
+    idx = want.nonzero()
+    if idx.shape[0]:
+        p_i, t_i = idx[:, 0], idx[:, 1]
+        r = line_bounces(model, P8[p_i], Td[t_i], A["X"][p_i, t_i], B["X"][p_i, t_i], alpha=alpha, pieces=pieces, **knobs)
+        S[p_i, t_i] = r["S"]
+        status[p_i, t_i] = r["status"]
+    soT = torch.where((status == 0) | (status == 1), S / Td[None, :], torch.full_like(S, float("nan")))
+    d = torch.where(distinct, A["V"] - B["V"], torch.full_like(S, float("nan")))
+    sc = (d[:, :-1] < 0) & (d[:, 1:] >= 0)
+    has_c = sc.any(dim=1)
+    ic = (sc.to(torch.int64) * ar[1:]).amax(dim=1).clamp(min=1)
+    d0, d1 = d.gather(1, (ic - 1)[:, None])[:, 0], d.gather(1, ic[:, None])[:, 0]
+    Tcrit = torch.where(has_c, Td[ic - 1] + (0.0 - d0) * (Td[ic] - Td[ic - 1]) / (d1 - d0), torch.full_like(d0, float("nan")))
+    cr = (soT[:, :-1] <= target) & (soT[:, 1:] > target)
+    has_n = cr.any(dim=1)
+    i_n = (cr.to(torch.int64) * ar[1:]).amax(dim=1).clamp(min=1)
+    y0, y1 = soT.gather(1, (i_n - 1)[:, None])[:, 0], soT.gather(1, i_n[:, None])[:, 0]
+    Tnuc = torch.where(has_n, Td[i_n - 1] + (target - y0) * (Td[i_n] - Td[i_n - 1]) / (y1 - y0),
+                       torch.full_like(y0, float("nan")))
+    return dict(T=Td, XA=A["X"], XB=B["X"], VA=A["V"], VB=B["V"], flagA=A["flag"], flagB=B["flag"], S=S, status=status,
+                S_over_T=soT, Tcrit=Tcrit, Tnuc=Tnuc, n_bounces=int(idx.shape[0]), endA=eA)

@@ -812,6 +812,82 @@ def gen_alpha14():
         print("alpha14", c_["alpha"], c_["c"], c_["opts"], {q: c_.get(q) for q in ("S", "npts", "n_shots", "error")})
 
 
+class XSM(gp.generic_potential):
+    """A second multi-field model, written against the real generic_potential: Higgs h + Z2 singlet s with the scalar
+    mass matrix eigenvalues, Goldstones, W, Z and a top quark -- the particle content a user's subclass would have
+    (generic_potential.py:132-238).  Mirrored in CUDA by tests/test_gpu_jit.py through jit.CompiledModel."""
+    P = dict(lh=0.129, ls=0.5, lhs=0.6, mus2=100. ** 2, g2=0.4225, gz2=0.55, yt2=0.98, v2=246. ** 2)
+
+    def init(self):
+        self.Ndim = 2
+        self.renormScaleSq = self.P["v2"]
+        self.muh2 = self.P["lh"] * self.P["v2"]
+
+    def V0(self, X):
+        X = np.asanyarray(X)
+        h, s_ = X[..., 0], X[..., 1]
+        P = self.P
+        return (-.5 * self.muh2 * h * h + .25 * P["lh"] * h ** 4 - .5 * P["mus2"] * s_ * s_ + .25 * P["ls"] * s_ ** 4
+                + .5 * P["lhs"] * h * h * s_ * s_)
+
+    def boson_massSq(self, X, T):
+        X = np.asanyarray(X)
+        h, s_ = X[..., 0], X[..., 1]
+        P = self.P
+        a = -self.muh2 + 3 * P["lh"] * h * h + P["lhs"] * s_ * s_
+        b = -P["mus2"] + 3 * P["ls"] * s_ * s_ + P["lhs"] * h * h
+        c = 2 * P["lhs"] * h * s_
+        A, B = .5 * (a + b), np.sqrt(.25 * (a - b) ** 2 + c * c)
+        gold = -self.muh2 + P["lh"] * h * h + P["lhs"] * s_ * s_
+        mW, mZ = .25 * P["g2"] * h * h, .25 * P["gz2"] * h * h
+        M = np.array([A + B, A - B, gold, mW, mZ])
+        M = np.rollaxis(M, 0, len(M.shape))
+        return M, np.array([1., 1., 3., 6., 3.]), np.array([1.5, 1.5, 1.5, 5. / 6, 5. / 6])
+
+    def fermion_massSq(self, X):
+        X = np.asanyarray(X)
+        h = X[..., 0]
+        M = np.array([.5 * self.P["yt2"] * h * h])
+        M = np.rollaxis(M, 0, len(M.shape))
+        return M, np.array([12.])
+
+
+def gen_xsm():
+    from scipy import optimize
+    m = XSM()
+    rng = np.random.default_rng(88)
+    X = np.concatenate([rng.uniform(-350, 350, (300, 2)), [[0., 0.], [246., 0.], [0., 141.4], [1e-3, -1e-3]]])
+    T = np.concatenate([rng.uniform(0, 250, 300), [0., 50., 120., 200.]])
+    out = dict(X=X, T=T, V=m.Vtot(X, T), params=np.array([XSM.P[k] for k in ("lh", "ls", "lhs", "mus2", "g2", "gz2", "yt2", "v2")]))
+    sel = slice(0, 60)
+    out["grad"] = m.gradV(X[sel], T[sel])
+    out["hess"] = m.d2V(X[sel], T[sel])
+    # minima: the electroweak vacuum (h, 0) and the singlet vacuum (0, s) followed in T by the reference's own fmin
+    Tm = np.linspace(0., 150., 31)
+    mins = {}
+    for name, seed in (("ew", np.array([246., 0.])), ("singlet", np.array([0., 141.4]))):
+        x = seed.copy()
+        rows = []
+        for t in Tm:
+            x = optimize.fmin(m.Vtot, x, args=(t,), xtol=1e-9, ftol=1e-13, maxiter=4000, maxfun=8000, disp=0)
+            xn = np.array(x, float)
+            for _ in range(4):
+                H = m.d2V(xn, t)
+                if np.linalg.eigvalsh(H)[0] <= 0:
+                    break
+                xn = xn - np.linalg.solve(H, m.gradV(xn, t))
+            ok = np.linalg.eigvalsh(m.d2V(xn, t))[0] > 0 and np.linalg.norm(xn - x) < 1.0
+            rows.append(xn if ok else [np.nan, np.nan])
+            if not ok:
+                break
+            x = xn
+        rows += [[np.nan, np.nan]] * (len(Tm) - len(rows))
+        mins[name] = np.array(rows, float)
+        print("xsm", name, "followed to T =", Tm[np.isfinite(mins[name][:, 0])][-1], mins[name][0], mins[name][np.isfinite(mins[name][:, 0])][-1])
+    out.update(Tm=Tm, min_ew=mins["ew"], min_singlet=mins["singlet"])
+    np.savez(os.path.join(GOLD, "xsm.npz"), **out)
+
+
 def gen_alpha_real():
     """Real-valued alpha (d = alpha + 1 dimensions, any real alpha >= 0): the reference's general-order Bessel start
     conditions (tunneling1D.py:336-372, scipy.special.iv / jv / gamma) -- exactSolution on random arguments, and full
@@ -846,7 +922,7 @@ def gen_alpha_real():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["tables", "jspline", "jseries", "quartic", "profiles", "units", "model1", "model1f",
-                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs", "phases", "alpha_real"]
+                               "thermal1f", "splinepath", "alpha14", "findaction", "jexact", "wall", "model1_derivs", "phases", "alpha_real", "xsm"]
     for w in which:
         print("generating", w)
         globals()["gen_" + w]()
