@@ -54,7 +54,7 @@ PIPE_DEPTH = 3
 BYTES_PER_BOUNCE = 64.0  # 16-24 B in + ~48 B out
 # dram__bytes_read.sum + dram__bytes_write.sum per STEP (every kernel of the step: setup + sort + shoot + save), from the
 # `ncu --set full` captures under profiles/ (see profiles/README.md); None until captured for a workload
-NCU_TRAFFIC_BYTES = {"c2": 25.7e6, "c3": None}
+NCU_TRAFFIC_BYTES = {"c2": 25.7e6 + 1.3e6, "c3": 80.2e6 + 55.2e6 + 120.1e6 + 14.0e6 + 56e6}   # c3: the set-up kernel (not captured) scaled from c2
 NCU_TRAFFIC_NOTE = ("whole step (setup + sort + shoot + save kernels), ncu dram__bytes_read+write summed over the "
                     "step's launches; algorithmic: 64 B x instances")
 

@@ -304,3 +304,51 @@ def test_finite_difference_stencils_are_exact_on_polynomials():
     assert m._rad(False) == 0.0 and abs(m._rad(True) - 6. * np.pi ** 4 / 45.) < 1e-12
     m.num_fermion_dof = 90.
     assert abs(m._rad(True) - (6. * np.pi ** 4 / 45. + 78. * 7 * np.pi ** 4 / 360.)) < 1e-10
+
+
+def test_sampled_potential_rows_reproduce_the_callable():
+    """potentials.SampledPotential (Python callables -> CTB_POT_SPLINE row): layout and interpolation error on the host."""
+    from cosmotransitions_b200 import _lib, potentials
+    c = 0.3
+    V = lambda p: .25 * p ** 4 - (1 + c) / 3 * p ** 3 + c / 2 * p ** 2
+    dV = lambda p: p * (p - c) * (p - 1.0)
+    x = np.random.default_rng(0).uniform(-0.04, 1.04, 2000)
+    for dv, pieces, tol in ((dV, 255, 1e-11), (None, 255, 2e-11), (dV, 32, 5e-8), (lambda p: float(dV(float(p))), 64, 5e-9)):
+        sp = potentials.SampledPotential.for_instanton(V, dv, 1.0, 0.0, pieces=pieces)
+        row = sp.params
+        assert sp.kind == _lib.POT_SPLINE and row.shape == (_lib.NPARAM[_lib.POT_SPLINE],) and int(row[0]) == pieces
+        brk = row[1:pieces + 2]
+        assert abs(brk[0] + 0.05) < 1e-15 and abs(brk[-1] - 1.05) < 1e-15 and (np.diff(brk) > 0).all()
+        coef = row[257:257 + 4 * pieces].reshape(pieces, 4)
+        j = np.clip(np.searchsorted(brk, x, side="right") - 1, 0, pieces - 1)
+        dx = x - brk[j]
+        v = coef[j, 0] + dx * (coef[j, 1] + dx * (coef[j, 2] + dx * coef[j, 3]))
+        assert np.abs(v - V(x)).max() < tol
+        if dv is not None:   # Hermite: V and dV exact at the knots
+            np.testing.assert_allclose(coef[:, 0], V(brk[:-1]), rtol=0, atol=1e-15)
+            np.testing.assert_allclose(coef[:, 1], dV(brk[:-1]), rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        potentials.SampledPotential(V, 0.0, 1.0, pieces=1000)
+    with pytest.raises(ValueError):
+        potentials.SampledPotential(lambda p: np.log(p), -1.0, 1.0)
+
+
+def test_compiled_model_builds_without_a_gpu():
+    """jit.CompiledModel: the generated source compiles for sm_100a here (nvcc cross-compiles), exports the three entry
+    points with the model's ndim / nparam, is cached by content, and reports nvcc errors with the source location."""
+    import ctypes as C
+    from cosmotransitions_b200 import _lib, jit
+    m = jit.model1_compiled()
+    assert (m.ndim, m.nparam, m.uses_fermions) == (2, 8, False) and os.path.exists(m.so_path)
+    lib = C.CDLL(m.so_path)
+    for name in ("ctbjit_info", "ctbjit_vtot", "ctbjit_trace_minima"):
+        assert hasattr(lib, name)
+    t0 = os.path.getmtime(m.so_path)
+    assert jit.model1_compiled().so_path == m.so_path and os.path.getmtime(m.so_path) == t0      # cache hit
+    m3 = jit.CompiledModel(3, ("k",), "return k * (X[0] * X[0] + X[1] * X[1] + X[2] * X[2]) + T * Jf(X[0] / T2);")
+    assert m3.uses_fermions and m3.so_path != m.so_path
+    with pytest.raises(_lib.CtbError) as e:
+        jit.CompiledModel(2, ("a",), "return no_such_symbol * X[0];")
+    assert "no_such_symbol" in str(e.value)
+    with pytest.raises(_lib.CtbError):     # no GPU here: the calls fail loudly, there is no CPU fallback
+        m.vtot(np.zeros(8), np.zeros((1, 2)), np.zeros(1))
