@@ -444,6 +444,43 @@ def run_quartic_single(args, wl, e, mode):
     value = e.world * n * args.steps / (total_ms * 1e-3)
     out_np = {k: v.cpu().numpy() for k, v in out.items()}
 
+    # ---- the same K device-resident steps with PIPE_DEPTH steps in flight (one stream each): what the GPU delivers when
+    # the thinning tail of one batch's kernels is filled by the next batches (reported beside `value`, which stays the
+    # per-step figure).  Inputs rotate over enough distinct device copies to exceed the L2 (no flush kernels between
+    # overlapping steps); device-timed between one start and one end event, everything joined before the end event.
+    overlapped = None
+    if e.world == 1 and args.order == "natural":
+        ncopy = max(PIPE_DEPTH + 1, int(130e6 // (n * 56)) + 1)          # 56 B of input per instance; > 126 MB in total
+        copies = [(d_params.clone(), d_abs.clone(), d_meta.clone()) for _ in range(ncopy)]
+        streams = [torch.cuda.Stream(device=e.dev) for _ in range(PIPE_DEPTH)]
+        outs = [batch.alloc_out(torch, n, e.dev) for _ in range(PIPE_DEPTH)]
+
+        def run_overlapped(steps):
+            main = torch.cuda.current_stream(e.dev)
+            for s_ in streams:
+                s_.wait_stream(main)
+            for k in range(steps):
+                cp = copies[k % ncopy]
+                with torch.cuda.stream(streams[k % PIPE_DEPTH]):
+                    batch.launch_bounce(_lib.POT_POLY4, cp[0], cp[1], cp[2], opts, outs[k % PIPE_DEPTH], schedule=args.schedule)
+            for s_ in streams:
+                main.wait_stream(s_)
+
+        run_overlapped(PIPE_DEPTH + 1)
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        run_overlapped(args.steps)
+        b_.record()
+        torch.cuda.synchronize()
+        ovl_ms = a_.elapsed_time(b_)
+        same = bool(torch.equal(outs[(args.steps - 1) % PIPE_DEPTH]["S"], out["S"]))
+        overlapped = {"value": n * args.steps / (ovl_ms * 1e-3), "unit": "bounces/s", "steps_in_flight": PIPE_DEPTH,
+                      "ms_per_step": ovl_ms / args.steps, "input_copies": ncopy, "bit_identical_to_serial": same,
+                      "how": "K device-resident steps on %d streams round-robin, inputs rotating over %d distinct device "
+                             "copies (%.0f MB > L2), one CUDA event pair around all K steps" % (PIPE_DEPTH, ncopy, ncopy * n * 56 / 1e6)}
+        del copies, outs
+
     # ---- end to end through the public API: host buffers in, host results out, every step ----
     # BouncePipeline: PIPE_DEPTH slots, each with its own stream -- the H2D copy of step k+1 and the D2H copy of step k-1
     # overlap the kernels of step k; every step's copies happen inside the timed region
@@ -501,6 +538,8 @@ def run_quartic_single(args, wl, e, mode):
         "gpu_launches": args.steps * (3 if sorted_sched else 1),
         "clocks": clocks,
     }
+    if overlapped is not None:
+        line["device_resident_overlapped"] = overlapped
     if not args.no_cpu_baseline:
         line.update(cpu_baseline_and_parity(args, wl, c, out_np))
     return line

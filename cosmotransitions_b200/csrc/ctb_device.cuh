@@ -893,6 +893,137 @@ CTB_DEV double hyp0f1m1(double b, double z, bool modified)
     return sqrt(2.0 / (CTB_PI * z)) * (P * cs - Q * sn) * pref - 1.0;
 }
 
+// I0(z), I1(z) for z >= 0 together (the alpha = 1, 3 start conditions evaluate both at every call: the library's
+// cyl_bessel_i0 + cyl_bessel_i1 are two independent ~120-instruction routines, 11.5 % of all C3 instructions).
+//   z <= 7.75: the ascending series in t = z^2 / 4, 21 all-positive terms each (no cancellation; <= 4 ulp), summed from
+//              k = 1 so that I0 - 1 and (2 / z) I1 - 1 -- what the start conditions actually need -- come without the
+//              cancellation the subtraction has at small z;
+//   z >  7.75: e^z / sqrt(2 pi z) times degree-22 polynomials in 1 / z (Chebyshev fits of sqrt(2 pi z) e^-z I_nu(z) on
+//              0 < 1/z <= 1/7.75 made with 50-digit mpmath values; 2.3e-16 relative), ONE exponential and ONE reciprocal
+//              square root for both; e^z is split for z > 700 so that the result overflows where I_nu does, not before.
+// Checked against mpmath on 1e-3 <= z <= 1e3: I0, I1 <= 5 ulp.
+struct BesselI01 { double i0, i1, i0m1, i1hm1; }; // i0m1 = I0 - 1, i1hm1 = (2 / z) I1 - 1
+CTB_DEV BesselI01 bessel_i01(double z)
+{
+    BesselI01 r;
+    if (z <= 7.75) {
+        const double t = 0.25 * z * z, t2 = t * t;
+        // (even / odd halves: four independent Horner chains of ten terms instead of two of twenty)
+        double p0e = 6.75788438580422547e-35;
+        p0e = fma(p0e, t2, 7.90429189301205402e-30);
+        p0e = fma(p0e, t2, 5.84791131412603850e-25);
+        p0e = fma(p0e, t2, 2.57892888952958276e-20);
+        p0e = fma(p0e, t2, 6.27608134555919329e-16);
+        p0e = fma(p0e, t2, 7.59405842812662392e-12);
+        p0e = fma(p0e, t2, 3.93675988914084175e-08);
+        p0e = fma(p0e, t2, 6.94444444444444444e-05);
+        p0e = fma(p0e, t2, 2.77777777777777762e-02);
+        p0e = fma(p0e, t2, 1.00000000000000000e+00);
+        double p0o = 1.68947109645105643e-37;
+        p0o = fma(p0o, t2, 2.43959626327532528e-32);
+        p0o = fma(p0o, t2, 2.28434035708048379e-27);
+        p0o = fma(p0o, t2, 1.31578004567835862e-22);
+        p0o = fma(p0o, t2, 4.35838982330499500e-18);
+        p0o = fma(p0o, t2, 7.59405842812662337e-14);
+        p0o = fma(p0o, t2, 6.15118732678256523e-10);
+        p0o = fma(p0o, t2, 1.92901234567901239e-06);
+        p0o = fma(p0o, t2, 1.73611111111111101e-03);
+        p0o = fma(p0o, t2, 2.50000000000000000e-01);
+        const double p0 = fma(p0o, t, p0e);
+        double p1e = 3.37894219290211260e-36;
+        p1e = fma(p1e, t2, 4.39127327389558567e-31);
+        p1e = fma(p1e, t2, 3.65494457132877406e-26);
+        p1e = fma(p1e, t2, 1.84209206394970202e-21);
+        p1e = fma(p1e, t2, 5.23006778796599400e-17);
+        p1e = fma(p1e, t2, 7.59405842812662312e-13);
+        p1e = fma(p1e, t2, 4.92094986142605219e-09);
+        p1e = fma(p1e, t2, 1.15740740740740735e-05);
+        p1e = fma(p1e, t2, 6.94444444444444406e-03);
+        p1e = fma(p1e, t2, 5.00000000000000000e-01);
+        double p1o = 8.04510045929074426e-39;
+        p1o = fma(p1o, t2, 1.28399803330280280e-33);
+        p1o = fma(p1o, t2, 1.34372962181204914e-28);
+        p1o = fma(p1o, t2, 8.77186697118905747e-24);
+        p1o = fma(p1o, t2, 3.35260755638845791e-19);
+        p1o = fma(p1o, t2, 6.90368948011511223e-15);
+        p1o = fma(p1o, t2, 6.83465258531396137e-11);
+        p1o = fma(p1o, t2, 2.75573192239858883e-07);
+        p1o = fma(p1o, t2, 3.47222222222222235e-04);
+        p1o = fma(p1o, t2, 8.33333333333333287e-02);
+        const double p1 = fma(p1o, t, p1e);
+        r.i0m1 = p0 * t;
+        r.i1hm1 = p1 * t;
+        r.i0 = r.i0m1 + 1.0;
+        r.i1 = (0.5 * z) * (r.i1hm1 + 1.0);
+    } else {
+        const double u = rcp_fast(z), u2 = u * u;
+        double g0e = 5.10439856463674160e+16;
+        g0e = fma(g0e, u2, 4.30710600204572800e+16);
+        g0e = fma(g0e, u2, 4.26278082774414200e+15);
+        g0e = fma(g0e, u2, 1.12849228600115922e+14);
+        g0e = fma(g0e, u2, 1.00993467373931482e+12);
+        g0e = fma(g0e, u2, 3.30983866591941309e+09);
+        g0e = fma(g0e, u2, 3.96114130742453830e+06);
+        g0e = fma(g0e, u2, 1.60629422238111147e+03);
+        g0e = fma(g0e, u2, 7.54450335052397558e-01);
+        g0e = fma(g0e, u2, 1.12156100369509099e-01);
+        g0e = fma(g0e, u2, 7.03125000067696959e-02);
+        g0e = fma(g0e, u2, 1.00000000000000000e+00);
+        double g0o = -6.90847115994374720e+16;
+        g0o = fma(g0o, u2, -1.63983679029149040e+16);
+        g0o = fma(g0o, u2, -8.01728730945816125e+14);
+        g0o = fma(g0o, u2, -1.21369303670207148e+13);
+        g0o = fma(g0o, u2, -6.54529112951727753e+10);
+        g0o = fma(g0o, u2, -1.30254789946553946e+08);
+        g0o = fma(g0o, u2, -9.19298952676435292e+04);
+        g0o = fma(g0o, u2, -1.86106739466121525e+01);
+        g0o = fma(g0o, u2, 2.26021504737211332e-01);
+        g0o = fma(g0o, u2, 7.32421795032049128e-02);
+        g0o = fma(g0o, u2, 1.24999999999999348e-01);
+        const double g0 = fma(g0o, u, g0e);
+        double g1e = -5.39685914928520960e+16;
+        g1e = fma(g1e, u2, -4.57949971183415680e+16);
+        g1e = fma(g1e, u2, -4.56594665224959400e+15);
+        g1e = fma(g1e, u2, -1.22096213504144156e+14);
+        g1e = fma(g1e, u2, -1.10837511090765234e+12);
+        g1e = fma(g1e, u2, -3.71040044690264654e+09);
+        g1e = fma(g1e, u2, -4.59308217909604032e+06);
+        g1e = fma(g1e, u2, -1.97488628412734852e+03);
+        g1e = fma(g1e, u2, -9.27920846064049454e-01);
+        g1e = fma(g1e, u2, -1.44202791873929648e-01);
+        g1e = fma(g1e, u2, -1.17187500026180808e-01);
+        g1e = fma(g1e, u2, 1.00000000000000000e+00);
+        double g1o = 7.32348604794205440e+16;
+        g1o = fma(g1o, u2, 1.74952333397986120e+16);
+        g1o = fma(g1o, u2, 8.62720432009044125e+14);
+        g1o = fma(g1o, u2, 1.32166579033533594e+13);
+        g1o = fma(g1o, u2, 7.25176396518202820e+10);
+        g1o = fma(g1o, u2, 1.48193099420835495e+08);
+        g1o = fma(g1o, u2, 1.09296831122297372e+05);
+        g1o = fma(g1o, u2, 2.42323657130146302e+01);
+        g1o = fma(g1o, u2, -2.75910766256493467e-01);
+        g1o = fma(g1o, u2, -1.02539043477997735e-01);
+        g1o = fma(g1o, u2, -3.74999999999987566e-01);
+        const double g1 = fma(g1o, u, g1e);
+        double rs;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(z));
+        rs = rs * fma(-0.5 * z * rs, rs, 1.5); // two Newton steps on 1 / sqrt(z)
+        rs = rs * fma(-0.5 * z * rs, rs, 1.5);
+        rs *= 0.39894228040143268; // 1 / sqrt(2 pi)
+        if (z < 700.0) {
+            const double E = exp(z) * rs;
+            r.i0 = g0 * E; r.i1 = g1 * E;
+        } else { // (also z = inf: exp -> inf, rs -> 0 would give NaN without the split order below)
+            const double e2 = exp(0.5 * z);
+            r.i0 = (g0 * rs * e2) * e2; r.i1 = (g1 * rs * e2) * e2;
+            if (z > 1e300) r.i0 = r.i1 = INFINITY;
+        }
+        r.i0m1 = r.i0 - 1.0;
+        r.i1hm1 = (2.0 * u) * r.i1 - 1.0;
+    }
+    return r;
+}
+
 template <int ALPHA>
 __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
 {
@@ -958,8 +1089,9 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
     } else if (ALPHA == 1) {
         // nu = 0: I_0(z) - 1 and (I_{-1} + I_1)/2 = I_1 ; J: J_0(z) - 1 and (J_{-1} - J_1)/2 = -J_1
         if (modified) {
-            phi = (cyl_bessel_i0(z) - 1.0) * ratio + phi0;
-            dphi = (beta * cyl_bessel_i1(z)) * ratio;
+            const BesselI01 b = bessel_i01(z);
+            phi = b.i0m1 * ratio + phi0;
+            dphi = (beta * b.i1) * ratio;
         } else {
             phi = (j0(z) - 1.0) * ratio + phi0;
             dphi = (-beta * j1(z)) * ratio;
@@ -1004,11 +1136,15 @@ __device__ __noinline__ double2 exact_solution(double r, const ExactCoef c)
         // nu = 1: f = (z/2)^-1 I_1(z), f' = (z/2)^-1 I_2(z) with I_2 = I_0 - (2/z) I_1 (J: f' = -(z/2)^-1 J_2,
         // J_2 = (2/z) J_1 - J_0), i.e. the reference's -nu (..) I_nu / r + (..) beta (I_{nu-1} +- I_{nu+1}) / 2 collected
         const double hp = 2.0 * rcp_fast(z); // (z/2)^-1, Gamma(2) = 1
-        double B0, B1;
-        if (modified) { B0 = cyl_bessel_i0(z); B1 = cyl_bessel_i1(z); }
-        else { B0 = j0(z); B1 = j1(z); }
-        phi = (hp * B1 - 1.0) * ratio + phi0;
-        dphi = ((beta * hp) * (B0 - hp * B1)) * ratio;
+        if (modified) { // f - 1 = (2/z) I1 - 1 and I2 = I0 - (2/z) I1 = (I0 - 1) - ((2/z) I1 - 1), both free of cancellation
+            const BesselI01 b = bessel_i01(z);
+            phi = b.i1hm1 * ratio + phi0;
+            dphi = ((beta * hp) * (b.i0m1 - b.i1hm1)) * ratio;
+        } else {
+            const double B0 = j0(z), B1 = j1(z);
+            phi = (hp * B1 - 1.0) * ratio + phi0;
+            dphi = ((beta * hp) * (B0 - hp * B1)) * ratio;
+        }
     }
     return make_double2(phi, dphi);
 }

@@ -81,3 +81,32 @@ def test_real_alpha_matches_integer_kernels_and_scalar_api(gold):
                                 alpha=2.5)
     with pytest.raises(ValueError):
         batch.make_opts(alpha=-1)
+
+
+def test_fused_bessel_i0_i1_against_mpmath():
+    """The fused I0 / I1 evaluation behind the alpha = 1, 3 start conditions (csrc/ctb_device.cuh bessel_i01), read out
+    through ctb_exact_solution with V' = V'' = 1 (phi - phi0 = I0(r) - 1, phi' = I1(r) for alpha = 1; (2/r) I1 - 1 and
+    (2/r) I2 for alpha = 3): a few ulp against 30-digit mpmath values, including the small-z end where the plain
+    subtraction I0 - 1 would lose digits."""
+    mp = pytest.importorskip("mpmath")
+    from cosmotransitions_b200 import batch
+    mp.mp.dps = 30
+    z = np.concatenate([np.logspace(-2 + 1e-9, np.log10(7.75), 250), np.logspace(np.log10(7.7500001), np.log10(690.0), 250),
+                        [7.75, 7.750000000000001, 100.0, 500.0]])
+    one, zero = np.ones_like(z), np.zeros_like(z)
+    p1, d1 = batch.exact_solution_batch(1, z, zero, one, one)
+    p3, d3 = batch.exact_solution_batch(3, z, zero, one, one)
+    ulp = lambda got, want: abs(got - float(want)) / np.spacing(abs(float(want)))
+    worst = dict(i0m1=0.0, i1=0.0, f3=0.0, d3=0.0)
+    for k, zk in enumerate(z):
+        zz = mp.mpf(float(zk))
+        i0, i1, i2 = mp.besseli(0, zz), mp.besseli(1, zz), mp.besseli(2, zz)
+        worst["i0m1"] = max(worst["i0m1"], ulp(p1[k], i0 - 1))
+        worst["i1"] = max(worst["i1"], ulp(d1[k], i1))
+        worst["f3"] = max(worst["f3"], ulp(p3[k], 2 * i1 / zz - 1))
+        worst["d3"] = max(worst["d3"], ulp(d3[k], 2 * i2 / zz))
+    print("fused Bessel, worst ulp errors:", {k: round(v, 1) for k, v in worst.items()})
+    assert worst["i0m1"] <= 8 and worst["i1"] <= 8 and worst["f3"] <= 12 and worst["d3"] <= 24
+    # overflow behaviour: inf where I_nu overflows (as scipy's iv), finite just below
+    p, d = batch.exact_solution_batch(1, np.array([705.0, 720.0, 1e5]), np.zeros(3), np.ones(3), np.ones(3))
+    assert np.isfinite(p[0]) and np.isinf(p[1]) and np.isinf(p[2]) and np.isinf(d[2])
