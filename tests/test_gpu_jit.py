@@ -116,3 +116,47 @@ def test_jit_errors_are_loud(jit):
         jit.CompiledModel(2, ("a",), "return undefined_symbol * X[0];")
     with pytest.raises(ValueError):
         jit.CompiledModel(7, (), "return 0.0;")
+
+
+def test_three_field_model_stencils_and_minima(jit):
+    """ndim = 3: the Hessian stencil has 61 points, i.e. two passes of the warp -- checked on a polynomial model whose
+    gradient / Hessian are known in closed form and whose minima scipy finds on the host from the same expression."""
+    from scipy import optimize
+    from cosmotransitions_b200 import _lib, generic_potential as gp, phases
+    body = '''
+    double v = 0.0;
+    const double vv[3] = {v0, v1, v2};
+    for (int i = 0; i < 3; i++) v += 0.25 * lam * sq(X[i] * X[i] - vv[i] * vv[i]) + 0.5 * cT * T * T * X[i] * X[i];
+    return v + g * X[0] * X[1] * X[2];
+    '''
+    model = jit.CompiledModel(3, ("lam", "cT", "g", "v0", "v1", "v2"), body)
+    par = np.array([0.2, 0.3, 0.05, 100.0, 140.0, 60.0])
+    cm = gp.compiled_model(model, par)
+
+    def V(x, T):
+        x = np.asarray(x, float)
+        vv = par[3:]
+        return float((0.25 * par[0] * (x * x - vv * vv) ** 2 + 0.5 * par[1] * T * T * x * x).sum() + par[2] * x[0] * x[1] * x[2])
+
+    rng = np.random.default_rng(9)
+    X, T = rng.uniform(-150, 150, (64, 3)), rng.uniform(0, 60, 64)
+    np.testing.assert_allclose(cm.Vtot(X, T), [V(x, t) for x, t in zip(X, T)], rtol=1e-13)
+    vv = par[3:]
+    grad = par[0] * X * (X * X - vv * vv) + par[1] * (T * T)[:, None] * X + par[2] * np.stack(
+        [X[:, 1] * X[:, 2], X[:, 0] * X[:, 2], X[:, 0] * X[:, 1]], -1)
+    np.testing.assert_allclose(cm.gradV(X, T), grad, rtol=1e-7, atol=1e-4)
+    H = cm.d2V(X, T)
+    for i in range(3):
+        np.testing.assert_allclose(H[:, i, i], par[0] * (3 * X[:, i] ** 2 - vv[i] ** 2) + par[1] * T * T, rtol=1e-5, atol=0.5)
+    np.testing.assert_allclose(H[:, 0, 1], par[2] * X[:, 2], rtol=1e-4, atol=0.5)
+    np.testing.assert_allclose(H[:, 1, 2], par[2] * X[:, 0], rtol=1e-4, atol=0.5)
+    # minima: 40 random starts near the eight vacua, at T = 10 and 40
+    starts = np.sign(rng.uniform(-1, 1, (40, 3))) * vv * rng.uniform(0.8, 1.2, (40, 3))
+    Tm = np.where(np.arange(40) % 2 == 0, 10.0, 40.0)
+    r = phases.find_minimum(par, starts, Tm, model=model)
+    assert (r["flag"].cpu().numpy() == _lib.MIN_OK).all()
+    Xd = r["X"].cpu().numpy()
+    for k in range(0, 40, 5):
+        ref = optimize.minimize(V, starts[k], args=(Tm[k],), method="BFGS", options=dict(gtol=1e-10)).x
+        ref = optimize.minimize(V, ref, args=(Tm[k],), method="Nelder-Mead", options=dict(xatol=1e-9, fatol=1e-14)).x
+        assert np.linalg.norm(Xd[k] - ref) < 2e-5 * (np.linalg.norm(ref) + 1.0), (k, Xd[k], ref)
