@@ -66,7 +66,10 @@ def _as_device(torch, x, device, shape=None):
     if isinstance(x, torch.Tensor):
         t = x.to(device=device, dtype=torch.float64, non_blocking=True)
     else:
-        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(device, non_blocking=True)
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        if not a.flags.writeable:     # (e.g. arrays out of an .npz: torch wants a writable buffer behind from_numpy)
+            a = a.copy()
+        t = torch.from_numpy(a).to(device, non_blocking=True)
     if shape is not None:
         t = t.expand(shape) if t.dim() == 0 or tuple(t.shape) != tuple(shape) else t
     return t.contiguous()
