@@ -119,8 +119,16 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
     lib = _lib.load()
     n = d_phi_abs.numel()
     dev = d_phi_abs.device
-    tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
-    jb, jf = (tabs.jb, tabs.jf) if tabs else (None, None)
+    custom = getattr(kind, "custom_entry", None)   # a run-time compiled functor (jit.LineFunctor): its own entry points
+    if custom is not None:
+        jb, jf = custom.tables(_tables.device_tables(dev))
+        setup = custom.setup
+        solve = custom.solve
+    else:
+        tabs = _tables.device_tables(dev) if kind in _lib.THERMAL_KINDS else None
+        jb, jf = (tabs.jb, tabs.jf) if tabs else (None, None)
+        setup = lambda *a: lib.ctb_bounce_setup(kind, *a)
+        solve = lambda *a: lib.ctb_bounce_batch(kind, *a)
     bo = _bounce_out(out, profiles)
     st = torch.cuda.current_stream(dev).cuda_stream
     if schedule == "auto":
@@ -130,7 +138,7 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
         if schedule == "sorted":
             key = torch.empty(n, dtype=torch.float32, device=dev)
             bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale)
-            _lib.check(lib.ctb_bounce_setup(kind, bi, jb, jf, bo, key.data_ptr(), st), "ctb_bounce_setup")
+            _lib.check(setup(bi, jb, jf, bo, key.data_ptr(), st), "ctb_bounce_setup")
             order = torch.argsort(key, descending=True)
             # the solve kernel reuses what the setup kernel found (NaN where __init__ failed: the solve
             # kernel then re-derives the same PotentialError status)
@@ -143,7 +151,7 @@ def launch_bounce(kind, d_params, d_phi_abs, d_phi_meta, opts, out, profiles=Non
         if split and profiles is None and opts.kernel != _lib.KERNEL_WARP:
             scratch = torch.empty(3 * n, dtype=torch.float64, device=dev)
         bi = _bounce_in(d_params, d_phi_abs, d_phi_meta, phi_bar, rscale, order, scratch)
-        _lib.check(lib.ctb_bounce_batch(kind, bi, opts, jb, jf, bo, st), "ctb_bounce_batch")
+        _lib.check(solve(bi, opts, jb, jf, bo, st), "ctb_bounce_batch")
 
 
 def bounce_setup(kind, params, phi_absMin, phi_metaMin, phi_bar=None, rscale=None):
@@ -255,7 +263,8 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
                       kernel="auto", split="auto", **findProfile_knobs):
     """Solve N independent bounces.
 
-    potential_kind : one of _lib.POT_* (or a DevicePotential subclass / instance, whose kind is used)
+    potential_kind : one of _lib.POT_* (or a DevicePotential subclass / instance, whose kind is used), or the line
+                     functor of a run-time compiled model (jit.CompiledModel.line_functor())
     params         : [N, K] tensor/array of potential coefficients (K = _lib.NPARAM[kind])
     phi_absMin, phi_metaMin : [N] (or scalars, broadcast)
     alpha, phi_eps : as SingleFieldInstanton.__init__ (tunneling1D.py:128-130)
@@ -272,15 +281,17 @@ def find_bounce_batch(potential_kind, params, phi_absMin, phi_metaMin, alpha=2, 
     status codes: see include/ctbounce.h (0/1 = solved; 2/3 = PotentialError kinds; 4-6 = IntegrationError).
     """
     torch = _lib.require_cuda()
-    kind = getattr(potential_kind, "kind", potential_kind)
-    if kind not in _lib.NPARAM:
+    custom = getattr(potential_kind, "custom_entry", None)
+    kind = custom if custom is not None else getattr(potential_kind, "kind", potential_kind)
+    if custom is None and kind not in _lib.NPARAM:
         raise ValueError("unknown potential kind %r" % (potential_kind,))
+    nparam = custom.nparam if custom is not None else _lib.NPARAM[kind]
     opts = make_opts(alpha=alpha, phi_eps=phi_eps, block_threads=block_threads, kernel=kernel, **findProfile_knobs)
     on_host = not (isinstance(params, torch.Tensor) and params.is_cuda)
     if device is None:
         device = params.device if not on_host else torch.device("cuda", torch.cuda.current_device())
     device = torch.device(device)
-    d_params = _as_device(torch, params, device).reshape(-1, _lib.NPARAM[kind])
+    d_params = _as_device(torch, params, device).reshape(-1, nparam)
     n = d_params.shape[0]
     d_abs = _as_device(torch, phi_absMin, device, (n,))
     d_meta = _as_device(torch, phi_metaMin, device, (n,))

@@ -783,45 +783,19 @@ CTB_API int ctb_sm_count(void)
     return sm_count();
 }
 
-static int fill_args(BounceArgs &a, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
-                     const ctb_bounce_out *out)
-{
-    if (!in || !out || in->n < 0) return CTB_ERR_BAD_ARG;
-    if (in->n > 0 && (!in->d_params || !in->d_phi_abs || !in->d_phi_meta)) return CTB_ERR_BAD_ARG;
-    a.params = in->d_params; a.phi_abs = in->d_phi_abs; a.phi_meta = in->d_phi_meta; a.n = in->n;
-    a.phi_bar_in = in->d_phi_bar; a.rscale_in = in->d_rscale; a.order = in->d_order; a.work_key = nullptr;
-    a.scratch = in->d_scratch;
-    a.jb = to_jtab(jb); a.jf = to_jtab(jf);
-    a.out = *out;
-    return CTB_OK;
-}
-
 CTB_API int ctb_bounce_batch(int pot_kind, const ctb_bounce_in *in, const ctb_opts *o, const ctb_jtable *jb,
                              const ctb_jtable *jf, const ctb_bounce_out *out, void *stream)
 {
     BounceArgs a;
-    if (!o) return CTB_ERR_BAD_ARG;
-    int rc = fill_args(a, in, jb, jf, out);
+    BounceLaunch L;
+    int rc = ctb::fill_bounce_args(a, in, jb, jf, out);
     if (rc) return rc;
-    if (a.n == 0) return CTB_OK;
-    if (o->npoints < 2 || o->npoints > 4096) return CTB_ERR_UNSUPPORTED;
-    if (out->d_prof_R) {
-        if (!out->d_prof_Phi || !out->d_prof_dPhi) return CTB_ERR_BAD_ARG;
-        int64_t maxint = o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts;
-        if (out->prof_stride < o->npoints + maxint) return CTB_ERR_BAD_ARG;
-    }
-    a.knobs.xtol = o->xtol; a.knobs.phitol = o->phitol; a.knobs.thinCutoff = o->thinCutoff; a.knobs.rmin = o->rmin;
-    a.knobs.rmax = o->rmax; a.knobs.phi_eps = o->phi_eps; a.knobs.xguess = o->xguess;
-    a.knobs.npoints = o->npoints; a.knobs.max_interior_pts = o->max_interior_pts;
-    a.knobs.alpha_real = o->alpha_real;
-    if (o->alpha == 0 && !(o->alpha_real >= 0.0 && o->alpha_real <= 8.0)) return CTB_ERR_UNSUPPORTED;
+    if (a.n == 0) return o ? CTB_OK : CTB_ERR_BAD_ARG;
+    rc = ctb::fill_bounce_knobs(a, o, out, pot_kind == CTB_POT_POLY4, L);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    // quartic potential, 64-thread blocks below the throughput regime: finer-grained hand-out of the work-sorted instances (C2: -2 %)
-    int block = o->block_threads ? o->block_threads : (pot_kind == CTB_POT_POLY4 && a.n < 300000 ? 64 : 128);
-    const int stage_cap = o->npoints + (o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts);
-    bool warp = o->kernel == CTB_KERNEL_WARP;
-    if (o->kernel == CTB_KERNEL_AUTO) warp = a.n < 4096 && stage_cap <= 2048 && o->alpha != 0;
-    if (o->kernel < 0 || o->kernel > 2 || (warp && stage_cap > 2048)) return CTB_ERR_UNSUPPORTED;
+    const int block = L.block, stage_cap = L.stage_cap;
+    const bool warp = L.warp;
     if ((pot_kind == CTB_POT_MODEL1_LINE || pot_kind == CTB_POT_MODEL1F) && !jtab_ok(jb)) return CTB_ERR_BAD_ARG;
     if (pot_kind == CTB_POT_THERMAL1F && !(jtab_ok(jb) && jtab_ok(jf))) return CTB_ERR_BAD_ARG;
     switch (pot_kind) {
@@ -848,7 +822,7 @@ CTB_API int ctb_bounce_setup(int pot_kind, const ctb_bounce_in *in, const ctb_jt
                              const ctb_bounce_out *out, float *d_work_key, void *stream)
 {
     BounceArgs a;
-    int rc = fill_args(a, in, jb, jf, out);
+    int rc = ctb::fill_bounce_args(a, in, jb, jf, out);
     if (rc) return rc;
     if (a.n == 0) return CTB_OK;
     a.work_key = d_work_key;

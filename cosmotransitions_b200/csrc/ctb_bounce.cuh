@@ -211,6 +211,45 @@ int launch_bounce_warp_any(const BounceArgs &a, int alpha, int stage_cap, cudaSt
     return (int)cudaGetLastError();
 }
 
+// ---- host side: C-ABI structures -> BounceArgs (shared by ctb_api.cu and the run-time compiled functors) ----
+inline int fill_bounce_args(BounceArgs &a, const ctb_bounce_in *in, const ctb_jtable *jb, const ctb_jtable *jf,
+                            const ctb_bounce_out *out)
+{
+    if (!in || !out || in->n < 0) return CTB_ERR_BAD_ARG;
+    if (in->n > 0 && (!in->d_params || !in->d_phi_abs || !in->d_phi_meta)) return CTB_ERR_BAD_ARG;
+    a.params = in->d_params; a.phi_abs = in->d_phi_abs; a.phi_meta = in->d_phi_meta; a.n = in->n;
+    a.phi_bar_in = in->d_phi_bar; a.rscale_in = in->d_rscale; a.order = in->d_order; a.work_key = nullptr;
+    a.scratch = in->d_scratch;
+    a.jb = to_jtab(jb); a.jf = to_jtab(jf);
+    a.out = *out;
+    return CTB_OK;
+}
+
+struct BounceLaunch { int block, stage_cap; bool warp; };
+// findProfile knobs + kernel choice (thread / warp, block size); small_blocks: the quartic functor's 64-thread blocks
+inline int fill_bounce_knobs(BounceArgs &a, const ctb_opts *o, const ctb_bounce_out *out, bool small_blocks, BounceLaunch &L)
+{
+    if (!o) return CTB_ERR_BAD_ARG;
+    if (o->npoints < 2 || o->npoints > 4096) return CTB_ERR_UNSUPPORTED;
+    if (out->d_prof_R) {
+        if (!out->d_prof_Phi || !out->d_prof_dPhi) return CTB_ERR_BAD_ARG;
+        int64_t maxint = o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts;
+        if (out->prof_stride < o->npoints + maxint) return CTB_ERR_BAD_ARG;
+    }
+    a.knobs.xtol = o->xtol; a.knobs.phitol = o->phitol; a.knobs.thinCutoff = o->thinCutoff; a.knobs.rmin = o->rmin;
+    a.knobs.rmax = o->rmax; a.knobs.phi_eps = o->phi_eps; a.knobs.xguess = o->xguess;
+    a.knobs.npoints = o->npoints; a.knobs.max_interior_pts = o->max_interior_pts;
+    a.knobs.alpha_real = o->alpha_real;
+    if (o->alpha == 0 && !(o->alpha_real >= 0.0 && o->alpha_real <= 8.0)) return CTB_ERR_UNSUPPORTED;
+    // quartic potential, 64-thread blocks below the throughput regime: finer-grained hand-out of the work-sorted instances (C2: -2 %)
+    L.block = o->block_threads ? o->block_threads : (small_blocks && a.n < 300000 ? 64 : 128);
+    L.stage_cap = o->npoints + (o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts);
+    L.warp = o->kernel == CTB_KERNEL_WARP;
+    if (o->kernel == CTB_KERNEL_AUTO) L.warp = a.n < 4096 && L.stage_cap <= 2048 && o->alpha != 0;
+    if (o->kernel < 0 || o->kernel > 2 || (L.warp && L.stage_cap > 2048)) return CTB_ERR_UNSUPPORTED;
+    return CTB_OK;
+}
+
 int launch_bounce_thermal1f(const BounceArgs &a, int alpha, int block, cudaStream_t st);
 int launch_setup_thermal1f(const BounceArgs &a, cudaStream_t st);
 int launch_bounce_warp_thermal1f(const BounceArgs &a, int alpha, int stage_cap, cudaStream_t st);

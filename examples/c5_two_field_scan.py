@@ -37,7 +37,7 @@ if rank == 0:
     sub = rows[:min(64, len(rows))]
     v = np.sqrt(sub[:, 7])
     t0 = time.perf_counter()
-    g = phases.phase_scan(m, sub, T, np.stack([v, v], -1))
+    g = phases.phase_scan(m, sub, T, np.stack([v, v], -1))   # bounce kernels instantiated for the compiled model
     torch.cuda.synchronize()
     d = np.abs(g["Tnuc"].cpu().numpy() - Tn[:len(sub)])
     print("compiled model, %d points: %.3f s; |Tnuc - built-in| max %.3g K" % (len(sub), time.perf_counter() - t0, np.nanmax(d)))

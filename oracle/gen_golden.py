@@ -885,6 +885,23 @@ def gen_xsm():
         mins[name] = np.array(rows, float)
         print("xsm", name, "followed to T =", Tm[np.isfinite(mins[name][:, 0])][-1], mins[name][0], mins[name][np.isfinite(mins[name][:, 0])][-1])
     out.update(Tm=Tm, min_ew=mins["ew"], min_singlet=mins["singlet"])
+    # bounces along the straight line between the two vacua (the 1-D solve of the reference on Vtot restricted to the
+    # line, finite-difference dV / d2V): from the higher (metastable) to the lower one, wherever both exist
+    res = []
+    for k, t in enumerate(Tm):
+        xe, xs = mins["ew"][k], mins["singlet"][k]
+        if not (np.isfinite(xe[0]) and np.isfinite(xs[0])) or t == 0.0:
+            continue
+        ve, vs = float(m.Vtot(xe, t)), float(m.Vtot(xs, t))
+        x_abs, x_meta = (xe, xs) if ve < vs else (xs, xe)
+        L = float(np.linalg.norm(x_meta - x_abs))
+        nh = (x_meta - x_abs) / L
+        Vline = lambda phi, x_abs=x_abs, nh=nh, t=t: m.Vtot(x_abs + np.asarray(phi)[..., None] * nh, t)
+        r = run_case(Vline, None, None, 0.0, L, 2)
+        r.update(T=float(t), L=L, x_abs=[float(q) for q in x_abs], x_meta=[float(q) for q in x_meta])
+        res.append(r)
+        print("xsm bounce T=%g" % t, {q: r.get(q) for q in ("S", "npts", "n_shots", "n_rkck", "error")})
+    out["bounces_json"] = json.dumps(res)
     np.savez(os.path.join(GOLD, "xsm.npz"), **out)
 
 

@@ -95,7 +95,7 @@ def test_line_bounces_through_the_sampled_functor(jit, gold_dir):
     m8, T = g["model8"][:4], np.linspace(70.0, 120.0, 26)
     ref = phases.model1_phase_scan(m8, T)
     v = np.sqrt(m8[:, 7])
-    gen = phases.phase_scan(m, m8, T, np.stack([v, v], -1))
+    gen = phases.phase_scan(m, m8, T, np.stack([v, v], -1), method="sampled")
     st_r, st_g = ref["status"].cpu().numpy(), gen["status"].cpu().numpy()
     both = ((st_r == 0) | (st_r == 1)) & ((st_g == 0) | (st_g == 1))
     assert both.sum() >= 0.9 * ((st_r == 0) | (st_r == 1)).sum() and both.sum() > 20
@@ -160,3 +160,45 @@ def test_three_field_model_stencils_and_minima(jit):
         ref = optimize.minimize(V, starts[k], args=(Tm[k],), method="BFGS", options=dict(gtol=1e-10)).x
         ref = optimize.minimize(V, ref, args=(Tm[k],), method="Nelder-Mead", options=dict(xatol=1e-9, fatol=1e-14)).x
         assert np.linalg.norm(Xd[k] - ref) < 2e-5 * (np.linalg.norm(ref) + 1.0), (k, Xd[k], ref)
+
+
+def test_compiled_line_functor_bounces_vs_reference(jit, gold_dir):
+    """The bounce kernels instantiated for a compiled model (CompiledModel.line_functor): 25 finite-T bounces of the
+    Higgs + singlet model along the line between its two vacua against the reference's SingleFieldInstanton on the same
+    lines (finite-difference dV / d2V on both sides), and against the exact built-in functor for model1."""
+    import json
+    from cosmotransitions_b200 import _lib, batch, phases
+    g = np.load(os.path.join(gold_dir, "xsm.npz"))
+    cases = json.loads(str(g["bounces_json"]))
+    model = jit.CompiledModel(2, XSM_PARAMS, XSM_BODY)
+    f = model.line_functor()
+    assert f.nparam == 8 + 1 + 4
+    rows, L = [], []
+    for c in cases:
+        xa, xm = np.array(c["x_abs"]), np.array(c["x_meta"])
+        rows.append(np.concatenate([g["params"], [c["T"]], xa, (xm - xa) / c["L"]]))
+        L.append(c["L"])
+    rows, L = np.array(rows), np.array(L)
+    for kernel in ("warp", "thread"):
+        r = batch.find_bounce_batch(f, rows, 0.0, L, alpha=2, kernel=kernel)
+        S, st = r["S"].numpy(), r["status"].numpy()
+        Sref = np.array([c["S"] for c in cases])
+        assert (st <= 1).all(), st
+        rel = np.abs(S - Sref) / Sref
+        print("compiled line functor (%s kernel) vs the reference, 25 bounces: max rel %.2e, median %.2e" % (kernel, rel.max(), np.median(rel)))
+        # thin walls next to T_crit (S > 1e5, S/T > 1e3: irrelevant for nucleation) are ill-conditioned in V's last digits
+        assert (rel[Sref < 1e5] < 1e-6).all() and (rel < 1e-4).all(), rel
+        assert (r["n_shots"].numpy()[Sref < 1e5] == np.array([c["n_shots"] for c in cases])[Sref < 1e5]).all()
+    # model1: compiled functor vs the built-in exact line functor on the lines of a phase scan
+    gph = np.load(os.path.join(gold_dir, "phases.npz"))
+    m1 = jit.model1_compiled()
+    m8, T = gph["model8"][:3], np.linspace(75.0, 115.0, 17)
+    ref = phases.model1_phase_scan(m8, T)
+    v = np.sqrt(m8[:, 7])
+    gen = phases.phase_scan(m1, m8, T, np.stack([v, v], -1))          # method="exact" is the default
+    st_r, st_g = ref["status"].cpu().numpy(), gen["status"].cpu().numpy()
+    assert np.array_equal((st_r == 0) | (st_r == 1), (st_g == 0) | (st_g == 1))
+    ok = (st_r == 0) | (st_r == 1)
+    rel = np.abs(gen["S"].cpu().numpy()[ok] - ref["S"].cpu().numpy()[ok]) / ref["S"].cpu().numpy()[ok]
+    print("compiled vs built-in line functor on %d model1 bounces: max rel %.2e" % (ok.sum(), rel.max()))
+    assert np.quantile(rel, 0.9) < 1e-6 and rel.max() < 1e-3
