@@ -186,19 +186,19 @@ def test_compiled_line_functor_bounces_vs_reference(jit, gold_dir):
         assert (st <= 1).all(), st
         rel = np.abs(S - Sref) / Sref
         print("compiled line functor (%s kernel) vs the reference, 25 bounces: max rel %.2e, median %.2e" % (kernel, rel.max(), np.median(rel)))
-        # thin walls next to T_crit (S > 1e5, S/T > 1e3: irrelevant for nucleation) are ill-conditioned in V's last digits
-        assert (rel[Sref < 1e5] < 1e-6).all() and (rel < 1e-4).all(), rel
-        assert (r["n_shots"].numpy()[Sref < 1e5] == np.array([c["n_shots"] for c in cases])[Sref < 1e5]).all()
+        assert (rel < 1e-6).all(), rel            # BASELINE.json's bar; measured: 3.4e-10 max, 9e-12 median
+        assert (r["n_shots"].numpy() == np.array([c["n_shots"] for c in cases])).all()
+        assert (r["n_points"].numpy() == np.array([c["npts"] for c in cases])).all()
     # model1: compiled functor vs the built-in exact line functor on the lines of a phase scan
     gph = np.load(os.path.join(gold_dir, "phases.npz"))
     m1 = jit.model1_compiled()
     m8, T = gph["model8"][:3], np.linspace(75.0, 115.0, 17)
     ref = phases.model1_phase_scan(m8, T)
     v = np.sqrt(m8[:, 7])
-    gen = phases.phase_scan(m1, m8, T, np.stack([v, v], -1))          # method="exact" is the default
+    gen = phases.phase_scan(m1, m8, T, np.stack([v, v], -1), seed_B=np.stack([v, -v], -1))   # method="exact" is the default
     st_r, st_g = ref["status"].cpu().numpy(), gen["status"].cpu().numpy()
     assert np.array_equal((st_r == 0) | (st_r == 1), (st_g == 0) | (st_g == 1))
     ok = (st_r == 0) | (st_r == 1)
     rel = np.abs(gen["S"].cpu().numpy()[ok] - ref["S"].cpu().numpy()[ok]) / ref["S"].cpu().numpy()[ok]
     print("compiled vs built-in line functor on %d model1 bounces: max rel %.2e" % (ok.sum(), rel.max()))
-    assert np.quantile(rel, 0.9) < 1e-6 and rel.max() < 1e-3
+    assert rel.max() < 1e-7
