@@ -352,3 +352,10 @@ def test_compiled_model_builds_without_a_gpu():
     assert "no_such_symbol" in str(e.value)
     with pytest.raises(_lib.CtbError):     # no GPU here: the calls fail loudly, there is no CPU fallback
         m.vtot(np.zeros(8), np.zeros((1, 2)), np.zeros(1))
+    # the bounce kernels instantiated for the model's line potential (second library, built on first use)
+    f = m.line_functor()
+    assert f.nparam == 8 + 1 + 2 * 2 and f.custom_entry is f and os.path.exists(f.so_path) and f.so_path != m.so_path
+    blib = C.CDLL(f.so_path)
+    for name in ("ctbjit_bounce_info", "ctbjit_bounce_setup", "ctbjit_bounce_batch"):
+        assert hasattr(blib, name)
+    assert m.line_functor() is f
