@@ -540,6 +540,32 @@ def run_quartic_single(args, wl, e, mode):
     }
     if overlapped is not None:
         line["device_resident_overlapped"] = overlapped
+    if getattr(args, "default_workload", False) and e.world == 1 and args.workload == "c2":
+        # The same command at N > 1 partitions the C3 batch (BASELINE.json configs[2]: "at 1/2/4/8 B200"): its one-GPU
+        # figure, measured here the same way as `value`, is the denominator a strong-scaling efficiency needs
+        w3 = WORKLOADS["c3"]
+        c3 = sweep_c(w3["n"])
+        p3 = torch.from_numpy(quartic_params(c3)).to(e.dev)
+        a3, m3 = torch.ones(w3["n"], dtype=torch.float64, device=e.dev), torch.zeros(w3["n"], dtype=torch.float64, device=e.dev)
+        o3 = batch.alloc_out(torch, w3["n"], e.dev)
+        opts3 = batch.make_opts(alpha=w3["alpha"], block_threads=args.block)
+        ms3 = []
+        for k in range(2 + 5):
+            e.flush.zero_()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            batch.launch_bounce(_lib.POT_POLY4, p3, a3, m3, opts3, o3, schedule=args.schedule)
+            b_.record()
+            torch.cuda.synchronize()
+            if k >= 2:
+                ms3.append(a_.elapsed_time(b_))
+        line["multi_gpu_workload_on_one_gpu"] = {
+            "workload": w3["name"], "value": w3["n"] / (float(np.mean(ms3)) * 1e-3), "unit": "bounces/s", "steps": len(ms3),
+            "ms_per_step": float(np.mean(ms3)), "solved_fraction": float((o3["status"] <= 1).float().mean()),
+            "note": "`bench.py --gpus N` (N > 1) partitions THIS batch over the ranks; divide its `value` by N times this "
+                    "figure for the strong-scaling efficiency (the N > 1 lines repeat the measurement as "
+                    "single_gpu_same_workload)"}
+        del p3, a3, m3, o3
     if not args.no_cpu_baseline:
         line.update(cpu_baseline_and_parity(args, wl, c, out_np))
     return line
@@ -947,6 +973,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.default_workload = args.workload is None
     if args.workload is None:
         args.workload = "c2" if world == 1 else "c3"
     wl = WORKLOADS[args.workload]
