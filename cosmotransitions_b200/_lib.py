@@ -26,7 +26,7 @@ EXPORTS = ["ctb_abi_version", "ctb_strerror", "ctb_status_string", "ctb_device_o
            "ctb_bounce_setup", "ctb_wall_batch", "ctb_find_action", "ctb_potential_batch", "ctb_minimize_1d",
            "ctb_jspline", "ctb_jseries", "ctb_jexact", "ctb_vtot_model1", "ctb_vtot_model1_grid", "ctb_vtot_thermal1f", "ctb_potential", "ctb_fp64_peak", "ctb_sm_count",
            "ctb_copy_blocks", "ctb_host_register", "ctb_host_unregister", "ctb_trace_minima", "ctb_exact_solution"]
-MODEL_MODEL1 = 0
+MODEL_MODEL1, MODEL_THERMAL1F = 0, 1
 MIN_OK, MIN_NOT_CONVERGED, MIN_NOT_A_MINIMUM, MIN_JUMPED, MIN_NOT_TRACED = range(5)
 
 
@@ -133,7 +133,7 @@ def load():
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
                                     C.c_void_p]
     lib.ctb_trace_minima.restype = C.c_int
-    lib.ctb_trace_minima.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_int64,
+    lib.ctb_trace_minima.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.POINTER(JTable), C.POINTER(JTable), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(MinOpts), C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ctb_exact_solution.restype = C.c_int

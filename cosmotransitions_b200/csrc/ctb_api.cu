@@ -13,6 +13,10 @@ int launch_trace_minima_model1(const double *d_params, int64_t param_stride, con
                                const double *d_T, int64_t T_stride, const int32_t *d_t_begin, const int32_t *d_t_dir,
                                int64_t n, int nT, const MinKnobs &k, double *d_X, double *d_V, int32_t *d_flag,
                                int32_t *d_iters, cudaStream_t st);
+int launch_trace_minima_thermal1f(const double *d_params, int64_t param_stride, const JTab &jb, const JTab &jf,
+                                  const double *d_X0, const double *d_T, int64_t T_stride, const int32_t *d_t_begin,
+                                  const int32_t *d_t_dir, int64_t n, int nT, const MinKnobs &k, double *d_X, double *d_V,
+                                  int32_t *d_flag, int32_t *d_iters, cudaStream_t st);
 }
 
 namespace {
@@ -1070,16 +1074,21 @@ CTB_API int ctb_find_action(int pot_kind, const double *d_params, const ctb_jtab
 }
 
 CTB_API int ctb_trace_minima(int model_kind, const double *d_params, int64_t param_stride, const ctb_jtable *jb,
-                             const double *d_X0, const double *d_T, int64_t T_stride, const int32_t *d_t_begin,
-                             const int32_t *d_t_dir, int64_t n, int32_t nT, const ctb_min_opts *opts, double *d_X,
-                             double *d_V, int32_t *d_flag, int32_t *d_iters, void *stream)
+                             const ctb_jtable *jf, const double *d_X0, const double *d_T, int64_t T_stride,
+                             const int32_t *d_t_begin, const int32_t *d_t_dir, int64_t n, int32_t nT, const ctb_min_opts *opts,
+                             double *d_X, double *d_V, int32_t *d_flag, int32_t *d_iters, void *stream)
 {
     if (n < 0 || nT < 0 || !opts || param_stride < 0 || T_stride < 0) return CTB_ERR_BAD_ARG;
-    if (model_kind != CTB_MODEL_MODEL1) return CTB_ERR_UNSUPPORTED;
+    if (model_kind != CTB_MODEL_MODEL1 && model_kind != CTB_MODEL_THERMAL1F) return CTB_ERR_UNSUPPORTED;
     if (n == 0 || nT == 0) return CTB_OK;
     if (!d_params || !d_X0 || !d_T || !d_X || !d_flag || !jtab_ok(jb)) return CTB_ERR_BAD_ARG;
     if (!(opts->x_eps > 0.0) || !(opts->xtol > 0.0) || !(opts->jump_tol > 0.0) || opts->max_iter < 1) return CTB_ERR_BAD_ARG;
     const MinKnobs k{opts->x_eps, opts->xtol, opts->jump_tol, opts->max_iter};
+    if (model_kind == CTB_MODEL_THERMAL1F) {
+        if (!jtab_ok(jf)) return CTB_ERR_BAD_ARG;
+        return launch_trace_minima_thermal1f(d_params, param_stride, to_jtab(jb), to_jtab(jf), d_X0, d_T, T_stride, d_t_begin,
+                                             d_t_dir, n, nT, k, d_X, d_V, d_flag, d_iters, (cudaStream_t)stream);
+    }
     return launch_trace_minima_model1(d_params, param_stride, to_jtab(jb), d_X0, d_T, T_stride, d_t_begin, d_t_dir, n, nT, k,
                                       d_X, d_V, d_flag, d_iters, (cudaStream_t)stream);
 }

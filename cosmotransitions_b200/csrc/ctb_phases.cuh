@@ -58,6 +58,34 @@ struct Model1XY {
     }
 };
 
+// The general one-field model (CTB_POT_THERMAL1F row: quartic V0, <= 8 bosons with thermal masses, <= 4 fermions;
+// generic_potential.py:240-337) as a one-dimensional Model: the parameter row stays in global memory (L1-resident)
+struct Thermal1FX {
+    static constexpr int ndim = 1;
+    static constexpr int nparam = CTB_NPARAM_THERMAL1F;
+    const double *p;
+    double inv_rs, T2, inv_T2, T4c;
+    int nb, nf;
+    CTB_DEV void load(const double *q)
+    {
+        p = q;
+        inv_rs = 1.0 / q[5];
+        nb = min(max((int)q[7], 0), CTB_THERMAL1F_MAX_BOSONS);
+        nf = min(max((int)q[8], 0), CTB_THERMAL1F_MAX_FERMIONS);
+    }
+    CTB_DEV void set_T(double T)
+    {
+        T2 = T * T;
+        inv_T2 = 1.0 / (T2 + 1e-100);
+        T4c = (T2 * T2) / (2 * CTB_PI * CTB_PI);
+    }
+    CTB_DEV double V(const Tabs &tb, const double *X) const
+    {
+        const PotThermal1F::Parts o = PotThermal1F::eval(p, nb, nf, inv_rs, T2, inv_T2, T4c, tb.jb, tb.jf, X[0]);
+        return o.v0 + o.v1 + o.v1t * T4c;
+    }
+};
+
 #define CTB_TRACE_SUBSTEPS 8
 struct MinKnobs {
     double x_eps;     // finite-difference step (generic_potential.x_eps, 1e-3)

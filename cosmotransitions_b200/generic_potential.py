@@ -78,40 +78,6 @@ class _FiniteDifferences:
         return V - Tb * dVdT
 
 
-    def findMinimum(self, X=None, T=0.0, max_iter=60, xtol=1e-9):
-        """The minimum of Vtot(., T) nearest to `X` (generic_potential.py:477-484, where it is one
-        scipy.optimize.fmin call per point).  Batched: X [..., Ndim] against T [...], every point iterates a damped
-        Newton step X <- X - (H + lam I)^-1 grad V with the device gradV / d2V (lam lifts a non-positive Hessian,
-        steps are capped at a tenth of |X| + 1 and halved while they do not lower V) until all points move by less
-        than xtol (|X| + 1).  Returns an array of the broadcast shape + (Ndim,)."""
-        if X is None:
-            X = self.approxZeroTMin()[0]
-        X = np.array(np.broadcast_to(np.asarray(X, dtype=np.float64),
-                                     np.broadcast_shapes(np.shape(X)[:-1], np.shape(T)) + (self.Ndim,)))
-        T = np.array(np.broadcast_to(np.asarray(T, dtype=np.float64), X.shape[:-1]))
-        eye = np.eye(self.Ndim)
-        V = np.asarray(self._combo(X, T, _lib.V_TOTAL, False, None))
-        for _ in range(max_iter):
-            g, H = np.asarray(self.gradV(X, T)), np.asarray(self.d2V(X, T))
-            lo = np.linalg.eigvalsh(H)[..., 0]
-            lam = np.where(lo > 0, 0.0, 1e-3 * np.abs(lo) - lo + 1e-12)
-            step = -np.linalg.solve(H + lam[..., None, None] * eye, g[..., None])[..., 0]
-            cap = 0.1 * (np.linalg.norm(X, axis=-1) + 1.0)
-            norm = np.linalg.norm(step, axis=-1)
-            step *= np.minimum(1.0, cap / np.maximum(norm, 1e-300))[..., None]
-            for _half in range(30):      # backtrack where the step does not lower V (beyond rounding noise)
-                Vn = np.asarray(self._combo(X + step, T, _lib.V_TOTAL, False, None))
-                worse = Vn > V + 1e-13 * np.abs(V)
-                if not worse.any():
-                    break
-                step = np.where(worse[..., None], 0.5 * step, step)
-            X = X + step
-            V = np.asarray(self._combo(X, T, _lib.V_TOTAL, False, None))
-            if np.all(np.linalg.norm(step, axis=-1) <= xtol * (np.linalg.norm(X, axis=-1) + 1.0)):
-                break
-        return X
-
-
 def _stack(parts, axis):
     if hasattr(parts[0], "is_cuda"):
         import torch
@@ -297,6 +263,20 @@ class one_field_model(_FiniteDifferences):
             return res if X.is_cuda else res.cpu()
         res = res.cpu().numpy()
         return float(res) if res.ndim == 0 else res
+
+    def findMinimum(self, X, T=0.0, max_iter=60, xtol=1e-9):
+        """generic_potential.findMinimum (generic_potential.py:477-484) for any number of points, entirely on the device
+        (ctb_trace_minima with the one-field model: warp-per-point damped Newton on the reference's finite-difference
+        derivatives).  X [..., 1] against T [...]; points whose iteration does not end on a minimum come back as NaN."""
+        from . import phases
+        X = np.asarray(X, dtype=np.float64)
+        shape = np.broadcast_shapes(X.shape[:-1], np.shape(T))
+        Xb = np.ascontiguousarray(np.broadcast_to(X, shape + (1,))).reshape(-1, 1)
+        Tb = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.float64), shape)).reshape(-1)
+        r = phases.find_minimum(np.array(self._row), Xb, Tb, max_iter=max_iter, xtol=xtol, x_eps=self.x_eps, model="thermal1f")
+        out = r["X"].cpu().numpy()
+        out[r["flag"].cpu().numpy() != _lib.MIN_OK] = np.nan
+        return out.reshape(shape + (1,))
 
     def Vtot(self, X, T, include_radiation=True):
         """The total finite temperature effective potential (generic_potential.py:312-337)."""

@@ -19,15 +19,21 @@ def trace_minima(model8, X0, T, t_begin=None, t_dir=None, x_eps=1e-3, xtol=1e-9,
     """Follow the minimum of Vtot(., T) that starts at X0[i] along a temperature grid.
 
     model = None: the built-in model1 (examples/testModel1.py); model8: [8] (one model for all instances) or [n, 8] rows
-    (potentials.model1_model8); X0: [n, 2].  model = a jit.CompiledModel: model8 holds its parameter rows ([nparam] or
-    [n, nparam]) and X0 is [n, model.ndim].
+    (potentials.model1_model8); X0: [n, 2].  model = "thermal1f": the general one-field model, rows of 64
+    (potentials.thermal1f_params; the T entry is ignored), X0 [n, 1].  model = a jit.CompiledModel: model8 holds its
+    parameter rows ([nparam] or [n, nparam]) and X0 is [n, model.ndim].
     T: [nT] shared grid or [n, nT] one row per instance; t_begin / t_dir: optional [n] start index and +1 / -1
     direction of the walk.  Returns device tensors dict(X [n, nT, ndim], V [n, nT], flag [n, nT] (MIN_*), iters [n]).
     An instance's walk stops at the first temperature whose flag is not MIN_OK; that entry holds the point the
     iteration ended on (for MIN_JUMPED: a minimum of the neighbouring phase)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
-    ndim, nparam = (2, 8) if model is None else (model.ndim, max(1, model.nparam))
+    builtin = {None: (_lib.MODEL_MODEL1, 2, 8), "model1": (_lib.MODEL_MODEL1, 2, 8),
+               "thermal1f": (_lib.MODEL_THERMAL1F, 1, _lib.NPARAM[_lib.POT_THERMAL1F])}
+    if model is None or isinstance(model, str):
+        kind_id, ndim, nparam = builtin[model]
+    else:
+        kind_id, ndim, nparam = None, model.ndim, max(1, model.nparam)
     dev = X0.device if isinstance(X0, torch.Tensor) and X0.is_cuda else torch.device("cuda", torch.cuda.current_device())
     X0d = batch._as_device(torch, X0, dev).reshape(-1, ndim).contiguous()
     n = X0d.shape[0]
@@ -51,13 +57,13 @@ def trace_minima(model8, X0, T, t_begin=None, t_dir=None, x_eps=1e-3, xtol=1e-9,
     iters = torch.empty((n,), dtype=torch.int32, device=dev)
     opts = _lib.MinOpts(float(x_eps), float(xtol), float(jump_tol), int(max_iter), 0)
     stride = nparam if (m8.shape[0] == n and n > 1) else 0
-    if model is not None:
+    if kind_id is None:
         model.trace_minima_raw(m8, stride, X0d, Td, T_stride, tb, td, n, nT, opts, X, V, flag, iters, dev)
         return dict(X=X, V=V, flag=flag, iters=iters)
     tabs = _tables.device_tables(dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.ctb_trace_minima(_lib.MODEL_MODEL1, m8.data_ptr(), stride, tabs.jb,
-                                        X0d.data_ptr(), Td.data_ptr(), T_stride, tb.data_ptr() if tb is not None else None,
+        _lib.check(lib.ctb_trace_minima(kind_id, m8.data_ptr(), stride, tabs.jb,
+                                        tabs.jf if kind_id == _lib.MODEL_THERMAL1F else None, X0d.data_ptr(), Td.data_ptr(), T_stride, tb.data_ptr() if tb is not None else None,
                                         td.data_ptr() if td is not None else None, n, nT, opts, X.data_ptr(), V.data_ptr(),
                                         flag.data_ptr(), iters.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
                    "ctb_trace_minima")

@@ -317,10 +317,12 @@ CTB_API int ctb_minimize_1d(int pot_kind, const double *d_params, const ctb_jtab
  * (helper_functions.py:446-554 with eps = x_eps), warm-started by extrapolating the previous two minima.  The walk of
  * an instance ends at the first temperature whose result is not CTB_MIN_OK (that entry holds the point it ended on);
  * entries never visited are NaN / CTB_MIN_NOT_TRACED.  model_kind: CTB_MODEL_MODEL1 (examples/testModel1.py, two
- * fields): d_params rows of 8 = l1, l2, mu2, Y1, Y2, n_boson, renormScaleSq, v2, param_stride doubles apart (0: one
- * row for all instances).  Outputs: d_X [n, nT, ndim], d_V [n, nT] (may be NULL), d_flag [n, nT], d_iters [n] (Newton
+ * fields): d_params rows of 8 = l1, l2, mu2, Y1, Y2, n_boson, renormScaleSq, v2; CTB_MODEL_THERMAL1F (the general
+ * one-field model, one field): rows of CTB_NPARAM_THERMAL1F as for CTB_POT_THERMAL1F (their T entry is ignored; jf
+ * required).  Rows are param_stride doubles apart (0: one row for all instances); jf may be NULL for MODEL1.  Outputs: d_X [n, nT, ndim], d_V [n, nT] (may be NULL), d_flag [n, nT], d_iters [n] (Newton
  * iterations, may be NULL).                                                                                         */
 #define CTB_MODEL_MODEL1 0
+#define CTB_MODEL_THERMAL1F 1
 #define CTB_MIN_OK 0             /* converged on a point with a positive definite Hessian                          */
 #define CTB_MIN_NOT_CONVERGED 1  /* max_iter iterations (or a non-finite potential)                                 */
 #define CTB_MIN_NOT_A_MINIMUM 2  /* converged on a saddle / maximum (Hessian had to be lifted)                      */
@@ -335,9 +337,9 @@ typedef struct ctb_min_opts {
     int32_t reserved;
 } ctb_min_opts;
 CTB_API int ctb_trace_minima(int model_kind, const double *d_params, int64_t param_stride, const ctb_jtable *jb,
-                             const double *d_X0, const double *d_T, int64_t T_stride, const int32_t *d_t_begin,
-                             const int32_t *d_t_dir, int64_t n, int32_t nT, const ctb_min_opts *opts, double *d_X,
-                             double *d_V, int32_t *d_flag, int32_t *d_iters, void *stream);
+                             const ctb_jtable *jf, const double *d_X0, const double *d_T, int64_t T_stride,
+                             const int32_t *d_t_begin, const int32_t *d_t_dir, int64_t n, int32_t nT, const ctb_min_opts *opts,
+                             double *d_X, double *d_V, int32_t *d_flag, int32_t *d_iters, void *stream);
 
 /* ---- host-side gather plumbing of the multi-GPU partition (no collective on the data path) ----
  * Block-cyclic partition: with blocks of B instances, device r of G owns global blocks r, r + G, r + 2G, ...

@@ -1002,6 +1002,18 @@ def test_thermal1f_general_model(ctb, oracle, tables, gold_dir):
     pot = potentials.Thermal1FPotential(g["V0_coefs"], g["renorm"], Ts[1], g["bosons"], g["fermions"])
     inst = t1.SingleFieldInstanton(pa[1], 0.0, pot)
     assert abs(inst.findAction(inst.findProfile()) - S_ref[1]) < S_RTOL * S_ref[1]
+    # generic_potential.findMinimum of the one-field model: one launch of the warp-per-point Newton kernel
+    # (ctb_trace_minima, CTB_MODEL_THERMAL1F) from displaced starts; phases.trace_minima follows the broken minimum in T
+    from cosmotransitions_b200 import generic_potential as gpm, phases
+    m = gpm.one_field_model(g["V0_coefs"], g["renorm"], g["bosons"], g["fermions"])
+    Xm = m.findMinimum(pa[:, None] + 7.0, np.array(Ts))
+    np.testing.assert_allclose(Xm[:, 0], pa, rtol=0, atol=5e-4)       # (the golden phi_abs carry fminbound's 2e-4)
+    assert np.abs(m.gradV(Xm, np.array(Ts))).max() < 1e-3 * np.abs(m.gradV(pa[:, None] + 7.0, np.array(Ts))).max()
+    order = np.argsort(Ts)
+    row = potentials.thermal1f_params(g["V0_coefs"], g["renorm"], 0.0, g["bosons"], g["fermions"])[0]
+    tr = phases.trace_minima(row, np.array([[pa[order[0]]]]), np.array(Ts)[order], model="thermal1f")
+    assert (tr["flag"].cpu().numpy() == _lib.MIN_OK).all()
+    np.testing.assert_allclose(tr["X"].cpu().numpy()[0, :, 0], pa[order], rtol=0, atol=5e-4)
 
 
 def test_one_field_generic_potential_surface(ctb, gold_dir):
