@@ -730,6 +730,12 @@ def test_vtot_unaligned_and_bad_out(ctb):
             m.Vtot_grid(x0, nhat, s, Tg, out=bad)
     good = torch.empty((100, 10), dtype=torch.float64, device="cuda")
     assert m.Vtot_grid(x0, nhat, s, Tg, out=good) is good
+    # host callers: the grid through a page-locked buffer (numpy axes in, numpy view of the buffer out)
+    pinned = torch.empty((100, 10), dtype=torch.float64).pin_memory()
+    h = m.Vtot_grid(x0, nhat, s.cpu().numpy(), Tg.cpu().numpy(), host_out=pinned)
+    assert isinstance(h, np.ndarray) and np.array_equal(h, good.cpu().numpy()) and np.shares_memory(h, pinned.numpy())
+    with pytest.raises(ValueError):
+        m.Vtot_grid(x0, nhat, s.cpu().numpy(), Tg.cpu().numpy(), host_out=torch.empty((10, 100), dtype=torch.float64))
 
 
 def test_model1_finite_difference_surface(ctb, gold_dir):
