@@ -241,8 +241,9 @@ inline int fill_bounce_knobs(BounceArgs &a, const ctb_opts *o, const ctb_bounce_
     a.knobs.npoints = o->npoints; a.knobs.max_interior_pts = o->max_interior_pts;
     a.knobs.alpha_real = o->alpha_real;
     if (o->alpha == 0 && !(o->alpha_real >= 0.0 && o->alpha_real <= 8.0)) return CTB_ERR_UNSUPPORTED;
-    // quartic potential, 64-thread blocks below the throughput regime: finer-grained hand-out of the work-sorted instances (C2: -2 %)
-    L.block = o->block_threads ? o->block_threads : (small_blocks && a.n < 300000 ? 64 : 128);
+    // quartic potential, alpha = 2, 64-thread blocks below the throughput regime: finer-grained hand-out of the work-sorted
+    // instances (C2: -2 %; alpha = 3 shares of 125 000 instances: 128-thread blocks are 2.5 % faster, tools/shard_timing.py)
+    L.block = o->block_threads ? o->block_threads : (small_blocks && a.n < 300000 && o->alpha == 2 ? 64 : 128);
     L.stage_cap = o->npoints + (o->max_interior_pts < 0 ? o->npoints / 2 : o->max_interior_pts);
     L.warp = o->kernel == CTB_KERNEL_WARP;
     if (o->kernel == CTB_KERNEL_AUTO) L.warp = a.n < 4096 && L.stage_cap <= 2048 && o->alpha != 0;
